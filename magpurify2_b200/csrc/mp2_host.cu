@@ -1,0 +1,180 @@
+// Host-buffer entry points: stage H2D/D2H around the device kernels.
+//
+// Pageable user memory is copied through a small ring of pinned buffers (parallel memcpy into the
+// ring, cudaMemcpyAsync out of it) so the PCIe copy of slice k+1 overlaps the kernels of slice k;
+// memory that is already pinned/registered is copied directly.
+#include <omp.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "mp2_common.h"
+
+namespace mp2 {
+
+int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n, int64_t n_bases,
+                     int64_t chunk_begin, int64_t chunk_end, uint32_t *d_counts,
+                     unsigned long long *d_gc_counts, cudaStream_t stream);
+int64_t tnf_num_chunks(const void *d_bases, int64_t n_bases);
+int tnf_finalize(const uint32_t *d_counts, const unsigned long long *d_gc_counts,
+                 const int64_t *d_offsets, int64_t n, float *d_rel, float *d_gc,
+                 cudaStream_t stream);
+
+constexpr size_t SLICE = 16u << 20;  // multiple of the 64 KiB work chunk
+constexpr int NRING = 4;
+
+struct Ring {
+    uint8_t *buf[NRING] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t freed[NRING];
+    bool ready = false;
+    std::mutex mu;
+};
+static Ring g_ring;
+
+static int ring_init() {
+    if (g_ring.ready) return MP2_OK;
+    for (int i = 0; i < NRING; i++) {
+        MP2_CUDA(cudaHostAlloc((void **)&g_ring.buf[i], SLICE, cudaHostAllocPortable));
+        MP2_CUDA(cudaEventCreateWithFlags(&g_ring.freed[i], cudaEventDisableTiming));
+    }
+    g_ring.ready = true;
+    return MP2_OK;
+}
+
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static void par_memcpy(void *dst, const void *src, size_t bytes) {
+    const size_t grain = 1u << 20;
+    if (bytes <= 2 * grain) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const int64_t parts = (int64_t)((bytes + grain - 1) / grain);
+    int nt = std::min<int64_t>(std::min(parts, (int64_t)omp_get_max_threads()), 16);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int64_t i = 0; i < parts; i++) {
+        size_t o = (size_t)i * grain;
+        memcpy((char *)dst + o, (const char *)src + o, std::min(grain, bytes - o));
+    }
+}
+
+// H2D of a whole host array (pinned: one async copy; pageable: through the ring).
+// `after_slice(bytes_done)` is called after each slice has been enqueued on `copy`.
+template <class F>
+static int upload(void *d_dst, const void *h_src, size_t bytes, cudaStream_t copy, F after_slice) {
+    if (bytes == 0) return after_slice((size_t)0);
+    if (is_pinned(h_src)) {
+        for (size_t o = 0; o < bytes; o += SLICE) {
+            size_t len = std::min(SLICE, bytes - o);
+            MP2_CUDA(cudaMemcpyAsync((char *)d_dst + o, (const char *)h_src + o, len,
+                                     cudaMemcpyHostToDevice, copy));
+            MP2_TRY(after_slice(o + len));
+        }
+        return MP2_OK;
+    }
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    MP2_TRY(ring_init());
+    int slot = 0;
+    for (size_t o = 0; o < bytes; o += SLICE, slot = (slot + 1) % NRING) {
+        size_t len = std::min(SLICE, bytes - o);
+        MP2_CUDA(cudaEventSynchronize(g_ring.freed[slot]));  // previous user of the slot is done
+        par_memcpy(g_ring.buf[slot], (const char *)h_src + o, len);
+        MP2_CUDA(cudaMemcpyAsync((char *)d_dst + o, g_ring.buf[slot], len, cudaMemcpyHostToDevice,
+                                 copy));
+        MP2_CUDA(cudaEventRecord(g_ring.freed[slot], copy));
+        MP2_TRY(after_slice(o + len));
+    }
+    return MP2_OK;
+}
+
+static int upload(void *d_dst, const void *h_src, size_t bytes, cudaStream_t copy) {
+    return upload(d_dst, h_src, bytes, copy, [](size_t) { return MP2_OK; });
+}
+
+// D2H into user memory; caller synchronises the stream afterwards.
+static int download(void *h_dst, const void *d_src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return MP2_OK;
+    MP2_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s));
+    return MP2_OK;
+}
+
+struct Streams {
+    cudaStream_t copy = nullptr, comp = nullptr;
+    cudaEvent_t ev = nullptr;
+    int init() {
+        MP2_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+        MP2_CUDA(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
+        MP2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        return MP2_OK;
+    }
+    ~Streams() {
+        if (ev) cudaEventDestroy(ev);
+        if (copy) cudaStreamDestroy(copy);
+        if (comp) cudaStreamDestroy(comp);
+    }
+};
+
+}  // namespace mp2
+
+using namespace mp2;
+
+extern "C" int mp2_tnf(const uint8_t *bases, const int64_t *offsets, int64_t n, int device,
+                       uint32_t *counts, float *rel, float *gc) {
+    if (n < 0) return fail(MP2_EINVAL, "negative n");
+    if (!offsets) return fail(MP2_EINVAL, "offsets is NULL");
+    if (n > INT32_MAX) return fail(MP2_EINVAL, "too many sequences in one call");
+    const int64_t total = offsets[n] - offsets[0];
+    if (offsets[0] != 0) return fail(MP2_EINVAL, "offsets[0] must be 0");
+    for (int64_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(MP2_EINVAL, "offsets must be non-decreasing");
+    if (total > 0 && !bases) return fail(MP2_EINVAL, "bases is NULL");
+    MP2_TRY(require_device(device));
+    if (n == 0) return MP2_OK;
+
+    Streams st;
+    MP2_TRY(st.init());
+    Temp d_bases, d_off, d_counts, d_gcc, d_rel, d_gc;
+    MP2_TRY(d_bases.alloc((size_t)total + 16, st.copy));
+    MP2_TRY(d_off.alloc(sizeof(int64_t) * (n + 1), st.copy));
+    MP2_TRY(d_counts.alloc(sizeof(uint32_t) * MP2_NCANON * n, st.comp));
+    MP2_TRY(d_gcc.alloc(sizeof(unsigned long long) * n, st.comp));
+    if (rel) MP2_TRY(d_rel.alloc(sizeof(float) * MP2_NCANON * n, st.comp));
+    if (gc) MP2_TRY(d_gc.alloc(sizeof(float) * n, st.comp));
+    MP2_CUDA(cudaMemsetAsync(d_counts.p, 0, sizeof(uint32_t) * MP2_NCANON * n, st.comp));
+    MP2_CUDA(cudaMemsetAsync(d_gcc.p, 0, sizeof(unsigned long long) * n, st.comp));
+
+    MP2_TRY(upload(d_off.p, offsets, sizeof(int64_t) * (n + 1), st.copy));
+    const int64_t n_chunks = tnf_num_chunks(d_bases.p, total);
+    int64_t next_chunk = 0;
+    auto after = [&](size_t done) -> int {
+        // chunks whose bytes have all been enqueued for copy can run behind that copy
+        int64_t upto = ((int64_t)done == total) ? n_chunks : (int64_t)(done / 65536);
+        if (upto > next_chunk) {
+            MP2_CUDA(cudaEventRecord(st.ev, st.copy));
+            MP2_CUDA(cudaStreamWaitEvent(st.comp, st.ev, 0));
+            MP2_TRY(tnf_launch_range(d_bases.as<uint8_t>(), d_off.as<int64_t>(), n, total,
+                                     next_chunk, upto, d_counts.as<uint32_t>(),
+                                     d_gcc.as<unsigned long long>(), st.comp));
+            next_chunk = upto;
+        }
+        return MP2_OK;
+    };
+    MP2_TRY(upload(d_bases.p, bases, (size_t)total, st.copy, after));
+    MP2_TRY(tnf_finalize(d_counts.as<uint32_t>(), d_gcc.as<unsigned long long>(),
+                         d_off.as<int64_t>(), n, d_rel.as<float>(), d_gc.as<float>(), st.comp));
+    if (counts) MP2_TRY(download(counts, d_counts.p, sizeof(uint32_t) * MP2_NCANON * n, st.comp));
+    if (rel) MP2_TRY(download(rel, d_rel.p, sizeof(float) * MP2_NCANON * n, st.comp));
+    if (gc) MP2_TRY(download(gc, d_gc.p, sizeof(float) * n, st.comp));
+    MP2_CUDA(cudaStreamSynchronize(st.comp));
+    MP2_CUDA(cudaStreamSynchronize(st.copy));
+    return MP2_OK;
+}

@@ -1,0 +1,202 @@
+"""Deterministic synthetic MAGs and alignments.
+
+Used by tests/ (small, NumPy on the host) and bench.py (large, generated on the device with torch
+used purely as RNG + buffer plumbing).  Nothing here is on the product path.
+
+MAG model: total length ~N(3.0 Mbp, 0.3 Mbp); ~300 contigs with log-normal lengths (sigma 1.0)
+rescaled to the total, floor 1500 bp, plus 1 % deliberately tiny contigs (0..200 bp, which covers
+the < 4 bp and <= 150 bp edge rules); per-MAG GC ~U(0.30, 0.70); 5 % "contaminant" contigs at
+GC +- 0.12; N runs (Poisson, 1 per 100 kbp, length U(1,100)); 2 % lower-case stretches; one
+IUPAC byte per Mbp.  `long_contigs=True` gives the C5 stress shape (5-10 Mbp, 3..20 contigs, the
+largest >= 50 % of the MAG).
+"""
+import numpy as np
+
+SEED_SEQ = 0x4D414732
+SEED_COV = 0x434F5631
+READ_LEN = 150
+
+
+def mag_layout(n_mags, seed=0, long_contigs=False, mean_bp=3.0e6, n_contigs=300):
+    """Contig lengths for n_mags MAGs.
+
+    Returns (contig_len int64[n], mag_off int64[n_mags+1], gc float64[n] per-contig GC target)."""
+    lens, gcs, mag_off = [], [], [0]
+    for m in range(n_mags):
+        rng = np.random.Generator(np.random.Philox(key=(SEED_SEQ ^ m) + (seed << 32)))
+        if long_contigs:
+            total = rng.uniform(5e6, 10e6)
+            k = int(rng.integers(3, 21))
+            w = rng.lognormal(0.0, 1.0, k)
+            w[0] = w[1:].sum() * rng.uniform(1.0, 3.0)  # largest contig >= 50 %
+            ln = np.maximum(1500, (w / w.sum() * total)).astype(np.int64)
+        else:
+            total = max(2e5, rng.normal(mean_bp, mean_bp * 0.1))
+            k = max(3, int(rng.normal(n_contigs, n_contigs * 0.1)))
+            w = rng.lognormal(0.0, 1.0, k)
+            ln = np.maximum(1500, (w / w.sum() * total)).astype(np.int64)
+            tiny = rng.random(k) < 0.01
+            ln[tiny] = rng.integers(0, 201, int(tiny.sum()))
+        gc0 = rng.uniform(0.30, 0.70)
+        g = np.full(len(ln), gc0)
+        cont = rng.random(len(ln)) < 0.05
+        g[cont] = np.clip(gc0 + rng.choice([-0.12, 0.12], int(cont.sum())), 0.05, 0.95)
+        lens.append(ln)
+        gcs.append(g)
+        mag_off.append(mag_off[-1] + len(ln))
+    return (np.concatenate(lens) if lens else np.zeros(0, np.int64),
+            np.asarray(mag_off, dtype=np.int64),
+            np.concatenate(gcs) if gcs else np.zeros(0))
+
+
+def _decorate(bases, offsets, rng):
+    """N runs, lower-case stretches and IUPAC bytes, in place (host arrays)."""
+    L = len(bases)
+    if L == 0:
+        return
+    for _ in range(int(rng.poisson(L / 1e5))):
+        p = int(rng.integers(0, L))
+        bases[p:p + int(rng.integers(1, 101))] = ord("N")
+    n_low = int(rng.poisson(L * 0.02 / 500)) + 1
+    for _ in range(n_low):
+        p = int(rng.integers(0, L))
+        bases[p:p + 500] |= 0x20
+    for _ in range(int(rng.poisson(L / 1e6)) + 1):
+        bases[int(rng.integers(0, L))] = ord("RYKMSW"[int(rng.integers(0, 6))])
+
+
+def make_mags(n_mags, seed=0, long_contigs=False, mean_bp=3.0e6, n_contigs=300, decorate=True):
+    """Host (NumPy) generator.  Returns dict(bases u8[L], offsets i64[n+1], mag_off, lengths)."""
+    clen, mag_off, gc = mag_layout(n_mags, seed, long_contigs, mean_bp, n_contigs)
+    offsets = np.zeros(len(clen) + 1, dtype=np.int64)
+    np.cumsum(clen, out=offsets[1:])
+    L = int(offsets[-1])
+    rng = np.random.Generator(np.random.Philox(key=SEED_SEQ + 7919 * (seed + 1)))
+    u = rng.random(L, dtype=np.float32)
+    v = rng.random(L, dtype=np.float32) < 0.5
+    gc_base = np.repeat(gc.astype(np.float32), clen)
+    is_gc = u < gc_base
+    bases = np.where(is_gc, np.where(v, ord("G"), ord("C")), np.where(v, ord("A"), ord("T"))).astype(np.uint8)
+    if decorate:
+        _decorate(bases, offsets, rng)
+    return dict(bases=bases, offsets=offsets, mag_off=mag_off, lengths=clen)
+
+
+def make_mags_device(n_mags, device, seed=0, long_contigs=False, mean_bp=3.0e6, n_contigs=300,
+                     mags_per_block=64):
+    """Same model, bases generated on `device` with torch (bench sizes: 3 Gbp would take minutes
+    on the host).  Returns dict(bases torch.uint8[L] on device, offsets/mag_off/lengths NumPy)."""
+    import torch
+
+    clen, mag_off, gc = mag_layout(n_mags, seed, long_contigs, mean_bp, n_contigs)
+    offsets = np.zeros(len(clen) + 1, dtype=np.int64)
+    np.cumsum(clen, out=offsets[1:])
+    L = int(offsets[-1])
+    bases = torch.empty(L + 64, dtype=torch.uint8, device=device)[:L]
+    gen = torch.Generator(device=device)
+    gen.manual_seed(SEED_SEQ + 7919 * (seed + 1))
+    lut = torch.tensor([ord("A"), ord("T"), ord("C"), ord("G")], dtype=torch.uint8, device=device)
+    for m0 in range(0, n_mags, mags_per_block):
+        m1 = min(n_mags, m0 + mags_per_block)
+        c0, c1 = int(mag_off[m0]), int(mag_off[m1])
+        b0, b1 = int(offsets[c0]), int(offsets[c1])
+        if b1 == b0:
+            continue
+        gcb = torch.repeat_interleave(
+            torch.from_numpy(gc[c0:c1].astype(np.float32)).to(device),
+            torch.from_numpy(clen[c0:c1]).to(device), output_size=b1 - b0)
+        u = torch.rand(b1 - b0, device=device, generator=gen)
+        v = torch.rand(b1 - b0, device=device, generator=gen) < 0.5
+        idx = (u < gcb).to(torch.int64) * 2 + v.to(torch.int64)
+        bases[b0:b1] = lut[idx]
+        del gcb, u, v, idx
+    # decorations: N runs / lower case / IUPAC at host-chosen positions (few thousand tiny writes)
+    rng = np.random.Generator(np.random.Philox(key=SEED_SEQ + 104729 * (seed + 1)))
+    n_runs = int(rng.poisson(L / 1e5))
+    if n_runs:
+        p = torch.from_numpy(rng.integers(0, L, n_runs)).to(device)
+        ln = torch.from_numpy(rng.integers(1, 101, n_runs)).to(device)
+        for k in range(100):
+            q = p + k
+            ok = (ln > k) & (q < L)
+            bases[q[ok]] = ord("N")
+    n_low = int(rng.poisson(L * 0.02 / 500)) + 1
+    p = torch.from_numpy(rng.integers(0, max(1, L - 512), n_low)).to(device)
+    idx = (p[:, None] + torch.arange(500, device=device)[None, :]).reshape(-1)
+    bases[idx] = bases[idx] | 0x20
+    n_iu = int(rng.poisson(L / 1e6)) + 1
+    p = torch.from_numpy(rng.integers(0, L, n_iu)).to(device)
+    bases[p] = torch.from_numpy(np.frombuffer(b"RYKMSW", dtype=np.uint8)[rng.integers(0, 6, n_iu)].copy()).to(device)
+    return dict(bases=bases, offsets=offsets, mag_off=mag_off, lengths=clen)
+
+
+# ---- alignments --------------------------------------------------------------------------
+
+def abundances(n_mags, n_samples, seed=0):
+    """a[m, s] ~ LogNormal(ln 20, 1.0); 10 % of (MAG, sample) pairs at 0.2x."""
+    rng = np.random.Generator(np.random.Philox(key=SEED_COV + 31 * (seed + 1)))
+    a = rng.lognormal(np.log(20.0), 1.0, (n_mags, n_samples))
+    a[rng.random((n_mags, n_samples)) < 0.10] *= 0.2 / 20.0
+    return a
+
+
+def make_events(lengths, mag_off, sample, seed=0, read_len=READ_LEN, variable=False, depth_scale=1.0):
+    """Host generator of one sample's alignment blocks, grouped by contig and sorted by start
+    inside a contig (BAM order).  Returns (starts u32, ends u32, ev_off i64[n+1])."""
+    n_mags = len(mag_off) - 1
+    ab = abundances(n_mags, sample + 1, seed)[:, sample] * depth_scale
+    rng = np.random.Generator(np.random.Philox(key=(SEED_COV ^ (sample << 20)) + (seed << 40)))
+    per_contig = np.repeat(ab, np.diff(mag_off))
+    cont = rng.random(len(lengths)) < 0.05
+    per_contig[cont] = rng.lognormal(np.log(20.0), 1.0, int(cont.sum())) * depth_scale
+    lam = per_contig * np.maximum(lengths - read_len + 1, 0) / read_len
+    n_reads = rng.poisson(lam).astype(np.int64)
+    n_reads[lengths < read_len] = 0
+    ev_off = np.zeros(len(lengths) + 1, dtype=np.int64)
+    np.cumsum(n_reads, out=ev_off[1:])
+    R = int(ev_off[-1])
+    cid = np.repeat(np.arange(len(lengths), dtype=np.int64), n_reads)
+    span = (lengths - read_len + 1)[cid]
+    st = np.floor(rng.random(R) * span).astype(np.int64)
+    if variable:
+        rl = np.clip(np.rint(rng.normal(read_len, 15, R)), 50, 250).astype(np.int64)
+    else:
+        rl = np.full(R, read_len, dtype=np.int64)
+    order = np.lexsort((st, cid))
+    st, rl = st[order], rl[order]
+    en = np.minimum(st + rl, lengths[cid])  # a BAM never aligns past the contig end
+    return st.astype(np.uint32), en.astype(np.uint32), ev_off
+
+
+def make_events_device(lengths, mag_off, sample, device, seed=0, read_len=READ_LEN, depth_scale=1.0):
+    """Device generator (bench sizes).  Same model, torch RNG; returns torch tensors
+    (starts u32-as-int32 storage, ends, ev_off int64) on `device`."""
+    import torch
+
+    n_mags = len(mag_off) - 1
+    ab = abundances(n_mags, sample + 1, seed)[:, sample] * depth_scale
+    rng = np.random.Generator(np.random.Philox(key=(SEED_COV ^ (sample << 20)) + (seed << 40)))
+    per_contig = np.repeat(ab, np.diff(mag_off))
+    cont = rng.random(len(lengths)) < 0.05
+    per_contig[cont] = rng.lognormal(np.log(20.0), 1.0, int(cont.sum())) * depth_scale
+    lam = per_contig * np.maximum(lengths - read_len + 1, 0) / read_len
+    n_reads = rng.poisson(lam).astype(np.int64)
+    n_reads[lengths < read_len] = 0
+    ev_off = np.zeros(len(lengths) + 1, dtype=np.int64)
+    np.cumsum(n_reads, out=ev_off[1:])
+    R = int(ev_off[-1])
+    gen = torch.Generator(device=device)
+    gen.manual_seed((SEED_COV ^ (sample << 20)) + seed)
+    d_n = torch.from_numpy(n_reads).to(device)
+    cid = torch.repeat_interleave(torch.arange(len(lengths), device=device, dtype=torch.int64), d_n,
+                                  output_size=R)
+    span = torch.from_numpy(lengths - read_len + 1).to(device)[cid]
+    st = torch.floor(torch.rand(R, device=device, generator=gen, dtype=torch.float64) * span).to(torch.int64)
+    key = (cid << 32) | st
+    del cid, span
+    key, _ = torch.sort(key)
+    st = (key & 0xFFFFFFFF)
+    del key
+    starts = st.to(torch.int32)  # bit pattern == uint32 (contigs are < 2^31)
+    ends = (st + read_len).to(torch.int32)
+    return starts, ends, torch.from_numpy(ev_off).to(device), R

@@ -1,0 +1,134 @@
+"""GPU parity: composition path (get_tnf / get_gc) through the C ABI vs the CPU oracle.
+
+Counts are compared bit-exactly; relative frequencies and GC are single IEEE f32 divisions of
+exact integers, so they are compared bit-exactly as well (tolerance in north_star: 1e-6 rel)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _same_f32(a, b):
+    return np.array_equal(a.view(np.uint32), b.view(np.uint32)) or np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.fixture(scope="module")
+def comp():
+    from magpurify2_b200 import _composition
+
+    return _composition
+
+
+def test_kats(comp, oracle, golden_dir):
+    kats = json.load(open(os.path.join(golden_dir, "kats.json")))
+    seqs = [k[0] for k in kats["tnf_gc"]]
+    counts = comp.get_tnf(seqs, relative=False)
+    assert counts.dtype == np.uint32 and counts.shape == (len(seqs), 136)
+    assert np.array_equal(counts, oracle.get_tnf(seqs, relative=False))
+    for row, k in zip(counts, kats["tnf_gc"]):
+        assert row.sum() == k[1]
+    rel = comp.get_tnf(seqs)
+    assert rel.dtype == np.float32
+    assert _same_f32(rel, oracle.get_tnf(seqs, relative=True))
+    gc = comp.get_gc(seqs)
+    assert gc.dtype == np.float32 and _same_f32(gc, oracle.get_gc(seqs))
+    assert np.isnan(gc[seqs.index("")])
+
+
+def test_signature_matches_reference(comp):
+    # positional and keyword use (PyO3 #[pyfunction(relative=true, threads=1)], composition.rs:94)
+    a = comp.get_tnf(["ACGTTGCA"], True, 4)
+    b = comp.get_tnf(seq_list=["ACGTTGCA"], relative=True, threads=1)
+    assert np.array_equal(a, b)
+    assert comp.get_tnf([]).shape == (0, 136)
+    assert comp.get_gc([]).shape == (0,)
+    with pytest.raises(TypeError):
+        comp.get_tnf("ACGT")
+    with pytest.raises(TypeError):
+        comp.get_tnf([1, 2])
+
+
+def test_ragged_random(comp, oracle):
+    rng = np.random.default_rng(11)
+    alphabet = np.frombuffer(b"ACGTacgtNRYKMSWnU-*", dtype=np.uint8)
+    p = np.array([20, 20, 20, 20, 3, 3, 3, 3, 2, .5, .5, .5, .5, .5, .5, 1, .5, .5, .5])
+    lens = [0, 1, 2, 3, 4, 5, 15, 16, 17, 31, 32, 33, 63, 64, 65, 1023, 1024, 1025, 4096, 65535,
+            65536, 65537, 70000, 0, 0, 3, 200000, 7, 131072, 1] + rng.integers(0, 3000, 300).tolist()
+    seqs = [bytes(rng.choice(alphabet, n, p=p / p.sum())).decode() for n in lens]
+    assert np.array_equal(comp.get_tnf(seqs, relative=False), oracle.get_tnf(seqs, relative=False, threads=4))
+    assert _same_f32(comp.get_tnf(seqs), oracle.get_tnf(seqs, threads=4))
+    assert _same_f32(comp.get_gc(seqs), oracle.get_gc(seqs))
+
+
+def test_all_boundaries_mod_16(comp, oracle):
+    """Every contig start alignment (mod 16) x N positions around the 16-byte groups."""
+    rng = np.random.default_rng(12)
+    seqs = []
+    for pad in range(0, 40):
+        seqs.append("ACGT"[pad % 4] * pad)
+        s = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 2100).copy()
+        s[rng.integers(0, 2100, 3)] = ord("N")
+        seqs.append(bytes(s).decode())
+    assert np.array_equal(comp.get_tnf(seqs, relative=False), oracle.get_tnf(seqs, relative=False))
+    assert _same_f32(comp.get_gc(seqs), oracle.get_gc(seqs))
+
+
+def test_revcomp_invariance_and_sum(comp):
+    rng = np.random.default_rng(13)
+    s = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 300001)).decode()
+    rc = s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    a, b = comp.get_tnf([s, rc], relative=False)
+    assert np.array_equal(a, b) and a.sum() == len(s) - 3
+
+
+def test_synthetic_mags_c1(comp, oracle):
+    """BASELINE config 1 shape: 10 MAGs x ~3 Mbp x ~300 contigs, full parity."""
+    from magpurify2_b200 import synth
+
+    d = synth.make_mags(10, seed=1)
+    counts, rel, gc = comp.tnf_from_concat(d["bases"], d["offsets"], relative=True, want_gc=True,
+                                           want_counts=True)
+    want = oracle.get_tnf_concat(d["bases"], d["offsets"], relative=False, threads=8)
+    assert np.array_equal(counts, want)
+    assert _same_f32(rel, oracle.get_tnf_concat(d["bases"], d["offsets"], relative=True, threads=8))
+    assert _same_f32(gc, oracle.get_gc_concat(d["bases"], d["offsets"]))
+
+
+def test_long_contig_c5(comp, oracle):
+    """BASELINE config 5 shape: few very large contigs (work per CTA independent of contig size)."""
+    from magpurify2_b200 import synth
+
+    d = synth.make_mags(2, seed=2, long_contigs=True)
+    counts, _rel, gc = comp.tnf_from_concat(d["bases"], d["offsets"], relative=False, want_gc=True)
+    assert np.array_equal(counts, oracle.get_tnf_concat(d["bases"], d["offsets"], relative=False, threads=8))
+    assert _same_f32(gc, oracle.get_gc_concat(d["bases"], d["offsets"]))
+
+
+def test_device_pointer_entry(comp, oracle):
+    """mp2_tnf_device on torch buffers (tensors are buffers only), unaligned base pointer too."""
+    import torch
+
+    from magpurify2_b200 import _lib, synth
+
+    d = synth.make_mags(2, seed=3, mean_bp=4e5, n_contigs=60)
+    n = len(d["offsets"]) - 1
+    want = oracle.get_tnf_concat(d["bases"], d["offsets"], relative=False, threads=4)
+    want_gc = oracle.get_gc_concat(d["bases"], d["offsets"])
+    lib = _lib.load()
+    for shift in (0, 1, 5, 15):
+        buf = torch.zeros(len(d["bases"]) + 64, dtype=torch.uint8, device="cuda")
+        view = buf[shift:shift + len(d["bases"])]
+        view.copy_(torch.from_numpy(d["bases"]))
+        off = torch.from_numpy(d["offsets"]).cuda()
+        counts = torch.full((n, 136), 7, dtype=torch.int32, device="cuda")
+        rel = torch.empty((n, 136), dtype=torch.float32, device="cuda")
+        gc = torch.empty(n, dtype=torch.float32, device="cuda")
+        _lib.check(lib.mp2_tnf_device(view.data_ptr(), off.data_ptr(), n, len(d["bases"]),
+                                      counts.data_ptr(), rel.data_ptr(), gc.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert np.array_equal(counts.cpu().numpy().view(np.uint32), want), shift
+        assert _same_f32(gc.cpu().numpy(), want_gc)
