@@ -12,16 +12,24 @@
 // codes the lanes hit.  The flush folds the 32 lane columns with warp reductions, folds
 // 256 codes -> 136 canonical classes and adds the non-zero classes to the contig's row with
 // integer global atomics (order independent => bit exact).
+#include <cstdlib>
+
 #include "mp2_common.h"
 
 namespace mp2 {
 
-constexpr int TNF_THREADS = 256;
-constexpr int TNF_CHUNK = 65536;     // bytes of the stream owned by one work item
-constexpr int TNF_SMALL_SEG = 1024;  // segments shorter than this go straight to global atomics
+constexpr int TNF_WARPS = 8;
+constexpr int TNF_THREADS = TNF_WARPS * 32;
+constexpr int TNF_PIECE = 16384;  // bytes of the stream owned by one work item (one warp)
+constexpr int TNF_UNROLL = 4;     // 16-byte groups in flight per lane
 
-__constant__ uint8_t c_lut256[256];         // code -> canonical class
-__constant__ uint8_t c_canon_code[MP2_NCANON];  // class -> smallest code
+// Table words per warp: MODE 4 counts one 4-mer per base into T4[256]; MODE 5 counts one 5-mer
+// per TWO bases into T5[1024] (a 5-mer b0..b4 stands for the 4-mers b0..b3 and b1..b4) and
+// keeps T4[256] for the odd ones out (segment edges, groups holding non-ACGT bytes).
+template <int MODE> struct TnfTab { static constexpr int WORDS = MODE == 5 ? 1280 : 256; };
+
+__constant__ uint8_t c_lut256[256];             // code -> canonical class
+__constant__ uint16_t c_canon_pair[MP2_NCANON];  // class -> smallest code | revcomp code << 8
 
 static int upload_tables() {
     static bool done[64] = {false};
@@ -29,7 +37,14 @@ static int upload_tables() {
     MP2_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && done[dev]) return MP2_OK;
     MP2_CUDA(cudaMemcpyToSymbol(c_lut256, host_lut256(), 256));
-    MP2_CUDA(cudaMemcpyToSymbol(c_canon_code, host_canon_code136(), MP2_NCANON));
+    uint16_t pair[MP2_NCANON];
+    const uint8_t *cc = host_canon_code136();
+    for (int k = 0; k < MP2_NCANON; k++) {
+        unsigned a = cc[k], t = a, rc = 0;
+        for (int i = 0; i < 4; i++) { rc = (rc << 2) | (3u - (t & 3u)); t >>= 2; }
+        pair[k] = (uint16_t)(a | (rc << 8));
+    }
+    MP2_CUDA(cudaMemcpyToSymbol(c_canon_pair, pair, sizeof pair));
     if (dev < 64) done[dev] = true;
     return MP2_OK;
 }
@@ -58,13 +73,17 @@ __device__ __forceinline__ uint32_t code1(uint32_t b) {
     return 4;
 }
 
-// ---- chunk -> first contig map -----------------------------------------------------------
+__device__ __forceinline__ void smem_inc(uint32_t saddr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory");
+}
+
+// ---- piece -> first contig map -----------------------------------------------------------
 __global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_t n, int mis,
                                      int64_t chunk_begin, int64_t n_chunks,
                                      int32_t *__restrict__ first_contig) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n_chunks) return;
-    int64_t pos = (chunk_begin + k) * TNF_CHUNK - mis;  // stream position of the chunk start
+    int64_t pos = (chunk_begin + k) * TNF_PIECE - mis;  // stream position of the piece start
     // largest c in [0, n-1] with offsets[c] <= pos (0 if none)
     int64_t lo = 0, hi = n;  // search upper_bound over offsets[0..n)
     while (lo < hi) {
@@ -76,144 +95,144 @@ __global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_
 }
 
 // ---- main kernel -------------------------------------------------------------------------
-__global__ void __launch_bounds__(TNF_THREADS, 4)
+// Every warp works alone: it draws a piece of the stream from a global counter, walks the
+// segments (piece ∩ contig) in it, counts each segment into its own 1 KB (MODE 4) / 5 KB
+// (MODE 5) shared-memory table with red.shared (same-address lanes are merged by the hardware,
+// measured 13.4 increments/clk/SM on B200 for a 256-word table) and flushes the table to the
+// contig's row of `counts` with integer global reductions (order independent => bit exact).
+// No block-level synchronisation anywhere.
+template <int MODE>
+__global__ void __launch_bounds__(TNF_THREADS)
 tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
            const int64_t *__restrict__ offsets, int64_t n,
            const int32_t *__restrict__ first_contig, int64_t chunk_begin, int64_t n_chunks,
            uint32_t *__restrict__ counts, unsigned long long *__restrict__ gc_counts,
            int *__restrict__ work_counter) {
-    __shared__ uint32_t hist[256 * 32];  // [code][lane]
-    __shared__ uint32_t red[256];
-    __shared__ unsigned long long s_gc[2];
-    __shared__ int s_chunk;
+    constexpr int WORDS = TnfTab<MODE>::WORDS;
+    __shared__ __align__(1024) uint32_t s_tab[TNF_WARPS * WORDS];
 
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    uint32_t *hist_lane = hist + lane;
-    char *hist_bytes = reinterpret_cast<char *>(hist);
-    const uint32_t lane4 = lane * 4;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t *tab = s_tab + warp * WORDS;
+    const uint32_t t5 = (uint32_t)__cvta_generic_to_shared(tab);  // T5 (MODE 5) or T4 (MODE 4)
+    const uint32_t t4 = MODE == 5 ? t5 + 4096u : t5;
 
-    for (int i = tid; i < 256 * 32; i += TNF_THREADS) hist[i] = 0;
-    if (tid < 2) s_gc[tid] = 0;
-    int par = 0;
-    __syncthreads();
+    for (int i = lane; i < WORDS; i += 32) tab[i] = 0;
+    __syncwarp();
 
     for (;;) {
-        if (tid == 0) s_chunk = atomicAdd(work_counter, 1);
-        __syncthreads();
-        const int64_t kc = s_chunk;
-        __syncthreads();
+        int64_t kc = 0;
+        if (lane == 0) kc = atomicAdd(work_counter, 1);
+        kc = __shfl_sync(0xffffffffu, kc, 0);
         if (kc >= n_chunks) break;
-        const int64_t chunk_lo_raw = (chunk_begin + kc) * TNF_CHUNK;
-        const int64_t chunk_lo = chunk_lo_raw < mis ? mis : chunk_lo_raw;
-        int64_t chunk_hi = chunk_lo_raw + TNF_CHUNK;
-        if (chunk_hi > end_q) chunk_hi = end_q;
+        const int64_t piece_lo_raw = (chunk_begin + kc) * TNF_PIECE;
+        const int64_t piece_lo = piece_lo_raw < mis ? mis : piece_lo_raw;
+        int64_t piece_hi = piece_lo_raw + TNF_PIECE;
+        if (piece_hi > end_q) piece_hi = end_q;
 
         for (int64_t c = first_contig[kc]; c < n; c++) {
             const int64_t o0 = offsets[c] + mis;
-            if (o0 >= chunk_hi) break;
+            if (o0 >= piece_hi) break;
             const int64_t o1 = offsets[c + 1] + mis;
-            const int64_t seg_lo = o0 > chunk_lo ? o0 : chunk_lo;
-            const int64_t seg_hi = o1 < chunk_hi ? o1 : chunk_hi;
+            const int64_t seg_lo = o0 > piece_lo ? o0 : piece_lo;
+            const int64_t seg_hi = o1 < piece_hi ? o1 : piece_hi;
             if (seg_hi <= seg_lo) continue;
 
-            if (seg_hi - seg_lo < TNF_SMALL_SEG) {
-                // ---- tiny segment: no shared histogram, straight to the contig's row ----
-                uint32_t gcl = 0;
-                for (int64_t q = seg_lo + tid; q < seg_hi; q += TNF_THREADS) {
-                    uint32_t c3 = code1(bases_al[q]);
-                    gcl += (c3 == 1 || c3 == 2);
-                    if (q - 3 >= o0 && c3 < 4) {
-                        uint32_t c0 = code1(bases_al[q - 3]);
-                        uint32_t c1 = code1(bases_al[q - 2]);
-                        uint32_t c2 = code1(bases_al[q - 1]);
-                        if ((c0 | c1 | c2) < 4) {
-                            uint32_t code = (c0 << 6) | (c1 << 4) | (c2 << 2) | c3;
-                            atomicAdd(&counts[c * MP2_NCANON + c_lut256[code]], 1u);
-                        }
-                    }
-                }
-                gcl = __reduce_add_sync(0xffffffffu, gcl);
-                if (lane == 0 && gcl) atomicAdd(&gc_counts[c], (unsigned long long)gcl);
-                continue;
-            }
-
-            // ---- regular segment: shared-memory histogram ----
             uint32_t gcl = 0;
-            const int64_t g_first = seg_lo >> 4, g_last = (seg_hi - 1) >> 4;
-            for (int64_t g = g_first + tid; g <= g_last; g += TNF_THREADS) {
-                const int64_t P = g << 4;
-                bool fast = (P - 3 >= o0) && (P >= seg_lo) && (P + 16 <= seg_hi);
-                uint32_t cw = 0, prev = 0;
-                if (fast) {
-                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(bases_al + P));
-                    const uint32_t h = __ldg(reinterpret_cast<const uint32_t *>(bases_al + P - 4));
-                    uint32_t d0, d1, d2, d3, dh;
-                    uint32_t p0 = decode4(v.x, d0), p1 = decode4(v.y, d1);
-                    uint32_t p2 = decode4(v.z, d2), p3 = decode4(v.w, d3);
-                    prev = decode4(h, dh);
-                    cw = (p0 << 24) | (p1 << 16) | (p2 << 8) | p3;
-                    fast = ((d0 | d1 | d2 | d3 | (dh & 0xFFFFFF00u)) == 0);
-                }
-                if (fast) {
-                    gcl += __popc((cw ^ (cw >> 1)) & 0x55555555u);
-                    // k-mer ending at base j = bits [2(15-j)+7 : 2(15-j)] of (prev:cw); its
-                    // counter sits at byte offset code*128 + lane*4, so shift straight to bit 7
+            const int64_t g_last = (seg_hi - 1) >> 4;
+            for (int64_t g0 = (seg_lo >> 4) + lane; g0 <= g_last; g0 += 32 * TNF_UNROLL) {
+                uint4 v[TNF_UNROLL];
+                uint32_t h[TNF_UNROLL];
+                bool fast[TNF_UNROLL];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int sh = 2 * (15 - j);
-                        const uint32_t t = sh >= 7 ? __funnelshift_r(cw, prev, sh - 7)
-                                                   : (cw << (7 - sh));
-                        atomicAdd(reinterpret_cast<uint32_t *>(hist_bytes + ((t & 0x7F80u) | lane4)),
-                                  1u);
+                for (int u = 0; u < TNF_UNROLL; u++) {
+                    const int64_t P = (g0 + 32 * u) << 4;
+                    fast[u] = (P - 3 >= o0) && (P >= seg_lo) && (P + 16 <= seg_hi);
+                    if (fast[u]) {
+                        v[u] = __ldg(reinterpret_cast<const uint4 *>(bases_al + P));
+                        h[u] = __ldg(reinterpret_cast<const uint32_t *>(bases_al + P - 4));
                     }
-                } else {
-                    // boundary group or a group holding non-ACGT bytes: rolling scalar walk
-                    uint32_t kmer = 0, run = 0;
-                    for (int i = -3; i < 16; i++) {
-                        const int64_t q = P + i;
-                        if (q >= seg_hi) break;
-                        if (q < o0) { run = 0; continue; }
-                        const uint32_t cd = code1(bases_al[q]);
-                        if (cd > 3) run = 0;
-                        else { kmer = ((kmer << 2) | cd) & 0xFFu; run++; }
-                        if (i >= 0 && q >= seg_lo) {
-                            gcl += (cd == 1 || cd == 2);
-                            if (run >= 4) atomicAdd(hist_lane + (kmer << 5), 1u);
+                }
+#pragma unroll
+                for (int u = 0; u < TNF_UNROLL; u++) {
+                    const int64_t P = (g0 + 32 * u) << 4;
+                    if (g0 + 32 * u > g_last) break;
+                    uint32_t cw = 0, prev = 0;
+                    bool ok = fast[u];
+                    if (ok) {
+                        uint32_t d0, d1, d2, d3, dh;
+                        const uint32_t p0 = decode4(v[u].x, d0), p1 = decode4(v[u].y, d1);
+                        const uint32_t p2 = decode4(v[u].z, d2), p3 = decode4(v[u].w, d3);
+                        prev = decode4(h[u], dh);
+                        cw = (p0 << 24) | (p1 << 16) | (p2 << 8) | p3;
+                        ok = ((d0 | d1 | d2 | d3 | (dh & 0xFFFFFF00u)) == 0);
+                    }
+                    if (ok) {
+                        gcl += __popc((cw ^ (cw >> 1)) & 0x55555555u);
+                        if (MODE == 5) {
+                            // 5-mer ending at base j+1 (j even) = bits [2(14-j)+9 : 2(14-j)] of
+                            // prev:cw; its counter is word index*4 bytes into T5
+#pragma unroll
+                            for (int j = 0; j < 16; j += 2) {
+                                const int sh = 2 * (14 - j);
+                                const uint32_t t = sh >= 2 ? __funnelshift_r(cw, prev, sh - 2) : (cw << 2);
+                                smem_inc(t5 + (t & 0xFFCu));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                const int sh = 2 * (15 - j);
+                                const uint32_t t = sh >= 2 ? __funnelshift_r(cw, prev, sh - 2) : (cw << 2);
+                                smem_inc(t4 + (t & 0x3FCu));
+                            }
+                        }
+                    } else {
+                        // boundary group or a group holding non-ACGT bytes: rolling scalar walk
+                        uint32_t kmer = 0, run = 0;
+                        for (int i = -3; i < 16; i++) {
+                            const int64_t q = P + i;
+                            if (q >= seg_hi) break;
+                            if (q < o0) { run = 0; continue; }
+                            const uint32_t cd = code1(bases_al[q]);
+                            if (cd > 3) run = 0;
+                            else { kmer = ((kmer << 2) | cd) & 0xFFu; run++; }
+                            if (i >= 0 && q >= seg_lo) {
+                                gcl += (cd == 1 || cd == 2);
+                                if (run >= 4) smem_inc(t4 + (kmer << 2));
+                            }
                         }
                     }
                 }
             }
             gcl = __reduce_add_sync(0xffffffffu, gcl);
-            if (lane == 0 && gcl) atomicAdd(&s_gc[par], (unsigned long long)gcl);
-            __syncthreads();
-            // fold the 32 lane columns; warp w owns codes 32w..32w+31, lane l keeps code 32w+l
-            uint32_t mine = 0;
-#pragma unroll 4
-            for (int i = 0; i < 32; i++) {
-                const int code = warp * 32 + i;
-                uint32_t v = hist[code * 32 + lane];
-                hist[code * 32 + lane] = 0;
-                v = __reduce_add_sync(0xffffffffu, v);
-                if (lane == i) mine = v;
-            }
-            red[tid] = mine;
-            __syncthreads();
-            if (tid < MP2_NCANON) {
-                const uint32_t a = c_canon_code[tid];
-                uint32_t rc = 0, t = a;
+            if (lane == 0 && gcl) atomicAdd(&gc_counts[c], (unsigned long long)gcl);
+            __syncwarp();
+            // ---- flush: fold 256 codes -> 136 canonical classes, add to the contig's row ----
 #pragma unroll
-                for (int i = 0; i < 4; i++) { rc = (rc << 2) | (3u - (t & 3u)); t >>= 2; }
-                uint32_t v = red[a];
-                if (rc != a) v += red[rc];
-                if (v) atomicAdd(&counts[c * MP2_NCANON + tid], v);
-            } else if (tid == MP2_NCANON) {
-                unsigned long long v = s_gc[par];
-                s_gc[par] = 0;
-                if (v) atomicAdd(&gc_counts[c], v);
+            for (int k = lane; k < MP2_NCANON + 24; k += 32) {
+                if (k < MP2_NCANON) {
+                    const uint32_t pr = c_canon_pair[k];
+                    const uint32_t a = pr & 0xFFu, rc = pr >> 8;
+                    uint32_t val = tab[(MODE == 5 ? 1024 : 0) + a];
+                    if (MODE == 5) {
+                        const uint4 q = *reinterpret_cast<const uint4 *>(tab + (a << 2));
+                        val += q.x + q.y + q.z + q.w + tab[a] + tab[256 + a] + tab[512 + a] + tab[768 + a];
+                    }
+                    if (rc != a) {
+                        val += tab[(MODE == 5 ? 1024 : 0) + rc];
+                        if (MODE == 5) {
+                            const uint4 q = *reinterpret_cast<const uint4 *>(tab + (rc << 2));
+                            val += q.x + q.y + q.z + q.w + tab[rc] + tab[256 + rc] + tab[512 + rc] + tab[768 + rc];
+                        }
+                    }
+                    if (val) atomicAdd(&counts[c * MP2_NCANON + k], val);
+                }
             }
-            par ^= 1;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < WORDS / 128; i++)
+                *reinterpret_cast<uint4 *>(tab + (i * 32 + lane) * 4) = make_uint4(0, 0, 0, 0);
+            __syncwarp();
         }
     }
 }
@@ -274,6 +293,16 @@ __global__ void tnf_gc_kernel(const unsigned long long *__restrict__ gc_counts,
     gc[i] = __fdiv_rn(__ull2float_rn(gc_counts[i]), __ull2float_rn(len));
 }
 
+// MP2_TNF_MODE=4|5 selects the counting scheme (development switch; default below).
+static int tnf_mode() {
+    static int mode = 0;
+    if (!mode) {
+        const char *e = getenv("MP2_TNF_MODE");
+        mode = (e && e[0] == '4') ? 4 : 5;
+    }
+    return mode;
+}
+
 // Enqueue the counting kernels for chunks [chunk_begin, chunk_end) of the stream.
 // d_counts / d_gc_counts must have been zeroed (once) before the first range.
 int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n, int64_t n_bases,
@@ -293,21 +322,40 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
             d_offsets, n, mis, chunk_begin, n_chunks, map.as<int32_t>());
     }
     MP2_CUDA(cudaGetLastError());
-    int64_t grid = (int64_t)num_sms() * 4;
-    if (grid > n_chunks) grid = n_chunks;
+    const int mode = tnf_mode();
+    int occ = 0;
+    if (mode == 5)
+        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_kernel<5>, TNF_THREADS, 0));
+    else
+        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_kernel<4>, TNF_THREADS, 0));
+    if (occ < 1) occ = 1;
+    int64_t grid = (int64_t)num_sms() * occ;
+    const int64_t need = (n_chunks + TNF_WARPS - 1) / TNF_WARPS;
+    if (grid > need) grid = need;
     {
         Launch L("tnf_kernel", stream);
-        tnf_kernel<<<(unsigned)grid, TNF_THREADS, 0, stream>>>(
-            d_bases - mis, mis, n_bases + mis, d_offsets, n, map.as<int32_t>(), chunk_begin,
-            n_chunks, d_counts, d_gc_counts, ctr.as<int>());
+        if (mode == 5)
+            tnf_kernel<5><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(
+                d_bases - mis, mis, n_bases + mis, d_offsets, n, map.as<int32_t>(), chunk_begin,
+                n_chunks, d_counts, d_gc_counts, ctr.as<int>());
+        else
+            tnf_kernel<4><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(
+                d_bases - mis, mis, n_bases + mis, d_offsets, n, map.as<int32_t>(), chunk_begin,
+                n_chunks, d_counts, d_gc_counts, ctr.as<int>());
     }
     MP2_CUDA(cudaGetLastError());
     return MP2_OK;
 }
 
+// Pieces wholly inside the first `done` bytes of the stream (host staging pipelines on this).
+int64_t tnf_chunks_ready(const void *d_bases, int64_t done) {
+    const int mis = (int)(reinterpret_cast<uintptr_t>(d_bases) & 15);
+    return (done + mis) / TNF_PIECE;
+}
+
 int64_t tnf_num_chunks(const void *d_bases, int64_t n_bases) {
     const int mis = (int)(reinterpret_cast<uintptr_t>(d_bases) & 15);
-    return (n_bases + mis + TNF_CHUNK - 1) / TNF_CHUNK;
+    return (n_bases + mis + TNF_PIECE - 1) / TNF_PIECE;
 }
 
 int tnf_finalize(const uint32_t *d_counts, const unsigned long long *d_gc_counts,

@@ -36,7 +36,7 @@ def mag_layout(n_mags, seed=0, long_contigs=False, mean_bp=3.0e6, n_contigs=300)
             w = rng.lognormal(0.0, 1.0, k)
             ln = np.maximum(1500, (w / w.sum() * total)).astype(np.int64)
             tiny = rng.random(k) < 0.01
-            ln[tiny] = rng.integers(0, 201, int(tiny.sum()))
+            ln[tiny] = rng.integers(1, 201, int(tiny.sum()))
         gc0 = rng.uniform(0.30, 0.70)
         g = np.full(len(ln), gc0)
         cont = rng.random(len(ln)) < 0.05

@@ -13,8 +13,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k(int iters, uint32_t *out) {
     extern __shared__ uint32_t sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int words = (MODE == 2) ? 256 * 8 : (MODE == 1 ? 128 * 32 : (MODE == 5 ? 64 * 32 : 256 * 32));
-    for (int i = tid; i < words * (MODE == 3 ? 2 : 1); i += 256) sm[i] = 0;
+    const int words = (MODE == 10 || MODE == 13) ? 8192 : (MODE == 11) ? 32768 : (MODE == 12) ? 4096 : (MODE == 4) ? 256 : (MODE == 2) ? 256 * 8 : (MODE == 1 ? 128 * 32 : (MODE == 5 ? 64 * 32 : (MODE == 3 ? 2 * 256 * 32 : 256 * 32)));
+    for (int i = tid; i < words; i += 256) sm[i] = 0;
     __syncthreads();
     uint32_t x = tid * 2654435761u + blockIdx.x * 40503u + 12345u;
     uint32_t acc = 0;
@@ -34,7 +34,15 @@ __global__ void __launch_bounds__(256) k(int iters, uint32_t *out) {
             else if (MODE == 6) {                                                  // non-atomic u32 RMW (racy; rate only)
                 uint32_t *p = &sm[c * 32 + lane];
                 *p = *p + 1;
-            } else if (MODE == 7) atomicAdd(&sm[c * 32 + ((lane + c) & 31)], 1u);     // conflict-free rotated
+            } else if (MODE == 8) atomicAdd(&sm[(c & 7)], 1u);                      // 8 hot addresses, no privatisation
+            else if (MODE == 9) atomicAdd(&sm[(c & 15) * 32 + lane], 1u);            // few rows, lane-private
+            else if (MODE == 10) { uint32_t c2 = (c << 2) | (x >> 22 & 3); atomicAdd(&sm[warp * 1024 + c2], 1u); }   // per-warp [1024]
+            else if (MODE == 11) { uint32_t c2 = (c << 4) | (x >> 20 & 15); atomicAdd(&sm[warp * 4096 + c2], 1u); }  // per-warp [4096]
+            else if (MODE == 12) atomicAdd(&sm[warp * 512 + c * 2 + (lane & 1)], 1u);    // per-warp [256] x2 replicas
+            else if (MODE == 13) atomicAdd(&sm[warp * 1024 + c * 4 + (lane & 3)], 1u);   // per-warp [256] x4 replicas
+            else if (MODE == 14) atomicAdd(&sm[c], 1u);                                  // one [256] per CTA
+            else if (MODE == 15) { uint32_t cc = (c & (c >> 1)) ; atomicAdd(&sm[warp * 256 + cc], 1u); }  // skewed codes
+            else if (MODE == 7) atomicAdd(&sm[c * 32 + ((lane + c) & 31)], 1u);     // conflict-free rotated
         }
         if (MODE == 3) asm volatile("" ::: "memory");
     }
@@ -77,7 +85,7 @@ void run(const char *name, int smem, int blocks_per_sm, int iters) {
 
 int main() {
     int iters = 2000;
-    for (int bps = 1; bps <= 8; bps *= 2) {
+    for (int bps = 2; bps <= 8; bps *= 4) {
         printf("--- %d CTA(s)/SM x 256 threads\n", bps);
         run<4>("alu_only", 1024, bps, iters);
         run<0>("atoms_u32_[code][lane]", 32768, bps, iters);
@@ -87,6 +95,14 @@ int main() {
         run<2>("atoms_per_warp_[256]", 8192, bps, iters);
         run<3>("rmw_private_u8", 65536, bps, iters);
         run<6>("rmw_nonatomic_u32", 32768, bps, iters);
+        run<8>("atoms_u32_same_addr_heavy", 32768, bps, iters);
+        run<9>("atoms_u32_[16][lane]", 32768, bps, iters);
+        run<10>("atoms_per_warp_[1024]", 32768, bps, iters);
+        run<11>("atoms_per_warp_[4096]", 131072, bps, iters);
+        run<12>("atoms_per_warp_[256]x2", 16384, bps, iters);
+        run<13>("atoms_per_warp_[256]x4", 32768, bps, iters);
+        run<14>("atoms_per_cta_[256]", 8192, bps, iters);
+        run<15>("atoms_per_warp_[256]_skewed", 8192, bps, iters);
     }
     return 0;
 }
