@@ -18,8 +18,7 @@
 
 namespace mp2 {
 
-constexpr int TNF_WARPS = 8;
-constexpr int TNF_THREADS = TNF_WARPS * 32;
+constexpr int TNF_THREADS = 32;   // one warp per CTA: the warp's table sits at a fixed shared address
 constexpr int TNF_PIECE = 16384;  // bytes of the stream owned by one work item (one warp)
 constexpr int TNF_UNROLL = 4;     // 16-byte groups in flight per lane
 
@@ -51,26 +50,24 @@ static int upload_tables() {
 
 // ---- byte decoding ---------------------------------------------------------------------
 // 4 ASCII bases in one 32-bit word -> 8 bits of 2-bit codes (first base most significant).
-// `diff` is zero in every byte that is one of AaCcGgTt and non-zero otherwise:
 //   code  = ((b>>1) ^ (b>>2)) & 3            A=0 C=1 G=2 T=3 (bit 5, the case bit, is unused)
 //   isT   = bit2 & ~bit1
 //   valid <=> (b & 0xD9) == (isT ? 0x50 : 0x41)
-__device__ __forceinline__ uint32_t decode4(uint32_t w, uint32_t &diff) {
-    uint32_t s1 = w >> 1, s2 = w >> 2;
-    uint32_t x = (s1 ^ s2) & 0x03030303u;
-    uint32_t isT = s2 & ~s1 & 0x01010101u;
-    diff = ((w & 0xD9D9D9D9u) ^ 0x41414141u) ^ (isT * 0x11u);
-    return (x * 0x40100401u) >> 24;
+// `sig` is 0x41414141 exactly when all four bytes are one of AaCcGgTt.
+__device__ __forceinline__ uint32_t decode4_hi(uint32_t w, uint32_t &sig) {
+    const uint32_t s1 = w >> 1, s2 = w >> 2;
+    const uint32_t x = (s1 ^ s2) & 0x03030303u;
+    const uint32_t isT = s2 & ~s1 & 0x01010101u;
+    sig = (w & 0xD9D9D9D9u) ^ (isT * 0x11u);
+    return x * 0x40100401u;  // the four codes are in bits 31:24
 }
+__device__ __forceinline__ uint32_t decode4(uint32_t w, uint32_t &sig) { return decode4_hi(w, sig) >> 24; }
 
-// scalar: 0..3 for AaCcGgTt, 4 otherwise (src/composition.rs:49-55)
-__device__ __forceinline__ uint32_t code1(uint32_t b) {
-    uint32_t u = b & 0xDFu;
-    if (u == 'A') return 0;
-    if (u == 'C') return 1;
-    if (u == 'G') return 2;
-    if (u == 'T') return 3;
-    return 4;
+// 4-bit mask (first byte most significant) of the bytes of `sig` that differ from 0x41
+__device__ __forceinline__ uint32_t bad4(uint32_t sig) {
+    const uint32_t d = sig ^ 0x41414141u;
+    const uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+    return ((nz >> 7) * 0x08040201u >> 24) & 0xFu;
 }
 
 __device__ __forceinline__ void smem_inc(uint32_t saddr) {
@@ -95,12 +92,18 @@ __global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_
 }
 
 // ---- main kernel -------------------------------------------------------------------------
-// Every warp works alone: it draws a piece of the stream from a global counter, walks the
-// segments (piece ∩ contig) in it, counts each segment into its own 1 KB (MODE 4) / 5 KB
-// (MODE 5) shared-memory table with red.shared (same-address lanes are merged by the hardware,
-// measured 13.4 increments/clk/SM on B200 for a 256-word table) and flushes the table to the
-// contig's row of `counts` with integer global reductions (order independent => bit exact).
-// No block-level synchronisation anywhere.
+// Every warp (= CTA) works alone: it draws a 16 KiB piece of the stream from a global counter,
+// walks the segments (piece ∩ contig) in it, counts each segment into its own shared-memory table
+// with red.shared (ATOMS.POPC.INC: same-address lanes are merged by the hardware) and flushes
+// the table to the contig's row of `counts` with integer global reductions (order independent
+// => bit exact).  No block-level synchronisation anywhere; work per warp is independent of
+// contig length (a 10 Mbp contig is just 640 pieces, a piece full of tiny contigs is a loop).
+//
+// A lane owns 16-byte groups, interleaved across the warp so every LDG.128 is a fully coalesced
+// 512-byte request.  The 3-base halo of a group comes from the neighbouring lane by shuffle.
+// Interior groups of 16 valid bases take the vector path (MODE 5: 8 increments for 16 bases);
+// groups touching a segment edge or holding a non-ACGT byte take the masked path, which
+// computes the exact per-base validity and counts single 4-mers.
 template <int MODE>
 __global__ void __launch_bounds__(TNF_THREADS)
 tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
@@ -109,13 +112,12 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
            uint32_t *__restrict__ counts, unsigned long long *__restrict__ gc_counts,
            int *__restrict__ work_counter) {
     constexpr int WORDS = TnfTab<MODE>::WORDS;
-    __shared__ __align__(1024) uint32_t s_tab[TNF_WARPS * WORDS];
+    __shared__ __align__(16) uint32_t tab[WORDS];
 
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    uint32_t *tab = s_tab + warp * WORDS;
+    const int lane = threadIdx.x;
     const uint32_t t5 = (uint32_t)__cvta_generic_to_shared(tab);  // T5 (MODE 5) or T4 (MODE 4)
     const uint32_t t4 = MODE == 5 ? t5 + 4096u : t5;
+    const int src_lane = (lane + 31) & 31;
 
     for (int i = lane; i < WORDS; i += 32) tab[i] = 0;
     __syncwarp();
@@ -125,80 +127,123 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
         if (lane == 0) kc = atomicAdd(work_counter, 1);
         kc = __shfl_sync(0xffffffffu, kc, 0);
         if (kc >= n_chunks) break;
-        const int64_t piece_lo_raw = (chunk_begin + kc) * TNF_PIECE;
-        const int64_t piece_lo = piece_lo_raw < mis ? mis : piece_lo_raw;
-        int64_t piece_hi = piece_lo_raw + TNF_PIECE;
-        if (piece_hi > end_q) piece_hi = end_q;
+        const int64_t base = (chunk_begin + kc) * TNF_PIECE;  // aligned-stream position of the piece
+        const uint8_t *__restrict__ pb = bases_al + base;     // 16-byte aligned
+        // everything below is relative to `base`, in 32 bits
+        const int piece_lo = base < mis ? mis - (int)base : 0;
+        const int piece_hi = (int)(end_q - base < TNF_PIECE ? end_q - base : TNF_PIECE);
+        const int safe_hi = piece_hi;  // bytes at or beyond this offset may not be read
+        const bool head_ok = base > 0; // bytes before the piece may be read (halo)
 
         for (int64_t c = first_contig[kc]; c < n; c++) {
-            const int64_t o0 = offsets[c] + mis;
-            if (o0 >= piece_hi) break;
-            const int64_t o1 = offsets[c + 1] + mis;
-            const int64_t seg_lo = o0 > piece_lo ? o0 : piece_lo;
-            const int64_t seg_hi = o1 < piece_hi ? o1 : piece_hi;
+            const int64_t o0_64 = offsets[c] + mis - base;
+            if (o0_64 >= piece_hi) break;
+            const int64_t o1_64 = offsets[c + 1] + mis - base;
+            const int o0 = o0_64 < -64 ? -64 : (int)o0_64;  // only compared with positions >= -3
+            const int seg_lo = o0 > piece_lo ? o0 : piece_lo;
+            const int seg_hi = o1_64 < piece_hi ? (int)o1_64 : piece_hi;
             if (seg_hi <= seg_lo) continue;
 
             uint32_t gcl = 0;
-            const int64_t g_last = (seg_hi - 1) >> 4;
-            for (int64_t g0 = (seg_lo >> 4) + lane; g0 <= g_last; g0 += 32 * TNF_UNROLL) {
+            const int g_first = seg_lo >> 4, g_last = (seg_hi - 1) >> 4;
+            // interior groups: all 16 bases in the segment and the 3 halo bases in the contig
+            const int in_lo = o0 + 3 > seg_lo ? o0 + 3 : seg_lo;
+            const int g_in_lo = (in_lo + 15) >> 4;
+            const int g_in_hi = (seg_hi >> 4) > g_in_lo ? (seg_hi >> 4) : g_in_lo;  // [g_in_lo, g_in_hi)
+            // packed halo (last 3 codes | bit 8 "not usable") of the group before g_first, kept by
+            // lane 31: the piece's first group of a long contig then takes the vector path too
+            uint32_t carry = 0x100u;
+            if (lane == 31 && (g_first << 4) - 3 >= o0 && ((g_first << 4) >= 4 || head_ok)) {
+                uint32_t sg;
+                const uint32_t ph = decode4(__ldg(reinterpret_cast<const uint32_t *>(pb + (g_first << 4) - 4)), sg);
+                carry = (ph & 0x3Fu) | (((sg ^ 0x41414141u) & 0xFFFFFF00u) ? 0x100u : 0u);
+            }
+            for (int g0 = g_first; g0 <= g_last; g0 += 32 * TNF_UNROLL) {
                 uint4 v[TNF_UNROLL];
-                uint32_t h[TNF_UNROLL];
-                bool fast[TNF_UNROLL];
 #pragma unroll
                 for (int u = 0; u < TNF_UNROLL; u++) {
-                    const int64_t P = (g0 + 32 * u) << 4;
-                    fast[u] = (P - 3 >= o0) && (P >= seg_lo) && (P + 16 <= seg_hi);
-                    if (fast[u]) {
-                        v[u] = __ldg(reinterpret_cast<const uint4 *>(bases_al + P));
-                        h[u] = __ldg(reinterpret_cast<const uint32_t *>(bases_al + P - 4));
+                    const int P = (g0 + 32 * u + lane) << 4;
+                    v[u] = make_uint4(0, 0, 0, 0);
+                    if (g0 + 32 * u + lane <= g_last) {
+                        if (P + 16 <= safe_hi) {
+                            v[u] = __ldg(reinterpret_cast<const uint4 *>(pb + P));
+                        } else {  // last group of the whole stream: never read past the buffer
+                            uint32_t w[4] = {0, 0, 0, 0};
+                            for (int i = 0; i < 16 && P + i < safe_hi; i++)
+                                w[i >> 2] |= (uint32_t)pb[P + i] << (8 * (i & 3));
+                            v[u] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < TNF_UNROLL; u++) {
-                    const int64_t P = (g0 + 32 * u) << 4;
-                    if (g0 + 32 * u > g_last) break;
-                    uint32_t cw = 0, prev = 0;
-                    bool ok = fast[u];
-                    if (ok) {
-                        uint32_t d0, d1, d2, d3, dh;
-                        const uint32_t p0 = decode4(v[u].x, d0), p1 = decode4(v[u].y, d1);
-                        const uint32_t p2 = decode4(v[u].z, d2), p3 = decode4(v[u].w, d3);
-                        prev = decode4(h[u], dh);
-                        cw = (p0 << 24) | (p1 << 16) | (p2 << 8) | p3;
-                        ok = ((d0 | d1 | d2 | d3 | (dh & 0xFFFFFF00u)) == 0);
-                    }
-                    if (ok) {
+                    const int g = g0 + 32 * u + lane;
+                    if (g0 + 32 * u > g_last) break;  // warp-uniform
+                    uint32_t s0, s1, s2, s3;
+                    const uint32_t m0 = decode4_hi(v[u].x, s0), m1 = decode4_hi(v[u].y, s1);
+                    const uint32_t m2 = decode4_hi(v[u].z, s2), m3 = decode4_hi(v[u].w, s3);
+                    // cw = top bytes of m0..m3, first base most significant
+                    const uint32_t cw = __byte_perm(__byte_perm(m3, m2, 0x0073), __byte_perm(m1, m0, 0x0073), 0x5410);
+                    // all four signatures equal to 0x41414141 <=> 16 valid bases
+                    const bool clean = (((s0 ^ s1) | (s2 ^ s3) | (s0 ^ s2)) == 0) && (s0 == 0x41414141u) &&
+                                       (g <= g_last);
+                    // halo = last 3 codes of the previous group + bit 8 "not usable"
+                    const uint32_t mine = (cw & 0x3Fu) | (clean ? 0u : 0x100u);
+                    const uint32_t give = lane == 31 ? carry : mine;
+                    const uint32_t halo = __shfl_sync(0xffffffffu, give, src_lane);
+                    carry = mine;  // only lane 31's copy is ever consumed
+                    if (g > g_last) continue;
+                    const bool fast = clean && (halo < 0x100u) && ((unsigned)(g - g_in_lo) < (unsigned)(g_in_hi - g_in_lo));
+                    if (fast) {
                         gcl += __popc((cw ^ (cw >> 1)) & 0x55555555u);
                         if (MODE == 5) {
                             // 5-mer ending at base j+1 (j even) = bits [2(14-j)+9 : 2(14-j)] of
-                            // prev:cw; its counter is word index*4 bytes into T5
+                            // halo:cw; its counter is word index*4 bytes into T5
 #pragma unroll
                             for (int j = 0; j < 16; j += 2) {
                                 const int sh = 2 * (14 - j);
-                                const uint32_t t = sh >= 2 ? __funnelshift_r(cw, prev, sh - 2) : (cw << 2);
+                                const uint32_t t = sh >= 2 ? __funnelshift_r(cw, halo, sh - 2) : (cw << 2);
                                 smem_inc(t5 + (t & 0xFFCu));
                             }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 16; j++) {
                                 const int sh = 2 * (15 - j);
-                                const uint32_t t = sh >= 2 ? __funnelshift_r(cw, prev, sh - 2) : (cw << 2);
+                                const uint32_t t = sh >= 2 ? __funnelshift_r(cw, halo, sh - 2) : (cw << 2);
                                 smem_inc(t4 + (t & 0x3FCu));
                             }
                         }
                     } else {
-                        // boundary group or a group holding non-ACGT bytes: rolling scalar walk
-                        uint32_t kmer = 0, run = 0;
-                        for (int i = -3; i < 16; i++) {
-                            const int64_t q = P + i;
-                            if (q >= seg_hi) break;
-                            if (q < o0) { run = 0; continue; }
-                            const uint32_t cd = code1(bases_al[q]);
-                            if (cd > 3) run = 0;
-                            else { kmer = ((kmer << 2) | cd) & 0xFFu; run++; }
-                            if (i >= 0 && q >= seg_lo) {
-                                gcl += (cd == 1 || cd == 2);
-                                if (run >= 4) smem_inc(t4 + (kmer << 2));
+                        // ---- masked path: exact per-base validity, single 4-mers into T4 ----
+                        const int P = g << 4;
+                        uint32_t hw = 0;  // halo bytes straight from memory (positions P-4..P-1)
+                        if (P >= 4 || head_ok) hw = __ldg(reinterpret_cast<const uint32_t *>(pb + P - 4));
+                        uint32_t sh_;
+                        const uint32_t ph = decode4(hw, sh_);
+                        // W: bit (18-i) <-> position P-3+i is a valid base of this contig below seg_hi
+                        uint32_t W = ~((bad4(sh_) & 7u) << 16 | bad4(s0) << 12 | bad4(s1) << 8 | bad4(s2) << 4 | bad4(s3)) & 0x7FFFFu;
+                        const int lo_i = o0 - (P - 3);       // positions i < lo_i precede the contig
+                        if (lo_i > 0) W &= lo_i >= 19 ? 0u : (0x7FFFFu >> lo_i);
+                        const int hi_i = seg_hi - (P - 3);   // positions i >= hi_i are beyond the segment
+                        if (hi_i < 19) W &= ~((1u << (19 - hi_i)) - 1u);
+                        if (P < 4 && !head_ok) W &= 0xFFFFu;
+                        // own: bit (15-j) <-> base j belongs to this segment (>= seg_lo)
+                        const int slo_j = seg_lo - P;
+                        const uint32_t own = slo_j > 0 ? (slo_j >= 16 ? 0u : (0xFFFFu >> slo_j)) : 0xFFFFu;
+                        // K: bit (15-j) <-> the 4-mer ENDING at base j is valid and counted here
+                        const uint32_t K = W & (W >> 1) & (W >> 2) & (W >> 3) & own;
+                        // GC: valid G/C bases of this group inside the segment
+                        uint32_t sp = W & own;  // spread bit b -> bit 2b
+                        sp = (sp | (sp << 8)) & 0x00FF00FFu;
+                        sp = (sp | (sp << 4)) & 0x0F0F0F0Fu;
+                        sp = (sp | (sp << 2)) & 0x33333333u;
+                        sp = (sp | (sp << 1)) & 0x55555555u;
+                        gcl += __popc((cw ^ (cw >> 1)) & sp);
+#pragma unroll
+                        for (int b = 0; b < 16; b++) {
+                            if (K & (1u << b)) {
+                                const uint32_t t = b ? __funnelshift_r(cw, ph, 2 * b - 2) : (cw << 2);
+                                smem_inc(t4 + (t & 0x3FCu));
                             }
                         }
                     }
@@ -330,7 +375,7 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
         MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_kernel<4>, TNF_THREADS, 0));
     if (occ < 1) occ = 1;
     int64_t grid = (int64_t)num_sms() * occ;
-    const int64_t need = (n_chunks + TNF_WARPS - 1) / TNF_WARPS;
+    const int64_t need = n_chunks;
     if (grid > need) grid = need;
     {
         Launch L("tnf_kernel", stream);
