@@ -100,26 +100,29 @@ typedef struct {
     uint64_t total;        /* integer numerator of the trimmed mean             */
     uint64_t max_depth;    /* highest occupied depth                            */
     float coverage;        /* (f32)total / (f32)(max_index - min_index)         */
-    uint32_t flags;        /* bit0: depth range overflowed (result invalid)     */
+    uint32_t flags;        /* reserved (0)                                      */
 } mp2_cov_stats;
 
 /* Alignment blocks (the M/=/X runs of the reads that passed the filters), grouped by contig
- * in BAM order: block e of contig c is (starts[e], ends[e]) for ev_off[c] <= e < ev_off[c+1],
- * 0-based start, exclusive end, relative to the contig.  max_span bounds, over all blocks,
- * both end-start and how far a block may start before an earlier one in the array
- * (0 = let the library compute it on the device).
- *   d_cov   : float32[n_contigs]          trimmed-mean coverage (REQUIRED)
- *   d_stats : mp2_cov_stats[n_contigs]    or NULL                                          */
+ * in BAM order: block e of contig c is [starts[e], ends[e]) for ev_off[c] <= e < ev_off[c+1],
+ * 0-based start, exclusive end, relative to the contig (any order inside a contig).
+ * contig_off: int64[n_contigs+1] cumulative contig lengths (the same array mp2_tnf takes);
+ * n_positions = contig_off[n_contigs] (passed so the call needs no device->host read).
+ *   d_cov   : float32, element c at d_cov[c*cov_stride] -- cov_stride = n_bams writes column s of
+ *             the reference's float32[n_contigs, n_bams] matrix in place        (REQUIRED)
+ *   d_stats : mp2_cov_stats[n_contigs]    or NULL
+ * trim_lower + trim_upper must be < 1 (the CLI clamps both, magpurify2/modules/coverage.py:39-49). */
 int mp2_cov_events_device(const void *d_starts, const void *d_ends, const void *d_ev_off,
-                          const void *d_contig_len, int64_t n_contigs, int64_t n_events,
-                          uint32_t max_span, uint32_t end_excl, float trim_lower,
-                          float trim_upper, void *d_cov, void *d_stats, void *stream);
+                          const void *d_contig_off, int64_t n_contigs, int64_t n_events,
+                          int64_t n_positions, uint32_t end_excl, float trim_lower,
+                          float trim_upper, void *d_cov, int64_t cov_stride, void *d_stats,
+                          void *stream);
 
 /* Host-buffer form of the same call (stages H2D/D2H itself). */
 int mp2_cov_events(const uint32_t *starts, const uint32_t *ends, const int64_t *ev_off,
-                   const int64_t *contig_len, int64_t n_contigs, int64_t n_events,
-                   uint32_t max_span, uint32_t end_excl, float trim_lower, float trim_upper,
-                   int device, float *cov, mp2_cov_stats *stats);
+                   const int64_t *contig_off, int64_t n_contigs, int64_t n_events,
+                   uint32_t end_excl, float trim_lower, float trim_upper, int device, float *cov,
+                   int64_t cov_stride, mp2_cov_stats *stats);
 
 /* ---- scoring: replaces tools.get_log_ratio_scores / get_weighted_median ----------------- */
 /* (magpurify2/tools.py:283-351; callers magpurify2/core.py:261-263 base 2, :310-312 base 25) */

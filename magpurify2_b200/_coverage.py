@@ -1,0 +1,39 @@
+"""Drop-in for the reference's PyO3 module `magpurify2._coverage`
+(/root/reference/src/coverage.rs:208-212): same function name, arguments and results, with the
+depth arithmetic done by the sm_100a kernels in libmp2.so and BAM decoding by libmp2's own
+BGZF/BAM reader (htslib is not used).
+
+    get_bam_coverages(bam_list, contig_end_exclusion=75, min_identity=0.97, trim_lower=0.0,
+                      trim_upper=0.0, contig_set=None, threads=1)
+        -> (list[str] names, float32[n_contigs, n_bams])                    (coverage.rs:81-98)
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+COV_STATS_DTYPE = _lib.COV_STATS_DTYPE
+
+
+def cov_from_events(starts, ends, ev_off, contig_off, contig_end_exclusion=75, trim_lower=0.0,
+                    trim_upper=0.0, want_stats=False, device=-1):
+    """One sample on host arrays: alignment blocks grouped by contig -> trimmed-mean coverage.
+
+    starts/ends: uint32[n_events] (0-based start, exclusive end, relative to the contig);
+    ev_off: int64[n_contigs+1]; contig_off: int64[n_contigs+1] cumulative contig lengths.
+    Returns float32[n_contigs] (and the per-contig integer statistics when want_stats)."""
+    starts = np.ascontiguousarray(starts, dtype=np.uint32)
+    ends = np.ascontiguousarray(ends, dtype=np.uint32)
+    ev_off = np.ascontiguousarray(ev_off, dtype=np.int64)
+    contig_off = np.ascontiguousarray(contig_off, dtype=np.int64)
+    n = len(contig_off) - 1
+    if len(ev_off) != n + 1:
+        raise ValueError("ev_off and contig_off must have the same length")
+    cov = np.empty(n, dtype=np.float32)
+    stats = np.zeros(n, dtype=COV_STATS_DTYPE) if want_stats else None
+    lib = _lib.load()
+    _lib.check(lib.mp2_cov_events(_lib.ptr(starts), _lib.ptr(ends), _lib.ptr(ev_off), _lib.ptr(contig_off),
+                                  n, len(starts), int(contig_end_exclusion), float(trim_lower),
+                                  float(trim_upper), device, _lib.ptr(cov), 1, _lib.ptr(stats)))
+    return (cov, stats) if want_stats else cov

@@ -1,0 +1,628 @@
+// Coverage path: per-contig depth accumulation + trimmed-mean coverage for ONE sample on sm_100a.
+//
+// Replaces the arithmetic coverm 0.3.2 performs under _coverage.get_bam_coverages
+// (/root/reference/src/coverage.rs:99-142: contig_coverage -> TrimmedMean add_contig /
+// calculate_coverage; restated in SURVEY.md Appendix A because the crate is not vendored).
+//
+// Layout in HBM: one int32 difference array D over ALL contigs concatenated (contig c owns
+// positions off[c] .. off[c+1]) plus one trailing slot.  An alignment block [s, e) of contig c
+// adds +1 at off[c]+s and -1 at off[c]+min(e, len): the reference skips the -1 when e == len
+// (`if end < len`), here it lands on the first slot of the NEXT contig, which makes the plain
+// (unsegmented) prefix sum of D equal to the per-contig depth everywhere -- no segment heads.
+//
+//   cov_scatter_kernel   events -> D (red.global +-1) and per-tile sums of D (tile = 65536 slots)
+//   cov_tile_scan_kernel exclusive scan of the tile sums  => depth just before every tile
+//   cov_depth_kernel     ONE pass over D: running depth, windowed depth histogram per contig in
+//                        shared memory (red.shared: equal depths in a warp are merged by the
+//                        hardware), trimmed mean for contigs whose window lies in one tile;
+//                        windows spanning tiles are merged through a global row and finished by
+//                        the last contributor.  D is read exactly once (4 B/position).
+//   cov_deep_kernel      exact fallback for contigs that reach depth >= 1023 (multi-pass over
+//                        depth ranges; rare).
+#include "mp2_common.h"
+
+namespace mp2 {
+
+constexpr int COV_THREADS = 256;
+constexpr int COV_ITEMS = 16;                         // positions per thread per sub-tile
+constexpr int COV_SUB = COV_THREADS * COV_ITEMS;      // 4096 positions
+constexpr int COV_TILE = 65536;                       // positions per tile
+constexpr int COV_NSUB = COV_TILE / COV_SUB;          // 16
+constexpr int COV_BINS = 1024;                        // depth bins 0..1022 exact, 1023 = overflow
+constexpr int COV_EV_TILE = 2048;                     // events per scatter CTA
+constexpr int COV_DEEP_BINS = 8192;
+
+// row bookkeeping for windows that span tiles (one row per tile: the window that STARTS in it)
+struct RowMeta {
+    unsigned long long done;  // window positions accounted for so far
+    unsigned int maxd;        // highest depth seen (1023 = overflow)
+    unsigned int pad;
+};
+
+// ---- small device helpers ------------------------------------------------------------------
+__device__ __forceinline__ void smem_inc(uint32_t saddr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory");
+}
+
+// upper_bound(a[lo..hi), x) - 1 : largest i in [lo, hi) with a[i] <= x (lo if none)
+__device__ __forceinline__ int64_t last_le(const int64_t *__restrict__ a, int64_t lo, int64_t hi, int64_t x) {
+    int64_t l = lo, h = hi;
+    while (l < h) {
+        int64_t m = (l + h) >> 1;
+        if (a[m] <= x) l = m + 1;
+        else h = m;
+    }
+    return l > lo ? l - 1 : lo;
+}
+
+struct TrimParams {
+    float lo;   // trim_lower
+    float hi;   // 1.0f - trim_upper   (src/coverage.rs:99)
+    uint32_t excl;
+};
+
+// Appendix A.4 (calculate_coverage) for one contig, executed by ONE warp.  bins[d] = number of
+// window positions with depth d, d in [0, nbins).  The sequential histogram walk of the reference
+// is evaluated in closed form per bin from the running count A_d:
+//   d0 = first d with A_d >= min_index            contributes (min(A_d, max_index) - min_index + 1) * d
+//   d > d0                                        contributes max(0, min(A_d, max_index+1) - A_{d-1}) * d
+// `acc`/`total` carry the state across calls (depth ranges of the fallback kernel).
+template <class Load>
+__device__ __forceinline__ void trim_walk_warp(Load load, uint32_t d_begin, uint32_t d_end, uint64_t min_index,
+                                               uint64_t max_index, unsigned long long &acc,
+                                               unsigned long long &total) {
+    const int lane = threadIdx.x & 31;
+    for (uint32_t d0 = d_begin; d0 < d_end; d0 += 32) {
+        const uint32_t d = d0 + lane;
+        unsigned long long cnt = d < d_end ? (unsigned long long)load(d) : 0ull;
+        unsigned long long incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const unsigned long long A = acc + incl, Ap = A - cnt;
+        unsigned long long take = 0;
+        if (d < d_end) {
+            const bool first = (A >= min_index) && (d == 0 || Ap < min_index);
+            if (first) take = (A > max_index ? max_index : A) - min_index + 1;
+            else if (d > 0 && Ap >= min_index) {
+                const unsigned long long top = A < max_index + 1 ? A : max_index + 1;
+                take = top > Ap ? top - Ap : 0;
+            }
+        }
+        unsigned long long part = take * d;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        total += part;
+        acc = __shfl_sync(0xffffffffu, A, 31);
+    }
+}
+
+__device__ __forceinline__ void trim_indices(uint64_t N, const TrimParams &tp, uint64_t &mn, uint64_t &mx) {
+    const float fn = __ull2float_rn(N);
+    mn = (uint64_t)floorf(__fmul_rn(tp.lo, fn));
+    mx = (uint64_t)ceilf(__fmul_rn(tp.hi, fn));
+}
+
+__device__ __forceinline__ void write_result(int64_t c, uint64_t N, uint64_t covered, uint64_t mn, uint64_t mx,
+                                             uint64_t total, uint32_t maxd, uint32_t flags,
+                                             float *__restrict__ cov, int64_t cov_stride,
+                                             mp2_cov_stats *__restrict__ stats) {
+    float r = 0.0f;
+    if (N != 0 && covered != 0) r = __fdiv_rn(__ull2float_rn(total), __ull2float_rn(mx - mn));
+    cov[c * cov_stride] = r;
+    if (stats) {
+        mp2_cov_stats s;
+        s.observed_len = N; s.covered = covered; s.min_index = mn; s.max_index = mx;
+        s.total = covered ? total : 0; s.max_depth = maxd; s.coverage = r; s.flags = flags;
+        stats[c] = s;
+    }
+}
+
+// ---- per-contig initialisation: contigs without a window get their final answer here --------
+__global__ void cov_init_kernel(const int64_t *__restrict__ off, int64_t n, uint32_t excl,
+                                float *__restrict__ cov, int64_t cov_stride,
+                                mp2_cov_stats *__restrict__ stats) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int64_t len = off[c + 1] - off[c];
+    if (2ll * excl >= len) write_result(c, 0, 0, 0, 0, 0, 0, 0, cov, cov_stride, stats);
+}
+
+// ---- tile -> first contig maps ------------------------------------------------------------------
+__global__ void cov_map_kernel(const int64_t *__restrict__ a, int64_t n, int64_t step, int64_t n_tiles,
+                               int32_t *__restrict__ first) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n_tiles) return;
+    first[k] = (int32_t)last_le(a, 0, n, k * step);  // a[n] (the total) is never a candidate
+}
+
+// ---- scatter -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cov_scatter_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends,
+                   const int64_t *__restrict__ ev_off, const int64_t *__restrict__ off, int64_t n,
+                   int64_t n_events, const int32_t *__restrict__ ev_first, int32_t *__restrict__ D,
+                   int32_t *__restrict__ tile_sum) {
+    const int64_t t0 = (int64_t)blockIdx.x * COV_EV_TILE;
+    const int64_t c_lo = ev_first[blockIdx.x];
+    const int64_t t_last = t0 + COV_EV_TILE - 1 < n_events - 1 ? t0 + COV_EV_TILE - 1 : n_events - 1;
+    __shared__ int64_t s_chi;
+    if (threadIdx.x == 0) s_chi = last_le(ev_off, c_lo, n, t_last);
+    __syncthreads();
+    const int64_t c_hi = s_chi;
+#pragma unroll
+    for (int k = 0; k < COV_EV_TILE / 256; k++) {
+        const int64_t e = t0 + k * 256 + threadIdx.x;
+        const bool live = e < n_events;
+        int64_t ps = -1, pe = -1;
+        if (live) {
+            const int64_t c = c_hi == c_lo ? c_lo : last_le(ev_off, c_lo, c_hi + 1, e);
+            const int64_t base = off[c], len = off[c + 1] - base;
+            const int64_t s = starts[e];
+            int64_t en = ends[e];
+            if (en > len) en = len;
+            if (s < len && en > s) {  // a start beyond the contig would panic in the reference
+                ps = base + s;
+                pe = base + en;
+                atomicAdd(&D[ps], 1);
+                atomicAdd(&D[pe], -1);
+            }
+        }
+        // tile sums of D: a block whose +1 and -1 fall in the same tile contributes nothing
+        if (ps >= 0) {
+            const int64_t ts = ps / COV_TILE, te = pe / COV_TILE;
+            if (ts != te) {
+                atomicAdd(&tile_sum[ts], 1);
+                atomicAdd(&tile_sum[te], -1);
+            }
+        }
+    }
+}
+
+// ---- exclusive scan of the tile sums (n_tiles is small: L / 65536) -------------------------------
+__global__ void __launch_bounds__(1024)
+cov_tile_scan_kernel(const int32_t *__restrict__ tile_sum, int64_t n_tiles, int32_t *__restrict__ tile_pre) {
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t b = 0; b < n_tiles; b += 1024) {
+        const int64_t i = b + tid;
+        const int v = i < n_tiles ? tile_sum[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_w[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_w[lane] = wi - w;  // exclusive
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (i < n_tiles) tile_pre[i] = carry + s_w[warp] + incl - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_w[warp] + incl;
+        __syncthreads();
+    }
+}
+
+// ---- fused scan + windowed depth histogram + trimmed mean -----------------------------------------
+struct DepthArgs {
+    const int32_t *D;
+    const int64_t *off;
+    int64_t n, n_pos;  // n_pos = off[n] + 1 slots in D
+    const int32_t *first;     // tile -> contig holding the tile's first position
+    const int32_t *tile_pre;  // depth just before the tile
+    int64_t n_tiles;
+    uint32_t *rows;           // [n_tiles][COV_BINS]
+    RowMeta *meta;            // [n_tiles]
+    int32_t *deep_list;       // contigs needing the exact fallback
+    int *deep_count;
+    int *work_counter;
+    float *cov;
+    int64_t cov_stride;
+    mp2_cov_stats *stats;
+    TrimParams tp;
+};
+
+// Finish contig c from a histogram (shared or global), by warp 0 of the CTA.
+template <class Load>
+__device__ __forceinline__ void finish_contig(const DepthArgs &a, int64_t c, uint64_t N, uint32_t maxd, Load load) {
+    const int lane = threadIdx.x & 31;
+    if (maxd >= COV_BINS - 1) {  // overflow: exact multi-pass fallback
+        if (lane == 0) a.deep_list[atomicAdd(a.deep_count, 1)] = (int32_t)c;
+        return;
+    }
+    uint64_t mn, mx;
+    trim_indices(N, a.tp, mn, mx);
+    const uint64_t covered = N - (uint64_t)load(0);
+    unsigned long long acc = 0, total = 0;
+    if (covered) trim_walk_warp(load, 0, maxd + 1, mn, mx, acc, total);
+    if (lane == 0) write_result(c, N, covered, mn, mx, total, maxd, 0, a.cov, a.cov_stride, a.stats);
+}
+
+__global__ void __launch_bounds__(COV_THREADS)
+cov_depth_kernel(const DepthArgs a) {
+    __shared__ uint32_t s_hist[COV_BINS];
+    __shared__ int s_wsum[COV_THREADS / 32];
+    __shared__ unsigned int s_maxd;
+    __shared__ int s_tile;
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t h0 = (uint32_t)__cvta_generic_to_shared(s_hist);
+    const int64_t excl = a.tp.excl;
+    for (int i = tid; i < COV_BINS; i += COV_THREADS) s_hist[i] = 0;
+    if (tid == 0) s_maxd = 0;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int64_t tile = s_tile;
+        __syncthreads();
+        if (tile >= a.n_tiles) break;
+        const int64_t tile_lo = tile * COV_TILE;
+        const int64_t tile_hi = tile_lo + COV_TILE < a.n_pos ? tile_lo + COV_TILE : a.n_pos;
+        int carry = a.tile_pre[tile];
+
+        // current contig: the first one whose window can still receive positions >= tile_lo
+        int64_t c = a.first[tile];
+        int64_t wlo = 0, whi = -1;  // window [wlo, whi] of contig c (global positions), empty if none
+        bool have = false;          // window of c loaded
+        uint64_t in_tile = 0;       // window positions of c histogrammed in this tile so far
+
+        for (int sub = 0; sub < COV_NSUB; sub++) {
+            const int64_t p0 = tile_lo + (int64_t)sub * COV_SUB;
+            if (p0 >= tile_hi) break;
+            const int64_t p1 = p0 + COV_SUB < tile_hi ? p0 + COV_SUB : tile_hi;
+            // ---- load 16 slots per thread, local + block scan ----
+            const int64_t q = p0 + (int64_t)tid * COV_ITEMS;
+            int d[COV_ITEMS];
+            if (q + COV_ITEMS <= a.n_pos && ((reinterpret_cast<uintptr_t>(a.D + q) & 15) == 0)) {
+                const int4 *src = reinterpret_cast<const int4 *>(a.D + q);
+#pragma unroll
+                for (int k = 0; k < COV_ITEMS / 4; k++) {
+                    const int4 v = __ldcs(src + k);
+                    d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < COV_ITEMS; k++) d[k] = q + k < a.n_pos ? a.D[q + k] : 0;
+            }
+#pragma unroll
+            for (int k = 1; k < COV_ITEMS; k++) d[k] += d[k - 1];
+            int incl = d[COV_ITEMS - 1];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int wpre = 0, sub_total = 0;
+#pragma unroll
+            for (int w = 0; w < COV_THREADS / 32; w++) {
+                const int v = s_wsum[w];
+                if (w < warp) wpre += v;
+                sub_total += v;
+            }
+            const int tpre = carry + wpre + incl - d[COV_ITEMS - 1];  // depth before this thread's first slot
+#pragma unroll
+            for (int k = 0; k < COV_ITEMS; k++) d[k] += tpre;         // d[k] = depth at position q + k
+            carry += sub_total;
+
+            // ---- windows intersecting [p0, p1) ----
+            for (;;) {
+                if (!have) {
+                    if (c >= a.n) break;
+                    const int64_t o0 = a.off[c], o1 = a.off[c + 1];
+                    if (o0 >= p1) break;  // contig starts after this sub-tile
+                    if (o1 - o0 > 2 * excl) { wlo = o0 + excl; whi = o1 - excl - 1; }
+                    else { wlo = 0; whi = -1; }
+                    have = true;
+                    in_tile = 0;
+                }
+                if (whi < wlo || whi < tile_lo) { c++; have = false; continue; }  // no window / ended before this tile
+                if (wlo >= p1) break;
+                // positions [lo, hi) of this sub-tile belong to the window
+                const int64_t lo = wlo > p0 ? wlo : p0, hi = whi + 1 < p1 ? whi + 1 : p1;
+                if (hi > lo) {
+                    const int ja = lo - q > 0 ? (lo - q > COV_ITEMS ? COV_ITEMS : (int)(lo - q)) : 0;
+                    const int jb = hi - q < COV_ITEMS ? (hi - q < 0 ? 0 : (int)(hi - q)) : COV_ITEMS;
+                    int mx = 0;
+#pragma unroll
+                    for (int k = 0; k < COV_ITEMS; k++) {
+                        if (k >= ja && k < jb) {
+                            int v = d[k] < 0 ? 0 : d[k];
+                            v = v > COV_BINS - 1 ? COV_BINS - 1 : v;
+                            mx = v > mx ? v : mx;
+                            smem_inc(h0 + 4u * (uint32_t)v);
+                        }
+                    }
+                    mx = __reduce_max_sync(0xffffffffu, mx);
+                    if (lane == 0 && mx) atomicMax(&s_maxd, (unsigned)mx);
+                    in_tile += (uint64_t)(hi - lo);
+                }
+                if (whi >= p1) break;  // window continues in the next sub-tile
+                // ---- the window of contig c ends in this sub-tile ----
+                __syncthreads();
+                const uint64_t N = (uint64_t)(whi - wlo + 1);
+                const uint32_t maxd = s_maxd;
+                if (wlo >= tile_lo) {
+                    // whole window inside this tile: finish from shared memory
+                    if (warp == 0) finish_contig(a, c, N, maxd, [&](uint32_t i) { return s_hist[i]; });
+                } else {
+                    // window started in an earlier tile: merge into its row, last contributor finishes
+                    const int64_t row = wlo / COV_TILE;
+                    uint32_t *r = a.rows + row * COV_BINS;
+                    for (uint32_t i = tid; i <= maxd; i += COV_THREADS) {
+                        const uint32_t v = s_hist[i];
+                        if (v) atomicAdd(&r[i], v);
+                    }
+                    __threadfence();
+                    __syncthreads();
+                    if (tid == 0) {
+                        atomicMax(&a.meta[row].maxd, maxd);
+                        __threadfence();
+                        const unsigned long long old = atomicAdd(&a.meta[row].done, (unsigned long long)in_tile);
+                        s_last = (old + in_tile == N);
+                    }
+                    __syncthreads();
+                    if (s_last) {
+                        __threadfence();
+                        const uint32_t gm = *((volatile unsigned int *)&a.meta[row].maxd);
+                        if (warp == 0) finish_contig(a, c, N, gm, [&](uint32_t i) { return __ldcg(r + i); });
+                    }
+                }
+                __syncthreads();
+                for (uint32_t i = tid; i <= maxd; i += COV_THREADS) s_hist[i] = 0;
+                if (tid == 0) s_maxd = 0;
+                __syncthreads();
+                c++;
+                have = false;
+            }
+            __syncthreads();  // s_wsum is rewritten by the next sub-tile
+        }
+        // ---- tile end: a window still open is merged into the row of the tile it started in ----
+        if (have && whi >= wlo && in_tile > 0) {
+            __syncthreads();
+            const uint64_t N = (uint64_t)(whi - wlo + 1);
+            const uint32_t maxd = s_maxd;
+            const int64_t row = wlo / COV_TILE;
+            uint32_t *r = a.rows + row * COV_BINS;
+            for (uint32_t i = tid; i <= maxd; i += COV_THREADS) {
+                const uint32_t v = s_hist[i];
+                if (v) atomicAdd(&r[i], v);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                atomicMax(&a.meta[row].maxd, maxd);
+                __threadfence();
+                const unsigned long long old = atomicAdd(&a.meta[row].done, (unsigned long long)in_tile);
+                s_last = (old + in_tile == N);
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                const uint32_t gm = *((volatile unsigned int *)&a.meta[row].maxd);
+                if (warp == 0) finish_contig(a, c, N, gm, [&](uint32_t i) { return __ldcg(r + i); });
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i <= maxd; i += COV_THREADS) s_hist[i] = 0;
+            if (tid == 0) s_maxd = 0;
+            __syncthreads();
+        }
+    }
+}
+
+// ---- exact fallback for very deep contigs ------------------------------------------------------
+// One CTA per flagged contig; the depth axis is swept in ranges of COV_DEEP_BINS bins, each range
+// re-scanning the contig's slice of D (the prefix restarts at 0 at a contig start).
+__global__ void __launch_bounds__(COV_THREADS)
+cov_deep_kernel(const DepthArgs a, int *__restrict__ deep_next) {
+    __shared__ uint32_t s_hist[COV_DEEP_BINS];
+    __shared__ int s_wsum[COV_THREADS / 32];
+    __shared__ unsigned int s_maxd;
+    __shared__ int s_item;
+    __shared__ unsigned long long s_acc, s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t excl = a.tp.excl;
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(deep_next, 1);
+        __syncthreads();
+        const int item = s_item;
+        __syncthreads();
+        if (item >= *a.deep_count) break;
+        const int64_t c = a.deep_list[item];
+        const int64_t o0 = a.off[c], o1 = a.off[c + 1];
+        const int64_t wlo = o0 + excl, whi = o1 - excl - 1;
+        const uint64_t N = (uint64_t)(whi - wlo + 1);
+        uint64_t mn, mx;
+        trim_indices(N, a.tp, mn, mx);
+        if (tid == 0) { s_maxd = 0; s_acc = 0; s_total = 0; }
+        uint64_t covered = 0;
+        uint32_t maxd = 0;
+        for (uint32_t base = 0;; base += COV_DEEP_BINS) {
+            for (int i = tid; i < COV_DEEP_BINS; i += COV_THREADS) s_hist[i] = 0;
+            __syncthreads();
+            int carry = 0;
+            for (int64_t p0 = o0; p0 < o1; p0 += COV_SUB) {
+                const int64_t q = p0 + (int64_t)tid * COV_ITEMS;
+                int d[COV_ITEMS];
+#pragma unroll
+                for (int k = 0; k < COV_ITEMS; k++) d[k] = q + k < o1 ? a.D[q + k] : 0;
+#pragma unroll
+                for (int k = 1; k < COV_ITEMS; k++) d[k] += d[k - 1];
+                int incl = d[COV_ITEMS - 1];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (lane == 31) s_wsum[warp] = incl;
+                __syncthreads();
+                int wpre = 0, sub_total = 0;
+#pragma unroll
+                for (int w = 0; w < COV_THREADS / 32; w++) {
+                    const int v = s_wsum[w];
+                    if (w < warp) wpre += v;
+                    sub_total += v;
+                }
+                const int tpre = carry + wpre + incl - d[COV_ITEMS - 1];
+                carry += sub_total;
+                unsigned int mxl = 0;
+#pragma unroll
+                for (int k = 0; k < COV_ITEMS; k++) {
+                    const int64_t p = q + k;
+                    if (p >= wlo && p <= whi) {
+                        const int v = d[k] + tpre;
+                        const uint32_t u = v < 0 ? 0u : (uint32_t)v;
+                        mxl = u > mxl ? u : mxl;
+                        if (u >= base && u - base < COV_DEEP_BINS) atomicAdd(&s_hist[u - base], 1u);
+                    }
+                }
+                mxl = __reduce_max_sync(0xffffffffu, mxl);
+                if (lane == 0 && base == 0) atomicMax(&s_maxd, mxl);
+                __syncthreads();
+            }
+            maxd = s_maxd;
+            if (base == 0) covered = N - s_hist[0];
+            if (warp == 0) {
+                unsigned long long acc = s_acc, total = s_total;
+                const uint32_t d_end = maxd + 1 < base + COV_DEEP_BINS ? maxd + 1 : base + COV_DEEP_BINS;
+                if (covered) trim_walk_warp([&](uint32_t i) { return s_hist[i - base]; }, base, d_end, mn, mx, acc, total);
+                if (lane == 0) { s_acc = acc; s_total = total; }
+            }
+            __syncthreads();
+            if ((uint64_t)base + COV_DEEP_BINS > maxd) break;
+        }
+        if (tid == 0) write_result(c, N, covered, mn, mx, s_total, maxd, 0, a.cov, a.cov_stride, a.stats);
+        __syncthreads();
+    }
+}
+
+}  // namespace mp2
+
+using namespace mp2;
+
+extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, const void *d_ev_off,
+                                     const void *d_contig_off, int64_t n_contigs, int64_t n_events,
+                                     int64_t n_positions, uint32_t end_excl, float trim_lower,
+                                     float trim_upper, void *d_cov, int64_t cov_stride, void *d_stats,
+                                     void *stream_) {
+    if (n_contigs < 0 || n_events < 0 || n_positions < 0) return fail(MP2_EINVAL, "negative size");
+    if (n_contigs > INT32_MAX) return fail(MP2_EINVAL, "too many contigs in one call");
+    if (!d_contig_off || !d_ev_off || !d_cov || (n_events > 0 && (!d_starts || !d_ends)))
+        return fail(MP2_EINVAL, "NULL argument");
+    if (!(trim_lower >= 0.0f) || !(trim_upper >= 0.0f) || !(trim_lower + trim_upper < 1.0f))
+        return fail(MP2_EINVAL, "trim_lower and trim_upper must be >= 0 and sum to < 1");
+    if (cov_stride < 1) return fail(MP2_EINVAL, "cov_stride must be >= 1");
+    MP2_TRY(require_device(-1));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_contigs == 0) return MP2_OK;
+
+    const int64_t n_pos = n_positions + 1;
+    const int64_t n_tiles = (n_pos + COV_TILE - 1) / COV_TILE;
+    const int64_t n_ev_tiles = (n_events + COV_EV_TILE - 1) / COV_EV_TILE;
+    if (n_tiles > INT32_MAX / 2) return fail(MP2_EINVAL, "too many positions in one call");
+
+    Temp D, tile_sum, tile_pre, first, ev_first, rows, meta, deep_list, ctrs;
+    MP2_TRY(D.alloc(sizeof(int32_t) * (size_t)n_pos, stream));
+    MP2_TRY(tile_sum.alloc(sizeof(int32_t) * n_tiles, stream));
+    MP2_TRY(tile_pre.alloc(sizeof(int32_t) * n_tiles, stream));
+    MP2_TRY(first.alloc(sizeof(int32_t) * n_tiles, stream));
+    MP2_TRY(ev_first.alloc(sizeof(int32_t) * (n_ev_tiles + 1), stream));
+    MP2_TRY(rows.alloc(sizeof(uint32_t) * COV_BINS * (size_t)n_tiles, stream));
+    MP2_TRY(meta.alloc(sizeof(RowMeta) * n_tiles, stream));
+    MP2_TRY(deep_list.alloc(sizeof(int32_t) * n_contigs, stream));
+    MP2_TRY(ctrs.alloc(sizeof(int) * 4, stream));
+    MP2_CUDA(cudaMemsetAsync(D.p, 0, sizeof(int32_t) * (size_t)n_pos, stream));
+    MP2_CUDA(cudaMemsetAsync(tile_sum.p, 0, sizeof(int32_t) * n_tiles, stream));
+    MP2_CUDA(cudaMemsetAsync(rows.p, 0, sizeof(uint32_t) * COV_BINS * (size_t)n_tiles, stream));
+    MP2_CUDA(cudaMemsetAsync(meta.p, 0, sizeof(RowMeta) * n_tiles, stream));
+    MP2_CUDA(cudaMemsetAsync(ctrs.p, 0, sizeof(int) * 4, stream));
+
+    const int64_t *off = (const int64_t *)d_contig_off;
+    TrimParams tp;
+    tp.lo = trim_lower;
+    tp.hi = 1.0f - trim_upper;  // src/coverage.rs:99
+    tp.excl = end_excl;
+    {
+        Launch L("cov_init_kernel", stream);
+        cov_init_kernel<<<(unsigned)((n_contigs + 255) / 256), 256, 0, stream>>>(
+            off, n_contigs, end_excl, (float *)d_cov, cov_stride, (mp2_cov_stats *)d_stats);
+    }
+    MP2_CUDA(cudaGetLastError());
+    {
+        Launch L("cov_map_kernel", stream);
+        cov_map_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(off, n_contigs, COV_TILE, n_tiles,
+                                                                            first.as<int32_t>());
+    }
+    MP2_CUDA(cudaGetLastError());
+    if (n_events > 0) {
+        {
+            Launch L("cov_map_kernel", stream);
+            cov_map_kernel<<<(unsigned)((n_ev_tiles + 255) / 256), 256, 0, stream>>>(
+                (const int64_t *)d_ev_off, n_contigs, COV_EV_TILE, n_ev_tiles, ev_first.as<int32_t>());
+        }
+        MP2_CUDA(cudaGetLastError());
+        {
+            Launch L("cov_scatter_kernel", stream);
+            cov_scatter_kernel<<<(unsigned)n_ev_tiles, 256, 0, stream>>>(
+                (const uint32_t *)d_starts, (const uint32_t *)d_ends, (const int64_t *)d_ev_off, off, n_contigs,
+                n_events, ev_first.as<int32_t>(), D.as<int32_t>(), tile_sum.as<int32_t>());
+        }
+        MP2_CUDA(cudaGetLastError());
+    }
+    {
+        Launch L("cov_tile_scan_kernel", stream);
+        cov_tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_sum.as<int32_t>(), n_tiles, tile_pre.as<int32_t>());
+    }
+    MP2_CUDA(cudaGetLastError());
+    DepthArgs a;
+    a.D = D.as<int32_t>();
+    a.off = off;
+    a.n = n_contigs;
+    a.n_pos = n_pos;
+    a.first = first.as<int32_t>();
+    a.tile_pre = tile_pre.as<int32_t>();
+    a.n_tiles = n_tiles;
+    a.rows = rows.as<uint32_t>();
+    a.meta = meta.as<RowMeta>();
+    a.deep_list = deep_list.as<int32_t>();
+    a.deep_count = ctrs.as<int>() + 0;
+    a.work_counter = ctrs.as<int>() + 1;
+    a.cov = (float *)d_cov;
+    a.cov_stride = cov_stride;
+    a.stats = (mp2_cov_stats *)d_stats;
+    a.tp = tp;
+    int occ = 0;
+    MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_depth_kernel, COV_THREADS, 0));
+    if (occ < 1) occ = 1;
+    int64_t grid = (int64_t)num_sms() * occ;
+    if (grid > n_tiles) grid = n_tiles;
+    {
+        Launch L("cov_depth_kernel", stream);
+        cov_depth_kernel<<<(unsigned)grid, COV_THREADS, 0, stream>>>(a);
+    }
+    MP2_CUDA(cudaGetLastError());
+    {
+        Launch L("cov_deep_kernel", stream);
+        cov_deep_kernel<<<(unsigned)(num_sms() * 2), COV_THREADS, 0, stream>>>(a, ctrs.as<int>() + 2);
+    }
+    MP2_CUDA(cudaGetLastError());
+    return MP2_OK;
+}

@@ -179,3 +179,45 @@ extern "C" int mp2_tnf(const uint8_t *bases, const int64_t *offsets, int64_t n, 
     MP2_CUDA(cudaStreamSynchronize(st.copy));
     return MP2_OK;
 }
+
+extern "C" int mp2_cov_events(const uint32_t *starts, const uint32_t *ends, const int64_t *ev_off,
+                              const int64_t *contig_off, int64_t n_contigs, int64_t n_events,
+                              uint32_t end_excl, float trim_lower, float trim_upper, int device,
+                              float *cov, int64_t cov_stride, mp2_cov_stats *stats) {
+    if (n_contigs < 0 || n_events < 0) return fail(MP2_EINVAL, "negative size");
+    if (!contig_off || !ev_off || !cov) return fail(MP2_EINVAL, "NULL argument");
+    if (n_events > 0 && (!starts || !ends)) return fail(MP2_EINVAL, "NULL events");
+    if (cov_stride < 1) return fail(MP2_EINVAL, "cov_stride must be >= 1");
+    if (contig_off[0] != 0 || ev_off[0] != 0) return fail(MP2_EINVAL, "offsets must start at 0");
+    if (ev_off[n_contigs] != n_events) return fail(MP2_EINVAL, "ev_off[n_contigs] != n_events");
+    for (int64_t i = 0; i < n_contigs; i++)
+        if (contig_off[i + 1] < contig_off[i] || ev_off[i + 1] < ev_off[i])
+            return fail(MP2_EINVAL, "offsets must be non-decreasing");
+    MP2_TRY(require_device(device));
+    if (n_contigs == 0) return MP2_OK;
+    Streams st;
+    MP2_TRY(st.init());
+    Temp d_s, d_e, d_eo, d_co, d_cov, d_stats;
+    MP2_TRY(d_s.alloc(sizeof(uint32_t) * n_events, st.comp));
+    MP2_TRY(d_e.alloc(sizeof(uint32_t) * n_events, st.comp));
+    MP2_TRY(d_eo.alloc(sizeof(int64_t) * (n_contigs + 1), st.comp));
+    MP2_TRY(d_co.alloc(sizeof(int64_t) * (n_contigs + 1), st.comp));
+    MP2_TRY(d_cov.alloc(sizeof(float) * n_contigs, st.comp));
+    if (stats) MP2_TRY(d_stats.alloc(sizeof(mp2_cov_stats) * n_contigs, st.comp));
+    MP2_TRY(upload(d_eo.p, ev_off, sizeof(int64_t) * (n_contigs + 1), st.comp));
+    MP2_TRY(upload(d_co.p, contig_off, sizeof(int64_t) * (n_contigs + 1), st.comp));
+    MP2_TRY(upload(d_s.p, starts, sizeof(uint32_t) * n_events, st.comp));
+    MP2_TRY(upload(d_e.p, ends, sizeof(uint32_t) * n_events, st.comp));
+    MP2_TRY(mp2_cov_events_device(d_s.p, d_e.p, d_eo.p, d_co.p, n_contigs, n_events, contig_off[n_contigs],
+                                  end_excl, trim_lower, trim_upper, d_cov.p, 1, d_stats.p, st.comp));
+    MP2_CUDA(cudaStreamSynchronize(st.comp));
+    if (cov_stride == 1) {
+        MP2_TRY(download(cov, d_cov.p, sizeof(float) * n_contigs, st.comp));
+    } else {
+        MP2_CUDA(cudaMemcpy2DAsync(cov, sizeof(float) * cov_stride, d_cov.p, sizeof(float), sizeof(float),
+                                   n_contigs, cudaMemcpyDeviceToHost, st.comp));
+    }
+    if (stats) MP2_TRY(download(stats, d_stats.p, sizeof(mp2_cov_stats) * n_contigs, st.comp));
+    MP2_CUDA(cudaStreamSynchronize(st.comp));
+    return MP2_OK;
+}

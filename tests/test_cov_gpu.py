@@ -1,0 +1,173 @@
+"""GPU parity: coverage path (difference array -> depth -> windowed histogram -> trimmed mean)
+through the C ABI vs the CPU oracle (PARITY UNPINNED w.r.t. coverm itself).
+
+Integers (observed length, covered, min/max index, total = the depth sum, max depth) are compared
+bit-exactly; the coverage is one IEEE f32 division of those integers, compared bit-exactly too."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+INT_FIELDS = ["observed_len", "covered", "total", "max_depth"]
+
+
+@pytest.fixture(scope="module")
+def covmod():
+    from magpurify2_b200 import _coverage
+
+    return _coverage
+
+
+def check_sample(covmod, oracle, starts, ends, ev_off, lengths, excl=75, lo=0.0, up=0.0):
+    lengths = np.asarray(lengths, dtype=np.int64)
+    off = np.zeros(len(lengths) + 1, dtype=np.int64)
+    np.cumsum(lengths, out=off[1:])
+    cov, st = covmod.cov_from_events(starts, ends, ev_off, off, excl, lo, up, want_stats=True)
+    wcov, wst = oracle.cov_sample(starts, ends, ev_off, lengths, excl, lo, up, threads=8)
+    for f in INT_FIELDS:
+        bad = np.nonzero(st[f] != wst[f])[0]
+        assert bad.size == 0, (f, bad[:5], st[f][bad[:5]], wst[f][bad[:5]], lengths[bad[:5]])
+    live = wst["covered"] > 0
+    assert np.array_equal(st["min_index"][live], wst["min_index"][live])
+    assert np.array_equal(st["max_index"][live], wst["max_index"][live])
+    assert np.array_equal(cov.view(np.uint32), wcov.view(np.uint32)) or np.array_equal(cov, wcov, equal_nan=True)
+    assert np.array_equal(st["coverage"], cov, equal_nan=True)
+    return cov, st
+
+
+def test_kats(covmod, oracle, golden_dir):
+    kats = json.load(open(os.path.join(golden_dir, "kats.json")))
+    for length, reads, lo, up, (N, mn, mx, total), want in kats["trimmed_mean"]:
+        starts = np.array([r[0] for r in reads], dtype=np.uint32)
+        ends = np.array([min(r[0] + r[1], length) for r in reads], dtype=np.uint32)
+        cov, st = check_sample(covmod, oracle, starts, ends, [0, len(reads)], [length], 75, lo, up)
+        assert cov[0] == np.float32(want)
+        assert (int(st["observed_len"][0]), int(st["total"][0])) == (N, total)
+
+
+def test_all_kats_in_one_sample(covmod, oracle, golden_dir):
+    """The same vectors as contigs of ONE concatenated sample (tests the -1 landing on the next contig)."""
+    kats = json.load(open(os.path.join(golden_dir, "kats.json")))
+    cases = [k for k in kats["trimmed_mean"] if (k[2], k[3]) == (0.05, 0.05)]
+    starts, ends, ev_off, lengths, want = [], [], [0], [], []
+    for length, reads, lo, up, _ints, w in cases:
+        starts += [r[0] for r in reads]
+        ends += [min(r[0] + r[1], length) for r in reads]
+        ev_off.append(len(starts))
+        lengths.append(length)
+        want.append(w)
+    cov, _ = check_sample(covmod, oracle, starts, ends, ev_off, lengths, 75, 0.05, 0.05)
+    assert np.array_equal(cov, np.array(want, dtype=np.float32))
+
+
+def test_empty_and_ragged(covmod, oracle):
+    # no events at all; zero-length / <=150 bp / 151 bp contigs; events only on some contigs
+    lengths = [0, 1, 150, 151, 152, 0, 3000, 149, 400, 0]
+    check_sample(covmod, oracle, [], [], [0] * 11, lengths, 75, 0.05, 0.05)
+    starts = [0, 0, 100, 2850, 10, 380]
+    ends = [151, 152, 250, 3000, 149, 400]
+    ev_off = [0, 0, 0, 0, 1, 2, 2, 4, 5, 6, 6]
+    for lo, up in [(0.0, 0.0), (0.05, 0.05), (0.3, 0.2)]:
+        check_sample(covmod, oracle, starts, ends, ev_off, lengths, 75, lo, up)
+    check_sample(covmod, oracle, starts, ends, ev_off, lengths, 0, 0.0, 0.0)   # no end exclusion
+    check_sample(covmod, oracle, starts, ends, ev_off, lengths, 10, 0.1, 0.1)
+
+
+def test_synthetic_sample_c2_shape(covmod, oracle):
+    """10 MAGs (~3 Mbp, ~300 contigs each) x one sample of ~4 M reads (BASELINE config 2 shape)."""
+    from magpurify2_b200 import synth
+
+    lengths, mag_off, _gc = synth.mag_layout(10, seed=1)
+    for sample, variable in [(0, False), (1, True)]:
+        st, en, ev_off = synth.make_events(lengths, mag_off, sample, seed=1, variable=variable)
+        check_sample(covmod, oracle, st, en, ev_off, lengths, 75, 0.05, 0.05)
+    st, en, ev_off = synth.make_events(lengths, mag_off, 2, seed=1)
+    check_sample(covmod, oracle, st, en, ev_off, lengths, 75, 0.0, 0.0)
+
+
+def test_long_contigs_span_tiles(covmod, oracle):
+    """Windows spanning many 65536-slot tiles, contig boundaries exactly on / next to tile edges."""
+    rng = np.random.default_rng(21)
+    lengths = [65536, 65536 - 75, 75, 65536 + 76, 1, 300000, 65535, 65537, 1500000, 131072, 200, 65536 * 3]
+    starts, ends, ev_off = [], [], [0]
+    for ln in lengths:
+        n = int(ln * 8 / 150) if ln > 150 else 0
+        s = np.sort(rng.integers(0, max(1, ln - 150), n)) if n else np.zeros(0, np.int64)
+        starts.append(s)
+        ends.append(np.minimum(s + rng.integers(50, 250, n), ln))
+        ev_off.append(ev_off[-1] + n)
+    starts = np.concatenate(starts).astype(np.uint32)
+    ends = np.concatenate(ends).astype(np.uint32)
+    for lo, up in [(0.05, 0.05), (0.0, 0.0)]:
+        check_sample(covmod, oracle, starts, ends, ev_off, lengths, 75, lo, up)
+
+
+def test_deep_coverage_fallback(covmod, oracle):
+    """Depth >= 1023 (the shared-memory histogram's range) and > 8192 (several fallback ranges)."""
+    rng = np.random.default_rng(22)
+    lengths = [5000, 2000, 100000, 800, 40000]
+    depth = [1500, 30, 20000, 1023, 1022]
+    starts, ends, ev_off = [], [], [0]
+    for ln, dp in zip(lengths, depth):
+        n = int(ln * dp / 150)
+        s = np.sort(rng.integers(0, ln - 150, n))
+        starts.append(s)
+        ends.append(s + 150)
+        ev_off.append(ev_off[-1] + n)
+    starts = np.concatenate(starts).astype(np.uint32)
+    ends = np.concatenate(ends).astype(np.uint32)
+    _cov, st = check_sample(covmod, oracle, starts, ends, ev_off, lengths, 75, 0.05, 0.05)
+    assert st["max_depth"][2] > 8192 * 2 and st["max_depth"][0] >= 1023
+    # a pile-up: every read on the same position
+    n = 3000
+    check_sample(covmod, oracle, np.full(n, 500, np.uint32), np.full(n, 650, np.uint32), [0, n, n], [2000, 900],
+                 75, 0.05, 0.05)
+
+
+def test_no_trim_equals_mean_depth(covmod):
+    rng = np.random.default_rng(23)
+    ln = 50000
+    s = np.sort(rng.integers(0, ln - 150, 3000)).astype(np.uint32)
+    cov, st = covmod.cov_from_events(s, s + 150, [0, len(s)], [0, ln], 75, 0.0, 0.0, want_stats=True)
+    d = np.zeros(ln + 1, dtype=np.int64)
+    np.add.at(d, s, 1)
+    np.add.at(d, s + 150, -1)
+    depth = np.cumsum(d)[75:ln - 75]
+    assert int(st["total"][0]) == int(depth.sum())
+    assert cov[0] == np.float32(depth.sum()) / np.float32(len(depth))
+
+
+def test_device_entry_strided_columns(covmod, oracle):
+    """mp2_cov_events_device writing column s of a float32[n_contigs, n_samples] matrix in place."""
+    import torch
+
+    from magpurify2_b200 import _lib, synth
+
+    lengths, mag_off, _gc = synth.mag_layout(3, seed=5, mean_bp=5e5, n_contigs=80)
+    off = np.zeros(len(lengths) + 1, dtype=np.int64)
+    np.cumsum(lengths, out=off[1:])
+    n, S = len(lengths), 3
+    d_off = torch.from_numpy(off).cuda()
+    mat = torch.full((n, S), -1.0, dtype=torch.float32, device="cuda")
+    lib = _lib.load()
+    want = np.zeros((n, S), dtype=np.float32)
+    for s in range(S):
+        st, en, ev_off = synth.make_events(lengths, mag_off, s, seed=5)
+        want[:, s], _ = oracle.cov_sample(st, en, ev_off, lengths, 75, 0.05, 0.05, threads=4)
+        d_st = torch.from_numpy(st.view(np.int32)).cuda()
+        d_en = torch.from_numpy(en.view(np.int32)).cuda()
+        d_eo = torch.from_numpy(ev_off).cuda()
+        _lib.check(lib.mp2_cov_events_device(d_st.data_ptr(), d_en.data_ptr(), d_eo.data_ptr(), d_off.data_ptr(),
+                                             n, len(st), int(off[-1]), 75, 0.05, 0.05,
+                                             mat.data_ptr() + 4 * s, S, None,
+                                             torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(mat.cpu().numpy(), want)
+
+
+def test_rejects_bad_trim(covmod):
+    with pytest.raises(ValueError):
+        covmod.cov_from_events([], [], [0, 0], [0, 1000], 75, 0.6, 0.5)
