@@ -96,6 +96,132 @@ def cpu_tnf_sample(oracle, bases, offsets, mag_off, n_mags, threads):
     return dt, b1, counts, gc
 
 
+def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
+    """Second metric of BASELINE.json: aligned reads/s of the coverage path.  One step = all S
+    samples of this rank's MAGs: events (start, end) resident in HBM -> float32[n_contigs, S]."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from magpurify2_b200 import _coverage, _lib, synth
+
+    lengths, mag_off, offsets = d["lengths"], d["mag_off"], d["offsets"]
+    n, L, S = len(lengths), int(offsets[-1]), args.samples
+    stream = torch.cuda.current_stream().cuda_stream
+    samples = []
+    R_total = 0
+    for s in range(S):
+        st, en, eo, R = synth.make_events_device(lengths, mag_off, s, dev, seed=args.seed + 1000 * rank,
+                                                 depth_scale=args.depth_scale)
+        samples.append((st, en, eo, R))
+        R_total += R
+    cov = torch.empty((n, S), dtype=torch.float32, device=dev)
+
+    def step():
+        for s, (st, en, eo, R) in enumerate(samples):
+            _lib.check(lib.mp2_cov_events_device(st.data_ptr(), en.data_ptr(), eo.data_ptr(), d_off.data_ptr(),
+                                                 n, R, L, 75, args.trim, args.trim,
+                                                 cov.data_ptr() + 4 * s, S, None, stream))
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    lib.mp2_profile_reset()
+    lib.mp2_profile_enable(1)
+    l0 = lib.mp2_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.mp2_launch_count() - l0
+    kern = {}
+    for name in ("cov_scatter_kernel", "cov_depth_kernel", "cov_deep_kernel", "cov_tile_scan_kernel"):
+        k_ms, k_n = C.c_double(0), C.c_int64(0)
+        lib.mp2_profile_read(name.encode(), C.byref(k_ms), C.byref(k_n))
+        kern[name] = (k_ms.value, k_n.value)
+    lib.mp2_profile_enable(0)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tot = torch.tensor([float(R_total)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot)
+        R_all = float(tot.item())
+    else:
+        R_all = float(R_total)
+    value = R_all * args.steps / (ms * 1e-3)
+
+    # end to end: one sample through the host-buffer API (pinned events in, coverage column out)
+    st, en, eo, R0 = samples[0]
+    h_st = torch.empty(R0, dtype=torch.int32, pin_memory=True); h_st.copy_(st)
+    h_en = torch.empty(R0, dtype=torch.int32, pin_memory=True); h_en.copy_(en)
+    torch.cuda.synchronize()
+    h_eo = eo.cpu().numpy()
+    a_st, a_en = h_st.numpy().view(np.uint32), h_en.numpy().view(np.uint32)
+    _coverage.cov_from_events(a_st, a_en, h_eo, offsets, 75, args.trim, args.trim, device=local)
+    barrier()
+    t0 = time.perf_counter()
+    h_cov = _coverage.cov_from_events(a_st, a_en, h_eo, offsets, 75, args.trim, args.trim, device=local)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s, float(R0)], dtype=torch.float64, device=dev)
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t)
+        e2e_val = float(t[1].item()) / float(tm[0].item())
+    else:
+        e2e_val = R0 / e2e_s
+    assert np.array_equal(h_cov, cov[:, 0].cpu().numpy(), equal_nan=True)
+    if rank != 0:
+        return None
+    peak, peak_src = peaks()
+    per_launch = lambda k: kern[k][0] / max(1, kern[k][1])
+    R_avg = R_total / S
+    rl = []
+    for name, bytes_ in (("cov_depth_kernel", 4.0 * (L + 1)), ("cov_scatter_kernel", 8.0 * R_avg + 8.0 * R_avg)):
+        t_ms = per_launch(name)
+        ach = bytes_ / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+        rl.append({"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                   "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": bytes_,
+                   "kernel_ms": t_ms, "launches_timed": kern[name][1]})
+    dom = max(rl, key=lambda r: r["kernel_ms"])
+    rec = {
+        "metric": "aligned reads/s coverage", "value": value, "unit": "reads/s", "ms_per_step": ms / args.steps,
+        "config": {"workload": f"C3: coverage of {args.mags} MAGs x {S} samples per GPU, {R_total / S / 1e6:.0f} M aligned blocks/sample",
+                   "samples": S, "reads_per_step": R_total, "positions": L, "trim": args.trim, "end_exclusion": 75,
+                   "input": "(start,end) uint32 pairs grouped by contig, resident in HBM"},
+        "roofline": dict(dom, peak_source=peak_src), "kernels": rl,
+        "sample_bytes_algorithmic": 8.0 * L + 20.0 * R_avg,
+        "sample_gbs": (8.0 * L + 20.0 * R_avg) / (ms / args.steps / S * 1e-3) / 1e9,
+        "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": 8 * R0 + 16 * (n + 1),
+                "d2h_bytes_per_step": 4 * n, "steps": 1,
+                "api": "magpurify2_b200._coverage.cov_from_events (mp2_cov_events, pinned host buffers, 1 sample)"},
+        "gpu_launches": int(launches),
+        "deep_fallback_ms": kern["cov_deep_kernel"][0] / max(1, kern["cov_deep_kernel"][1]),
+    }
+    if not args.no_cpu:
+        import oracle
+
+        m = min(args.mags, max(1, args.ref_mags // 5))
+        c1 = int(mag_off[m])
+        e1_ = int(h_eo[c1])
+        t0 = time.perf_counter()
+        c_cov, _ = oracle.cov_sample(a_st[:e1_], a_en[:e1_], h_eo[:c1 + 1], lengths[:c1], 75, args.trim, args.trim, threads=1)
+        dt = time.perf_counter() - t0
+        ok = bool(np.array_equal(c_cov, h_cov[:c1], equal_nan=True))
+        rec["cpu_baseline"] = {"value": e1_ / dt, "unit": "reads/s", "cores": 1, "kind": "port",
+                               "sample": f"sample 0, first {m} MAGs ({e1_ / 1e6:.1f} M blocks, {int(offsets[c1]) / 1e6:.0f} Mbp); "
+                                         "single thread per sample as coverm's record loop is (events already decoded)",
+                               "parity_with_gpu": ok}
+        if not ok:
+            raise SystemExit("PARITY FAILURE: GPU coverage differs from the CPU oracle")
+    return rec
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -144,6 +270,8 @@ def main():
     ap.add_argument("--ref-mags", type=int, default=100, help="MAGs per step of the CPU arms")
     ap.add_argument("--long-contigs", action="store_true", help="C5 shape instead of C3")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--trim", type=float, default=0.05)
+    ap.add_argument("--depth-scale", type=float, default=1.0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -224,6 +352,11 @@ def main():
         L_all = float(L)
     value = L_all * args.steps / (ms * 1e-3) / 1e9
 
+    # ---- coverage phase: S samples of device-resident alignment blocks ----
+    cov_rec = None
+    if args.samples > 0:
+        cov_rec = coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier)
+
     # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region) ----
     h_bases = torch.empty(L, dtype=torch.uint8, pin_memory=True)
     h_bases.copy_(bases)
@@ -274,9 +407,11 @@ def main():
                      "launches_timed": k_n.value, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "magpurify2_b200._composition.tnf_from_concat (mp2_tnf, pinned host buffers)"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) + (cov_rec["gpu_launches"] if cov_rec else 0),
         "clocks": clocks,
     }
+    if cov_rec:
+        line["coverage"] = cov_rec
 
     if not args.no_cpu:
         import oracle

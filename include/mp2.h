@@ -130,16 +130,24 @@ int mp2_cov_events(const uint32_t *starts, const uint32_t *ends, const int64_t *
 /* data: float32 row-major [n_rows, n_cols] for ALL MAGs stacked; MAG m owns rows
  * mag_off[m] .. mag_off[m+1]; weights: int64[n_rows] (contig lengths).
  * col_mask: uint8[n_mags*n_cols] (1 = column takes part for that MAG) or NULL = all.
+ * base / pseudo / clip_lo / clip_hi: get_log_ratio_scores' base, pseudo (1e-5), min (0), max (1).
+ * min_rows: MAGs with fewer rows are not scored and get 1.0 -- 3 reproduces core.py:248-250 and
+ *           :306-308 ("len(self) <= 2"), 1 is the bare function.
+ * one_sided: 0 = the reference formula; 1 = only values above the median are penalised (used
+ *           for the centroid-distance score, which the reference does not have).
  *   scores  : float64[n_rows]  row mean over the selected columns of
- *             1 - |ln((x+1e-5)/(median+1e-5)) / ln(base)|, clipped to [0,1];
- *             MAGs with <= 2 rows or no selected column get 1.0 (core.py:248-250, 306-308)
- *   medians : float32[n_mags*n_cols] weighted medians, or NULL                             */
+ *             1 - |ln((x+pseudo)/(median+pseudo)) / ln(base)|, clipped; MAGs with no selected
+ *             column get 1.0
+ *   medians : float32[n_mags*n_cols] weighted medians (NaN where not computed), or NULL        */
 int mp2_logratio_device(const void *d_data, const void *d_weights, const void *d_mag_off,
                         int64_t n_mags, int64_t n_rows, int64_t n_cols, const void *d_col_mask,
-                        double base, void *d_scores, void *d_medians, void *stream);
+                        double base, float pseudo, double clip_lo, double clip_hi,
+                        int64_t min_rows, int one_sided, void *d_scores, void *d_medians,
+                        void *stream);
 int mp2_logratio(const float *data, const int64_t *weights, const int64_t *mag_off,
                  int64_t n_mags, int64_t n_rows, int64_t n_cols, const uint8_t *col_mask,
-                 double base, int device, double *scores, float *medians);
+                 double base, float pseudo, double clip_lo, double clip_hi, int64_t min_rows,
+                 int one_sided, int device, double *scores, float *medians);
 
 /* core.Coverage sample selection (core.py:301-305): length-weighted mean per (MAG, column)
  * in f64, selected = mean >= min_average_coverage.  sel: uint8[n_mags*n_cols]. */
@@ -182,6 +190,8 @@ void mp2_bam_close(mp2_bam *b);
  * header with '~' -> '_'.  Sequence bytes are concatenated with line ends removed. */
 typedef struct mp2_fasta mp2_fasta;
 int mp2_fasta_open(const char *path, mp2_fasta **out);
+/* Same parser on a FASTA text already in memory (bzip2 / xz inputs are decompressed by the caller). */
+int mp2_fasta_open_mem(const uint8_t *data, int64_t size, mp2_fasta **out);
 int64_t mp2_fasta_n(const mp2_fasta *f);
 const uint8_t *mp2_fasta_bases(const mp2_fasta *f);
 const int64_t *mp2_fasta_offsets(const mp2_fasta *f);

@@ -37,3 +37,41 @@ def cov_from_events(starts, ends, ev_off, contig_off, contig_end_exclusion=75, t
                                   n, len(starts), int(contig_end_exclusion), float(trim_lower),
                                   float(trim_upper), device, _lib.ptr(cov), 1, _lib.ptr(stats)))
     return (cov, stats) if want_stats else cov
+
+
+def get_bam_coverages(bam_list, contig_end_exclusion=75, min_identity=0.97, trim_lower=0.0, trim_upper=0.0,
+                      contig_set=None, threads=1):
+    """Trimmed-mean coverage of every contig in every BAM (src/coverage.rs:81-206).
+
+    Returns (names, float32[n_contigs, n_bams]); columns follow bam_list.  Rows follow the @SQ
+    order of the first BAM (the reference returns them in Rust HashMap order, i.e. arbitrary:
+    callers index by name, magpurify2/modules/coverage.py:113-119)."""
+    from . import _bam
+
+    if isinstance(bam_list, (str, bytes)):
+        raise TypeError("bam_list must be a list of paths")
+    bam_list = [str(b) for b in bam_list]
+    if not bam_list:
+        raise ValueError("bam_list is empty")
+    names = None
+    cols = []
+    for path in bam_list:
+        with _bam.BamEvents(path, min_identity=min_identity, threads=threads) as b:
+            if names is None:
+                names, lengths = b.names, b.lengths
+                contig_off = np.zeros(len(lengths) + 1, dtype=np.int64)
+                np.cumsum(lengths, out=contig_off[1:])
+            elif b.names != names:
+                raise ValueError(f"{path}: @SQ lines differ from {bam_list[0]} (the reference assumes identical headers)")
+            cols.append(cov_from_events(b.starts, b.ends, b.ev_off, contig_off, contig_end_exclusion,
+                                        trim_lower, trim_upper))
+    if not names:
+        raise ValueError("no reference sequences in the BAM header")  # the reference panics (coverage.rs:200)
+    mat = np.stack(cols, axis=1).astype(np.float32, copy=False)
+    if contig_set is not None:
+        keep = np.fromiter((nm in contig_set for nm in names), dtype=bool, count=len(names))
+        names = [nm for nm, k in zip(names, keep) if k]
+        mat = mat[keep]
+        if not names:
+            raise ValueError("contig_set matches no reference sequence")
+    return names, np.ascontiguousarray(mat)

@@ -67,8 +67,8 @@ SIGNATURES = {
     "mp2_pack_device": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "mp2_cov_events_device": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _u32, _f32, _f32, _vp, _i64, _vp, _vp]),
     "mp2_cov_events": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _u32, _f32, _f32, _i32, _vp, _i64, _vp]),
-    "mp2_logratio_device": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _f64, _vp, _vp, _vp]),
-    "mp2_logratio": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _f64, _i32, _vp, _vp]),
+    "mp2_logratio_device": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _f64, _f32, _f64, _f64, _i64, _i32, _vp, _vp, _vp]),
+    "mp2_logratio": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _f64, _f32, _f64, _f64, _i64, _i32, _i32, _vp, _vp]),
     "mp2_select_samples_device": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _f64, _vp, _vp, _vp]),
     "mp2_clr_centroid_device": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "mp2_bam_open": (_i32, [C.c_char_p, _f32, _i32, C.POINTER(_vp)]),
@@ -85,6 +85,7 @@ SIGNATURES = {
     "mp2_bam_header_text": (_vp, [_vp, C.POINTER(_i64)]),
     "mp2_bam_close": (None, [_vp]),
     "mp2_fasta_open": (_i32, [C.c_char_p, C.POINTER(_vp)]),
+    "mp2_fasta_open_mem": (_i32, [_vp, _i64, C.POINTER(_vp)]),
     "mp2_fasta_n": (_i64, [_vp]),
     "mp2_fasta_bases": (_vp, [_vp]),
     "mp2_fasta_offsets": (_vp, [_vp]),
@@ -108,9 +109,7 @@ def load():
         )
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name, None)
-        if fn is None:  # TODO(round 1): strict once every entry point is implemented
-            continue
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
     _lib = lib

@@ -1,0 +1,415 @@
+// Host-side BAM ingest: BGZF inflate (zlib, parallel over blocks) + record filter + alignment-block
+// extraction.  Replaces htslib + coverm's ReferenceSortedBamFilter / CIGAR walk under
+// _coverage.get_bam_coverages (/root/reference/src/coverage.rs:102-142).
+// BAM decoding stays on host threads (north_star); the output (start, end) arrays are pinned so
+// they can be copied to the device asynchronously.
+#include <fcntl.h>
+#include <omp.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <atomic>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mp2_common.h"
+
+struct mp2_bam {
+    std::vector<std::string> names;
+    std::vector<int64_t> lens;
+    std::vector<int64_t> ev_off;
+    uint32_t *starts = nullptr, *ends = nullptr;
+    bool pinned = false;
+    int64_t n_events = 0, n_records = 0, n_kept = 0;
+    uint32_t max_span = 0;
+    std::string header_text;
+};
+
+namespace mp2 {
+
+struct Block {
+    int64_t coff;   // offset of the block in the file
+    uint32_t csize; // whole block size
+    uint32_t usize; // ISIZE
+};
+
+static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline int32_t rds32(const uint8_t *p) { int32_t v; memcpy(&v, p, 4); return v; }
+static inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+// Index of the BGZF blocks (SAM spec 4.1: gzip member with a 'BC' extra subfield holding BSIZE-1).
+static int index_blocks(const uint8_t *f, int64_t size, std::vector<Block> &blocks, const char *path) {
+    int64_t o = 0;
+    while (o < size) {
+        if (size - o < 28) return fail(MP2_EIO, "%s: truncated BGZF block header at %lld", path, (long long)o);
+        const uint8_t *h = f + o;
+        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4))
+            return fail(MP2_EIO, "%s: not a BGZF file (bad gzip member at %lld)", path, (long long)o);
+        const uint32_t xlen = rd16(h + 10);
+        int64_t bsize = -1;
+        for (uint32_t x = 0; x + 4 <= xlen;) {
+            const uint8_t *s = h + 12 + x;
+            const uint32_t slen = rd16(s + 2);
+            if (s[0] == 'B' && s[1] == 'C' && slen == 2) bsize = (int64_t)rd16(s + 4) + 1;
+            x += 4 + slen;
+        }
+        if (bsize < 0 || o + bsize > size)
+            return fail(MP2_EIO, "%s: BGZF block at %lld has no BC field or runs past the end", path, (long long)o);
+        Block b;
+        b.coff = o;
+        b.csize = (uint32_t)bsize;
+        b.usize = rd32(f + o + bsize - 4);
+        if (b.usize > 65536) return fail(MP2_EIO, "%s: BGZF block larger than 64 KiB", path);
+        blocks.push_back(b);
+        o += bsize;
+    }
+    return MP2_OK;
+}
+
+static bool inflate_block(const uint8_t *f, const Block &b, uint8_t *dst) {
+    if (b.usize == 0) return true;
+    const uint32_t xlen = rd16(f + b.coff + 10);
+    const uint8_t *src = f + b.coff + 12 + xlen;
+    const int64_t clen = (int64_t)b.csize - 12 - xlen - 8;
+    if (clen < 0) return false;
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<Bytef *>(src);
+    zs.avail_in = (uInt)clen;
+    zs.next_out = dst;
+    zs.avail_out = b.usize;
+    const int rc = inflate(&zs, Z_FINISH);
+    const bool ok = (rc == Z_STREAM_END) && zs.total_out == b.usize;
+    inflateEnd(&zs);
+    return ok;
+}
+
+// One record -> alignment blocks, straight from the BAM wire format.
+// Returns the number of M/=/X blocks (0 = dropped),
+// -1 = NM tag missing, -2 = malformed.  The first block goes to (s0, e0).
+static int record_blocks(const uint8_t *r, uint32_t block_size, float min_identity, int32_t &tid, uint32_t &s0,
+                         uint32_t &e0, uint32_t *more_s, uint32_t *more_e, int max_more) {
+    if (block_size < 32) return -2;
+    tid = rds32(r);
+    const int32_t pos = rds32(r + 4);
+    const uint32_t l_read_name = r[8];
+    const uint32_t n_cigar = rd16(r + 12);
+    const uint32_t flag = rd16(r + 14);
+    const uint32_t l_seq = rd32(r + 16);
+    const uint64_t fixed = 32ull + l_read_name + 4ull * n_cigar + (l_seq + 1) / 2 + l_seq;
+    if (fixed > block_size) return -2;
+    if (flag & 0x100) return 0;  // secondary      (src/coverage.rs:104)
+    if (flag & 0x800) return 0;  // supplementary  (src/coverage.rs:105)
+    if ((flag & 0x4) || tid < 0 || pos < 0) return 0;  // unmapped: contributes nothing
+    const uint8_t *cig = r + 32 + l_read_name;
+    if (min_identity > 0.0f) {
+        // NM aux tag (required, as in coverm: the reference panics without it)
+        const uint8_t *a = r + fixed, *end = r + block_size;
+        int64_t nm = -1;
+        while (a + 3 <= end) {
+            const uint8_t t0 = a[0], t1 = a[1], ty = a[2];
+            a += 3;
+            int64_t val = 0;
+            size_t sz = 0;
+            switch (ty) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'Z': case 'H': {
+                const uint8_t *z = (const uint8_t *)memchr(a, 0, end - a);
+                if (!z) return -2;
+                sz = (z - a) + 1;
+                break;
+            }
+            case 'B': {
+                if (a + 5 > end) return -2;
+                const uint8_t st = a[0];
+                const uint32_t cnt = rd32(a + 1);
+                const size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+                sz = 5 + es * (size_t)cnt;
+                break;
+            }
+            default: return -2;
+            }
+            if (a + sz > end) return -2;
+            if (t0 == 'N' && t1 == 'M') {
+                switch (ty) {
+                case 'c': val = (int8_t)a[0]; break;
+                case 'C': val = a[0]; break;
+                case 's': val = (int16_t)rd16(a); break;
+                case 'S': val = rd16(a); break;
+                case 'i': val = rds32(a); break;
+                case 'I': val = rd32(a); break;
+                default: return -2;
+                }
+                nm = val;
+                break;
+            }
+            a += sz;
+        }
+        if (nm < 0) return -1;
+        uint32_t aligned = 0;
+        for (uint32_t i = 0; i < n_cigar; i++) {
+            const uint32_t c = rd32(cig + 4 * i), op = c & 0xF, l = c >> 4;
+            if (op == 0 || op == 1 || op == 7 || op == 8) aligned += l;  // M I = X
+        }
+        volatile float q = (float)nm / (float)aligned;
+        volatile float ident = 1.0f - q;
+        if (!(ident >= min_identity)) return 0;
+    }
+    int nb = 0;
+    uint32_t cursor = (uint32_t)pos;
+    for (uint32_t i = 0; i < n_cigar; i++) {
+        const uint32_t c = rd32(cig + 4 * i), op = c & 0xF, l = c >> 4;
+        if (op == 0 || op == 7 || op == 8) {  // M = X
+            if (nb == 0) { s0 = cursor; e0 = cursor + l; }
+            else if (nb - 1 < max_more) { more_s[nb - 1] = cursor; more_e[nb - 1] = cursor + l; }
+            nb++;
+            cursor += l;
+        } else if (op == 2 || op == 3) {  // D N
+            cursor += l;
+        }  // I S H P: nothing
+    }
+    return nb;
+}
+
+static void *host_alloc(size_t bytes, bool &pinned) {
+    void *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) {
+        pinned = true;
+        return p;
+    }
+    (void)cudaGetLastError();
+    pinned = false;
+    return malloc(bytes);
+}
+
+}  // namespace mp2
+
+using namespace mp2;
+
+extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, mp2_bam **out) {
+    if (!path || !out) return fail(MP2_EINVAL, "NULL argument");
+    *out = nullptr;
+    if (threads < 1) threads = 1;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(MP2_EIO, "cannot open %s", path);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size <= 0) {
+        close(fd);
+        return fail(MP2_EIO, "cannot stat %s (or it is empty)", path);
+    }
+    const int64_t size = sb.st_size;
+    const uint8_t *f = (const uint8_t *)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (f == MAP_FAILED) return fail(MP2_EIO, "cannot mmap %s", path);
+    struct Unmap {
+        const uint8_t *p; int64_t n;
+        ~Unmap() { munmap((void *)p, n); }
+    } unmap{f, size};
+    madvise((void *)f, size, MADV_SEQUENTIAL);
+
+    std::vector<Block> blocks;
+    MP2_TRY(index_blocks(f, size, blocks, path));
+
+    mp2_bam *b = new mp2_bam();
+    struct Guard {
+        mp2_bam *b;
+        ~Guard() { if (b) mp2_bam_close(b); }
+    } guard{b};
+
+    std::vector<uint8_t> buf;          // uncompressed window (leftover + batch)
+    std::vector<uint32_t> ev_s, ev_e;  // accepted blocks in BAM order
+    std::vector<int64_t> per_tid;
+    const int64_t BATCH = 256ll << 20;
+    size_t bi = 0;
+    int64_t have = 0;   // valid bytes in buf
+    bool header_done = false;
+    int64_t last_tid = -1;
+    std::vector<int64_t> rec_off;
+    std::vector<int32_t> rec_tid;
+    std::vector<int32_t> rec_n;
+    std::vector<uint32_t> rec_s, rec_e;
+
+    while (bi < blocks.size() || have > 0) {
+        // ---- inflate the next batch of blocks behind the leftover bytes ----
+        size_t bj = bi;
+        int64_t add = 0;
+        while (bj < blocks.size() && (add == 0 || add + blocks[bj].usize <= BATCH)) add += blocks[bj++].usize;
+        buf.resize(have + add);
+        std::vector<int64_t> uoff(bj - bi + 1, have);
+        for (size_t k = bi; k < bj; k++) uoff[k - bi + 1] = uoff[k - bi] + blocks[k].usize;
+        std::atomic<int> bad{0};
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads)
+        for (int64_t k = (int64_t)bi; k < (int64_t)bj; k++)
+            if (!inflate_block(f, blocks[k], buf.data() + uoff[k - bi])) bad = 1;
+        if (bad) return fail(MP2_EIO, "%s: corrupt BGZF block (inflate failed)", path);
+        const bool last_batch = bj == blocks.size();
+        bi = bj;
+        have += add;
+        const uint8_t *p = buf.data();
+        int64_t o = 0;
+        // ---- header ----
+        if (!header_done) {
+            if (have < 12) {
+                if (last_batch) return fail(MP2_EIO, "%s: truncated BAM header", path);
+                continue;
+            }
+            if (memcmp(p, "BAM\1", 4) != 0) return fail(MP2_EIO, "%s: not a BAM file (bad magic)", path);
+            const int64_t l_text = rds32(p + 4);
+            if (l_text < 0 || 12 + l_text > have) {
+                if (last_batch) return fail(MP2_EIO, "%s: truncated BAM header", path);
+                continue;  // header larger than one batch: keep accumulating
+            }
+            const int64_t n_ref = rds32(p + 8 + l_text);
+            int64_t q = 12 + l_text;
+            bool complete = n_ref >= 0;
+            std::vector<std::string> names;
+            std::vector<int64_t> lens;
+            for (int64_t r = 0; complete && r < n_ref; r++) {
+                if (q + 4 > have) { complete = false; break; }
+                const int64_t l_name = rds32(p + q);
+                if (l_name < 1 || q + 4 + l_name + 4 > have) { complete = false; break; }
+                names.emplace_back((const char *)p + q + 4, (size_t)l_name - 1);
+                lens.push_back((int64_t)rd32(p + q + 4 + l_name));
+                q += 8 + l_name;
+            }
+            if (!complete) {
+                if (last_batch) return fail(MP2_EIO, "%s: truncated BAM reference list", path);
+                continue;
+            }
+            b->header_text.assign((const char *)p + 8, (size_t)l_text);
+            b->names.swap(names);
+            b->lens.swap(lens);
+            per_tid.assign(b->names.size(), 0);
+            header_done = true;
+            o = q;
+        }
+        // ---- record boundaries (sequential hop), then parallel filter ----
+        rec_off.clear();
+        while (o + 4 <= have) {
+            const int64_t bs = rd32(p + o);
+            if (o + 4 + bs > have) break;
+            rec_off.push_back(o);
+            o += 4 + bs;
+        }
+        const int64_t nr = (int64_t)rec_off.size();
+        rec_tid.resize(nr);
+        rec_n.resize(nr);
+        rec_s.resize(nr);
+        rec_e.resize(nr);
+        std::atomic<int> err{0};
+#pragma omp parallel for schedule(static) num_threads(threads)
+        for (int64_t i = 0; i < nr; i++) {
+            const uint8_t *r = p + rec_off[i];
+            int32_t tid = -1;
+            uint32_t s0 = 0, e0 = 0;
+            const int k = record_blocks(r + 4, rd32(r), min_identity, tid, s0, e0, nullptr, nullptr, 0);
+            if (k < 0) err = k == -1 ? 1 : 2;
+            rec_tid[i] = tid;
+            rec_n[i] = k;
+            rec_s[i] = s0;
+            rec_e[i] = e0;
+        }
+        if (err == 1)
+            return fail(MP2_EFORMAT, "%s: a mapped record has no NM tag (needed for the identity filter; "
+                        "the reference panics here)", path);
+        if (err) return fail(MP2_EIO, "%s: malformed BAM record", path);
+        for (int64_t i = 0; i < nr; i++) {
+            b->n_records++;
+            const int k = rec_n[i];
+            if (k <= 0) continue;
+            const int64_t tid = rec_tid[i];
+            if (tid >= (int64_t)b->names.size()) return fail(MP2_EIO, "%s: record refers to an unknown reference", path);
+            if (tid < last_tid)
+                return fail(MP2_EFORMAT, "%s: records are not sorted by reference (SO:coordinate required)", path);
+            last_tid = tid;
+            b->n_kept++;
+            if (k == 1) {
+                ev_s.push_back(rec_s[i]);
+                ev_e.push_back(rec_e[i]);
+                const uint32_t span = rec_e[i] - rec_s[i];
+                if (span > b->max_span) b->max_span = span;
+            } else {
+                std::vector<uint32_t> ms(k), me(k);
+                int32_t t2; uint32_t s0, e0;
+                const uint8_t *r = p + rec_off[i];
+                record_blocks(r + 4, rd32(r), min_identity, t2, s0, e0, ms.data(), me.data(), k - 1);
+                ev_s.push_back(s0); ev_e.push_back(e0);
+                for (int x = 0; x < k - 1; x++) { ev_s.push_back(ms[x]); ev_e.push_back(me[x]); }
+                const uint32_t span = me[k - 2] - s0;  // the whole read footprint bounds every block
+                if (span > b->max_span) b->max_span = span;
+            }
+            per_tid[tid] += k;
+        }
+        // ---- keep the partial record for the next batch ----
+        const int64_t left = have - o;
+        if (left > 0 && last_batch) {
+            return fail(MP2_EIO, "%s: truncated BAM record at end of file", path);
+        }
+        if (left > 0) memmove(buf.data(), buf.data() + o, left);
+        have = left;
+        if (last_batch) break;
+    }
+    if (!header_done) return fail(MP2_EIO, "%s: no BAM header", path);
+
+    const int64_t n = (int64_t)b->names.size();
+    b->ev_off.assign(n + 1, 0);
+    for (int64_t i = 0; i < n; i++) b->ev_off[i + 1] = b->ev_off[i] + per_tid[i];
+    b->n_events = (int64_t)ev_s.size();
+    bool pin1 = false, pin2 = false;
+    b->starts = (uint32_t *)host_alloc(sizeof(uint32_t) * ev_s.size(), pin1);
+    b->ends = (uint32_t *)host_alloc(sizeof(uint32_t) * ev_e.size(), pin2);
+    if (!b->starts || !b->ends) return fail(MP2_ENOMEM, "out of host memory for %lld events", (long long)b->n_events);
+    b->pinned = pin1 && pin2;
+    if (pin1 != pin2) {  // keep the free path simple: both pinned or both malloc'ed
+        if (pin1) { cudaFreeHost(b->starts); b->starts = (uint32_t *)malloc(sizeof(uint32_t) * ev_s.size() + 16); }
+        if (pin2) { cudaFreeHost(b->ends); b->ends = (uint32_t *)malloc(sizeof(uint32_t) * ev_e.size() + 16); }
+        b->pinned = false;
+    }
+    if (!ev_s.empty()) {
+        memcpy(b->starts, ev_s.data(), sizeof(uint32_t) * ev_s.size());
+        memcpy(b->ends, ev_e.data(), sizeof(uint32_t) * ev_e.size());
+    }
+    guard.b = nullptr;
+    *out = b;
+    return MP2_OK;
+}
+
+extern "C" {
+
+int64_t mp2_bam_n_contigs(const mp2_bam *b) { return b ? (int64_t)b->names.size() : 0; }
+int64_t mp2_bam_n_events(const mp2_bam *b) { return b ? b->n_events : 0; }
+int64_t mp2_bam_n_records(const mp2_bam *b) { return b ? b->n_records : 0; }
+int64_t mp2_bam_n_kept(const mp2_bam *b) { return b ? b->n_kept : 0; }
+uint32_t mp2_bam_max_span(const mp2_bam *b) { return b ? b->max_span : 0; }
+const char *mp2_bam_contig_name(const mp2_bam *b, int64_t i) {
+    return (b && i >= 0 && i < (int64_t)b->names.size()) ? b->names[i].c_str() : nullptr;
+}
+const int64_t *mp2_bam_contig_len(const mp2_bam *b) { return b ? b->lens.data() : nullptr; }
+const int64_t *mp2_bam_ev_off(const mp2_bam *b) { return b ? b->ev_off.data() : nullptr; }
+const uint32_t *mp2_bam_starts(const mp2_bam *b) { return b ? b->starts : nullptr; }
+const uint32_t *mp2_bam_ends(const mp2_bam *b) { return b ? b->ends : nullptr; }
+const char *mp2_bam_header_text(const mp2_bam *b, int64_t *len) {
+    if (!b) return nullptr;
+    if (len) *len = (int64_t)b->header_text.size();
+    return b->header_text.data();
+}
+void mp2_bam_close(mp2_bam *b) {
+    if (!b) return;
+    if (b->pinned) {
+        if (b->starts) cudaFreeHost(b->starts);
+        if (b->ends) cudaFreeHost(b->ends);
+    } else {
+        free(b->starts);
+        free(b->ends);
+    }
+    delete b;
+}
+
+}  // extern "C"

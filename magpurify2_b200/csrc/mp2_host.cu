@@ -221,3 +221,37 @@ extern "C" int mp2_cov_events(const uint32_t *starts, const uint32_t *ends, cons
     MP2_CUDA(cudaStreamSynchronize(st.comp));
     return MP2_OK;
 }
+
+extern "C" int mp2_logratio(const float *data, const int64_t *weights, const int64_t *mag_off,
+                            int64_t n_mags, int64_t n_rows, int64_t n_cols, const uint8_t *col_mask,
+                            double base, float pseudo, double clip_lo, double clip_hi, int64_t min_rows,
+                            int one_sided, int device, double *scores, float *medians) {
+    if (n_mags < 0 || n_rows < 0 || n_cols < 1) return fail(MP2_EINVAL, "bad shape");
+    if (!mag_off || !scores || (n_rows > 0 && (!data || !weights))) return fail(MP2_EINVAL, "NULL argument");
+    if (mag_off[0] != 0 || mag_off[n_mags] != n_rows) return fail(MP2_EINVAL, "mag_off must span [0, n_rows]");
+    for (int64_t i = 0; i < n_mags; i++)
+        if (mag_off[i + 1] < mag_off[i]) return fail(MP2_EINVAL, "mag_off must be non-decreasing");
+    MP2_TRY(require_device(device));
+    if (n_rows == 0) return MP2_OK;
+    Streams st;
+    MP2_TRY(st.init());
+    Temp d_data, d_w, d_mo, d_mask, d_sc, d_med;
+    MP2_TRY(d_data.alloc(sizeof(float) * n_rows * n_cols, st.comp));
+    MP2_TRY(d_w.alloc(sizeof(int64_t) * n_rows, st.comp));
+    MP2_TRY(d_mo.alloc(sizeof(int64_t) * (n_mags + 1), st.comp));
+    MP2_TRY(d_sc.alloc(sizeof(double) * n_rows, st.comp));
+    MP2_TRY(d_med.alloc(sizeof(float) * n_mags * n_cols, st.comp));
+    if (col_mask) {
+        MP2_TRY(d_mask.alloc(n_mags * n_cols, st.comp));
+        MP2_TRY(upload(d_mask.p, col_mask, n_mags * n_cols, st.comp));
+    }
+    MP2_TRY(upload(d_data.p, data, sizeof(float) * n_rows * n_cols, st.comp));
+    MP2_TRY(upload(d_w.p, weights, sizeof(int64_t) * n_rows, st.comp));
+    MP2_TRY(upload(d_mo.p, mag_off, sizeof(int64_t) * (n_mags + 1), st.comp));
+    MP2_TRY(mp2_logratio_device(d_data.p, d_w.p, d_mo.p, n_mags, n_rows, n_cols, col_mask ? d_mask.p : nullptr,
+                                base, pseudo, clip_lo, clip_hi, min_rows, one_sided, d_sc.p, d_med.p, st.comp));
+    MP2_TRY(download(scores, d_sc.p, sizeof(double) * n_rows, st.comp));
+    if (medians) MP2_TRY(download(medians, d_med.p, sizeof(float) * n_mags * n_cols, st.comp));
+    MP2_CUDA(cudaStreamSynchronize(st.comp));
+    return MP2_OK;
+}

@@ -1,0 +1,367 @@
+// Per-MAG scoring on sm_100a: length-weighted median + log-ratio scores, sample selection,
+// CLR / centroid distance.
+//
+// Replaces tools.get_weighted_median / tools.get_log_ratio_scores
+// (/root/reference/magpurify2/tools.py:283-311, 314-351) and the glue in core.Composition /
+// core.Coverage that sits directly on the native outputs (magpurify2/core.py:248-263, 301-312).
+// All MAGs of a batch are stacked row-wise; MAG m owns rows mag_off[m] .. mag_off[m+1].
+#include <cfloat>
+
+#include "mp2_common.h"
+
+namespace mp2 {
+
+constexpr int WM_THREADS = 256;
+constexpr int WM_SMEM_CAP = 4096;  // (value, weight) pairs sorted in shared memory; larger MAGs use scratch
+
+struct VW {
+    uint32_t key;  // order-preserving image of the f32 value (NaN last)
+    float v;
+    long long w;
+};
+
+__device__ __forceinline__ uint32_t f32_key(float v) {
+    if (v != v) return 0xFFFFFFFFu;          // NaN sorts last (Python's sort has no defined place for it)
+    if (v == 0.0f) v = 0.0f;                 // -0.0 == +0.0
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__device__ __forceinline__ bool vw_less(const VW &a, const VW &b) {  // tuple order (value, weight), tools.py:300
+    return a.key < b.key || (a.key == b.key && a.w < b.w);
+}
+
+// One CTA per (MAG, column).  medians[m * n_cols + j]; NaN for columns that are masked out or MAGs
+// that are not scored (<= 2 rows).
+__global__ void __launch_bounds__(WM_THREADS)
+wmedian_kernel(const float *__restrict__ data, const long long *__restrict__ weights,
+               const long long *__restrict__ mag_off, int64_t n_cols, const uint8_t *__restrict__ col_mask,
+               int64_t min_rows, VW *__restrict__ scratch, float *__restrict__ medians) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ long long s_red[WM_THREADS / 32];
+    __shared__ long long s_total, s_wmax;
+    __shared__ long long s_first;
+    __shared__ long long s_scan[WM_THREADS / 32];
+    __shared__ long long s_idx;
+
+    const int64_t m = blockIdx.x / n_cols, j = blockIdx.x % n_cols;
+    const int64_t r0 = mag_off[m], n = mag_off[m + 1] - r0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *out = medians + m * n_cols + j;
+    if (n < min_rows || n < 1 || (col_mask && !col_mask[m * n_cols + j])) {
+        if (tid == 0) *out = __uint_as_float(0x7FC00000u);
+        return;
+    }
+    // ---- total weight, max weight, first row (original order) holding the max ----
+    long long tot = 0, wmax = -1;
+    for (int64_t i = tid; i < n; i += WM_THREADS) {
+        const long long w = weights[r0 + i];
+        tot += w;
+        wmax = w > wmax ? w : wmax;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        const long long t = __shfl_xor_sync(0xffffffffu, wmax, o);
+        wmax = t > wmax ? t : wmax;
+    }
+    if (lane == 0) { s_red[warp] = tot; s_scan[warp] = wmax; }
+    __syncthreads();
+    if (tid == 0) {
+        long long t = 0, x = -1;
+        for (int w = 0; w < WM_THREADS / 32; w++) { t += s_red[w]; x = s_scan[w] > x ? s_scan[w] : x; }
+        s_total = t; s_wmax = x; s_first = n; s_idx = -1;
+    }
+    __syncthreads();
+    const long long total = s_total;
+    if (2 * s_wmax > total) {  // tools.py:302-303: one weight above the midpoint wins
+        long long f = n;
+        for (int64_t i = tid; i < n; i += WM_THREADS)
+            if (weights[r0 + i] == s_wmax) { f = i; break; }
+        atomicMin(&s_first, f);
+        __syncthreads();
+        if (tid == 0) *out = data[(r0 + s_first) * n_cols + j];
+        return;
+    }
+    // ---- sort (value, weight) ascending: bitonic network over the next power of two ----
+    int64_t np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    VW *a = np2 <= WM_SMEM_CAP ? reinterpret_cast<VW *>(s_raw) : scratch + (r0 * n_cols + j * n) * 2;
+    for (int64_t i = tid; i < np2; i += WM_THREADS) {
+        VW e;
+        if (i < n) {
+            e.v = data[(r0 + i) * n_cols + j];
+            e.key = f32_key(e.v);
+            e.w = weights[r0 + i];
+        } else {
+            e.v = 0.f; e.key = 0xFFFFFFFFu; e.w = LLONG_MAX;  // padding sorts after everything
+        }
+        a[i] = e;
+    }
+    __syncthreads();
+    for (int64_t k = 2; k <= np2; k <<= 1) {
+        for (int64_t s = k >> 1; s > 0; s >>= 1) {
+            for (int64_t i = tid; i < np2; i += WM_THREADS) {
+                const int64_t p = i ^ s;
+                if (p > i) {
+                    const VW x = a[i], y = a[p];
+                    const bool up = (i & k) == 0;
+                    if (up ? vw_less(y, x) : vw_less(x, y)) { a[i] = y; a[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- cumulative weights; idx = last position with 2*cs <= total (tools.py:305-306) ----
+    long long carry = 0;
+    for (int64_t b = 0; b < n; b += WM_THREADS) {
+        const int64_t i = b + tid;
+        const long long w = i < n ? a[i].w : 0;
+        long long incl = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        long long wpre = 0, blk = 0;
+        for (int w2 = 0; w2 < WM_THREADS / 32; w2++) {
+            if (w2 < warp) wpre += s_scan[w2];
+            blk += s_scan[w2];
+        }
+        const long long cs = carry + wpre + incl;
+        if (i < n && 2 * cs <= total) atomicMax(&s_idx, (long long)i);
+        carry += blk;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const long long idx = s_idx;
+        float med;
+        if (idx < 0) med = a[0].v;  // unreachable for non-negative weights (first weight <= midpoint here)
+        else {
+            long long cs = 0;  // recompute cs[idx] exactly (sequential; n is small)
+            for (long long i = 0; i <= idx; i++) cs += a[i].w;
+            if (2 * cs == total) med = idx + 1 < n ? __fdiv_rn(__fadd_rn(a[idx].v, a[idx + 1].v), 2.0f) : a[idx].v;
+            else med = a[idx + 1 < n ? idx + 1 : idx].v;
+        }
+        *out = med;
+    }
+}
+
+// score[r] = mean over the MAG's selected columns of 1 - |ln((x+1e-5)/(med+1e-5)) / ln(base)|, clipped
+// to [0,1] (tools.py:347-351).  one_sided: only values ABOVE the median are penalised (used for the
+// centroid-distance score; not a reference behaviour).
+__global__ void logratio_kernel(const float *__restrict__ data, const long long *__restrict__ mag_off,
+                                int64_t n_mags, int64_t n_rows, int64_t n_cols,
+                                const uint8_t *__restrict__ col_mask, const float *__restrict__ medians,
+                                double log_base, float pseudo, double clip_lo, double clip_hi,
+                                int64_t min_rows, int one_sided, double *__restrict__ scores) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    int64_t lo = 0, hi = n_mags;  // MAG of row r: largest m with mag_off[m] <= r
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (mag_off[mid] <= r) lo = mid + 1;
+        else hi = mid;
+    }
+    const int64_t m = lo - 1;
+    const int64_t n = mag_off[m + 1] - mag_off[m];
+    double acc = 0.0;
+    int64_t k = 0;
+    if (n >= min_rows) {
+        for (int64_t j = 0; j < n_cols; j++) {
+            if (col_mask && !col_mask[m * n_cols + j]) continue;
+            const float num = __fadd_rn(data[r * n_cols + j], pseudo);
+            const float den = __fadd_rn(medians[m * n_cols + j], pseudo);
+            const float ratio = __fdiv_rn(num, den);
+            const float lg = (float)log((double)ratio);  // f32 log, correctly rounded via f64
+            double t = (double)lg / log_base;
+            if (one_sided) t = t < 0.0 ? 0.0 : t;
+            acc += 1.0 - fabs(t);
+            k++;
+        }
+    }
+    double sc;
+    if (n < min_rows || k == 0) sc = 1.0;  // core.py:248-250, 306-308
+    else {
+        sc = k == 1 ? acc : acc / (double)k;
+        if (sc < clip_lo) sc = clip_lo;  // np.clip keeps NaN
+        if (sc > clip_hi) sc = clip_hi;
+    }
+    scores[r] = sc;
+}
+
+// core.py:301-305: np.average(cov, axis=0, weights=lengths) >= min_average_coverage, in f64, rows
+// added in order (the order NumPy uses for an axis-0 reduction) so the comparison is reproducible.
+__global__ void select_samples_kernel(const float *__restrict__ cov, const long long *__restrict__ weights,
+                                      const long long *__restrict__ mag_off, int64_t n_mags, int64_t n_cols,
+                                      double min_avg, uint8_t *__restrict__ sel, double *__restrict__ means) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_mags * n_cols) return;
+    const int64_t m = t / n_cols, j = t % n_cols;
+    double acc = 0.0, wsum = 0.0;
+    for (int64_t r = mag_off[m]; r < mag_off[m + 1]; r++) {
+        const double w = (double)weights[r];
+        acc = __dadd_rn(acc, __dmul_rn((double)cov[r * n_cols + j], w));
+        wsum = __dadd_rn(wsum, w);
+    }
+    const double mean = acc / wsum;
+    if (means) means[t] = mean;
+    sel[t] = mean >= min_avg ? 1 : 0;
+}
+
+// ---- CLR + centroid distance (self-specified: the reference has no such code) -----------------
+// clr_ij = ln(c_ij + 1) - mean_j ln(c_ij + 1); centroid_j = sum_i len_i clr_ij / sum_i len_i;
+// d_i = ||clr_i - centroid||_2.  f64 throughout.
+__global__ void clr_rowmean_kernel(const uint32_t *__restrict__ counts, int64_t n_rows, double *__restrict__ rowmean) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rows) return;
+    double s = 0.0;
+    for (int j = lane; j < MP2_NCANON; j += 32) s += log((double)counts[r * MP2_NCANON + j] + 1.0);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) rowmean[r] = s / (double)MP2_NCANON;
+}
+
+__global__ void __launch_bounds__(160)
+clr_centroid_kernel(const uint32_t *__restrict__ counts, const long long *__restrict__ weights,
+                    const long long *__restrict__ mag_off, const double *__restrict__ rowmean,
+                    double *__restrict__ centroid /*[n_mags,136]*/) {
+    const int64_t m = blockIdx.x;
+    const int j = threadIdx.x;
+    if (j >= MP2_NCANON) return;
+    double acc = 0.0, wsum = 0.0;
+    for (int64_t r = mag_off[m]; r < mag_off[m + 1]; r++) {
+        const double w = (double)weights[r];
+        acc += w * (log((double)counts[r * MP2_NCANON + j] + 1.0) - rowmean[r]);
+        wsum += w;
+    }
+    centroid[m * MP2_NCANON + j] = wsum > 0.0 ? acc / wsum : 0.0;
+}
+
+__global__ void clr_dist_kernel(const uint32_t *__restrict__ counts, const long long *__restrict__ mag_off,
+                                int64_t n_mags, int64_t n_rows, const double *__restrict__ rowmean,
+                                const double *__restrict__ centroid, float *__restrict__ clr,
+                                double *__restrict__ dist) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rows) return;
+    int64_t lo = 0, hi = n_mags;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (mag_off[mid] <= r) lo = mid + 1;
+        else hi = mid;
+    }
+    const int64_t m = lo - 1;
+    double d2 = 0.0;
+    for (int j = lane; j < MP2_NCANON; j += 32) {
+        const double v = log((double)counts[r * MP2_NCANON + j] + 1.0) - rowmean[r];
+        if (clr) clr[r * MP2_NCANON + j] = (float)v;
+        const double d = v - centroid[m * MP2_NCANON + j];
+        d2 += d * d;
+    }
+    for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    if (lane == 0) dist[r] = sqrt(d2);
+}
+
+}  // namespace mp2
+
+using namespace mp2;
+
+extern "C" int mp2_logratio_device(const void *d_data, const void *d_weights, const void *d_mag_off,
+                                   int64_t n_mags, int64_t n_rows, int64_t n_cols, const void *d_col_mask,
+                                   double base, float pseudo, double clip_lo, double clip_hi,
+                                   int64_t min_rows, int one_sided, void *d_scores, void *d_medians,
+                                   void *stream_) {
+    if (n_mags < 0 || n_rows < 0 || n_cols < 1) return fail(MP2_EINVAL, "bad shape");
+    if (!(base > 0.0) || base == 1.0) return fail(MP2_EINVAL, "base must be > 0 and != 1");
+    if (!d_data || !d_weights || !d_mag_off || !d_scores) return fail(MP2_EINVAL, "NULL argument");
+    if (n_mags * n_cols > INT32_MAX) return fail(MP2_EINVAL, "too many (MAG, column) pairs");
+    MP2_TRY(require_device(-1));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_rows == 0 || n_mags == 0) return MP2_OK;
+    Temp med, scratch;
+    float *medians = (float *)d_medians;
+    if (!medians) {
+        MP2_TRY(med.alloc(sizeof(float) * n_mags * n_cols, stream));
+        medians = med.as<float>();
+    }
+    // scratch for MAGs with more rows than fit in shared memory: 2x (power-of-two padding) pairs
+    MP2_TRY(scratch.alloc(sizeof(VW) * 2 * (size_t)n_rows * n_cols, stream));
+    static bool attr_done = false;
+    if (!attr_done) {
+        MP2_CUDA(cudaFuncSetAttribute(wmedian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(VW) * WM_SMEM_CAP)));
+        attr_done = true;
+    }
+    {
+        Launch L("wmedian_kernel", stream);
+        wmedian_kernel<<<(unsigned)(n_mags * n_cols), WM_THREADS, sizeof(VW) * WM_SMEM_CAP, stream>>>(
+            (const float *)d_data, (const long long *)d_weights, (const long long *)d_mag_off, n_cols,
+            (const uint8_t *)d_col_mask, min_rows, scratch.as<VW>(), medians);
+    }
+    MP2_CUDA(cudaGetLastError());
+    {
+        Launch L("logratio_kernel", stream);
+        logratio_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, stream>>>(
+            (const float *)d_data, (const long long *)d_mag_off, n_mags, n_rows, n_cols,
+            (const uint8_t *)d_col_mask, medians, log(base), pseudo, clip_lo, clip_hi, min_rows, one_sided,
+            (double *)d_scores);
+    }
+    MP2_CUDA(cudaGetLastError());
+    return MP2_OK;
+}
+
+extern "C" int mp2_select_samples_device(const void *d_cov, const void *d_weights, const void *d_mag_off,
+                                         int64_t n_mags, int64_t n_rows, int64_t n_cols,
+                                         double min_average_coverage, void *d_sel, void *d_means,
+                                         void *stream_) {
+    if (n_mags < 0 || n_rows < 0 || n_cols < 1) return fail(MP2_EINVAL, "bad shape");
+    if (!d_cov || !d_weights || !d_mag_off || !d_sel) return fail(MP2_EINVAL, "NULL argument");
+    MP2_TRY(require_device(-1));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_mags == 0) return MP2_OK;
+    const int64_t t = n_mags * n_cols;
+    {
+        Launch L("select_samples_kernel", stream);
+        select_samples_kernel<<<(unsigned)((t + 127) / 128), 128, 0, stream>>>(
+            (const float *)d_cov, (const long long *)d_weights, (const long long *)d_mag_off, n_mags, n_cols,
+            min_average_coverage, (uint8_t *)d_sel, (double *)d_means);
+    }
+    MP2_CUDA(cudaGetLastError());
+    return MP2_OK;
+}
+
+extern "C" int mp2_clr_centroid_device(const void *d_counts, const void *d_weights, const void *d_mag_off,
+                                       int64_t n_mags, int64_t n_rows, void *d_clr, void *d_dist,
+                                       void *stream_) {
+    if (n_mags < 0 || n_rows < 0) return fail(MP2_EINVAL, "bad shape");
+    if (!d_counts || !d_weights || !d_mag_off || !d_dist) return fail(MP2_EINVAL, "NULL argument");
+    MP2_TRY(require_device(-1));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_rows == 0 || n_mags == 0) return MP2_OK;
+    Temp rowmean, centroid;
+    MP2_TRY(rowmean.alloc(sizeof(double) * n_rows, stream));
+    MP2_TRY(centroid.alloc(sizeof(double) * MP2_NCANON * n_mags, stream));
+    {
+        Launch L("clr_rowmean_kernel", stream);
+        clr_rowmean_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, stream>>>(
+            (const uint32_t *)d_counts, n_rows, rowmean.as<double>());
+    }
+    MP2_CUDA(cudaGetLastError());
+    {
+        Launch L("clr_centroid_kernel", stream);
+        clr_centroid_kernel<<<(unsigned)n_mags, 160, 0, stream>>>(
+            (const uint32_t *)d_counts, (const long long *)d_weights, (const long long *)d_mag_off,
+            rowmean.as<double>(), centroid.as<double>());
+    }
+    MP2_CUDA(cudaGetLastError());
+    {
+        Launch L("clr_dist_kernel", stream);
+        clr_dist_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, stream>>>(
+            (const uint32_t *)d_counts, (const long long *)d_mag_off, n_mags, n_rows, rowmean.as<double>(),
+            centroid.as<double>(), (float *)d_clr, (double *)d_dist);
+    }
+    MP2_CUDA(cudaGetLastError());
+    return MP2_OK;
+}

@@ -91,6 +91,92 @@ __global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_
     first_contig[k] = (int32_t)(lo > 0 ? lo - 1 : 0);
 }
 
+// Fold the warp's table into the contig's row: 256 codes -> 136 canonical classes (MODE 5: first
+// 5-mer counts -> 4-mer counts), integer global reductions, then zero the table.
+template <int MODE>
+__device__ __forceinline__ void tnf_flush(uint32_t *tab, int lane, uint32_t *__restrict__ row) {
+    constexpr int WORDS = TnfTab<MODE>::WORDS;
+    __syncwarp();
+#pragma unroll
+    for (int k = lane; k < MP2_NCANON + 24; k += 32) {
+        if (k < MP2_NCANON) {
+            const uint32_t pr = c_canon_pair[k];
+            const uint32_t a = pr & 0xFFu, rc = pr >> 8;
+            uint32_t val = tab[(MODE == 5 ? 1024 : 0) + a];
+            if (MODE == 5) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(tab + (a << 2));
+                val += q.x + q.y + q.z + q.w + tab[a] + tab[256 + a] + tab[512 + a] + tab[768 + a];
+            }
+            if (rc != a) {
+                val += tab[(MODE == 5 ? 1024 : 0) + rc];
+                if (MODE == 5) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(tab + (rc << 2));
+                    val += q.x + q.y + q.z + q.w + tab[rc] + tab[256 + rc] + tab[512 + rc] + tab[768 + rc];
+                }
+            }
+            if (val) atomicAdd(&row[k], val);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < WORDS / 128; i++)
+        *reinterpret_cast<uint4 *>(tab + (i * 32 + lane) * 4) = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+}
+
+// Vector path of one group of 16 valid bases whose 3 halo bases are valid too: 8 (MODE 5) or 16
+// (MODE 4) increments.  halo = codes of the 3 bases before the group in bits 5:0.
+template <int MODE>
+__device__ __forceinline__ void tnf_count16(uint32_t cw, uint32_t halo, uint32_t t5, uint32_t t4) {
+    if (MODE == 5) {
+        // 5-mer ending at base j+1 (j even) = bits [2(14-j)+9 : 2(14-j)] of halo:cw; its counter is
+        // word index*4 bytes into T5
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            const int sh = 2 * (14 - j);
+            const uint32_t t = sh >= 2 ? __funnelshift_r(cw, halo, sh - 2) : (cw << 2);
+            smem_inc(t5 + (t & 0xFFCu));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int sh = 2 * (15 - j);
+            const uint32_t t = sh >= 2 ? __funnelshift_r(cw, halo, sh - 2) : (cw << 2);
+            smem_inc(t4 + (t & 0x3FCu));
+        }
+    }
+}
+
+// Masked path of one group: W has bit (18-i) set when position P-3+i is a valid base of this contig
+// below seg_hi (i = 0..2 halo, 3..18 the group); own has bit (15-j) set when base j is >= seg_lo.
+// Counts single 4-mers into T4 and returns the number of G/C bases owned.
+__device__ __forceinline__ uint32_t tnf_masked16(uint32_t cw, uint32_t ph, uint32_t W, uint32_t own, uint32_t t4) {
+    const uint32_t K = W & (W >> 1) & (W >> 2) & (W >> 3) & own;  // bit (15-j): the 4-mer ENDING at base j counts
+    uint32_t sp = W & own;  // spread bit b -> bit 2b
+    sp = (sp | (sp << 8)) & 0x00FF00FFu;
+    sp = (sp | (sp << 4)) & 0x0F0F0F0Fu;
+    sp = (sp | (sp << 2)) & 0x33333333u;
+    sp = (sp | (sp << 1)) & 0x55555555u;
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+        if (K & (1u << b)) {
+            const uint32_t t = b ? __funnelshift_r(cw, ph, 2 * b - 2) : (cw << 2);
+            smem_inc(t4 + (t & 0x3FCu));
+        }
+    }
+    return __popc((cw ^ (cw >> 1)) & sp);
+}
+
+// range masks shared by the ASCII and the packed kernels (positions relative to the piece)
+__device__ __forceinline__ void tnf_range_masks(int P, int o0, int seg_lo, int seg_hi, uint32_t &W, uint32_t &own) {
+    const int lo_i = o0 - (P - 3);       // positions i < lo_i precede the contig
+    if (lo_i > 0) W &= lo_i >= 19 ? 0u : (0x7FFFFu >> lo_i);
+    const int hi_i = seg_hi - (P - 3);   // positions i >= hi_i are beyond the segment
+    if (hi_i < 19) W &= ~((1u << (19 - hi_i)) - 1u);
+    const int slo_j = seg_lo - P;
+    own = slo_j > 0 ? (slo_j >= 16 ? 0u : (0xFFFFu >> slo_j)) : 0xFFFFu;
+}
+
 // ---- main kernel -------------------------------------------------------------------------
 // Every warp (= CTA) works alone: it draws a 16 KiB piece of the stream from a global counter,
 // walks the segments (piece ∩ contig) in it, counts each segment into its own shared-memory table
@@ -196,23 +282,7 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                     const bool fast = clean && (halo < 0x100u) && ((unsigned)(g - g_in_lo) < (unsigned)(g_in_hi - g_in_lo));
                     if (fast) {
                         gcl += __popc((cw ^ (cw >> 1)) & 0x55555555u);
-                        if (MODE == 5) {
-                            // 5-mer ending at base j+1 (j even) = bits [2(14-j)+9 : 2(14-j)] of
-                            // halo:cw; its counter is word index*4 bytes into T5
-#pragma unroll
-                            for (int j = 0; j < 16; j += 2) {
-                                const int sh = 2 * (14 - j);
-                                const uint32_t t = sh >= 2 ? __funnelshift_r(cw, halo, sh - 2) : (cw << 2);
-                                smem_inc(t5 + (t & 0xFFCu));
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; j++) {
-                                const int sh = 2 * (15 - j);
-                                const uint32_t t = sh >= 2 ? __funnelshift_r(cw, halo, sh - 2) : (cw << 2);
-                                smem_inc(t4 + (t & 0x3FCu));
-                            }
-                        }
+                        tnf_count16<MODE>(cw, halo, t5, t4);
                     } else {
                         // ---- masked path: exact per-base validity, single 4-mers into T4 ----
                         const int P = g << 4;
@@ -222,70 +292,152 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                         const uint32_t ph = decode4(hw, sh_);
                         // W: bit (18-i) <-> position P-3+i is a valid base of this contig below seg_hi
                         uint32_t W = ~((bad4(sh_) & 7u) << 16 | bad4(s0) << 12 | bad4(s1) << 8 | bad4(s2) << 4 | bad4(s3)) & 0x7FFFFu;
-                        const int lo_i = o0 - (P - 3);       // positions i < lo_i precede the contig
-                        if (lo_i > 0) W &= lo_i >= 19 ? 0u : (0x7FFFFu >> lo_i);
-                        const int hi_i = seg_hi - (P - 3);   // positions i >= hi_i are beyond the segment
-                        if (hi_i < 19) W &= ~((1u << (19 - hi_i)) - 1u);
                         if (P < 4 && !head_ok) W &= 0xFFFFu;
-                        // own: bit (15-j) <-> base j belongs to this segment (>= seg_lo)
-                        const int slo_j = seg_lo - P;
-                        const uint32_t own = slo_j > 0 ? (slo_j >= 16 ? 0u : (0xFFFFu >> slo_j)) : 0xFFFFu;
-                        // K: bit (15-j) <-> the 4-mer ENDING at base j is valid and counted here
-                        const uint32_t K = W & (W >> 1) & (W >> 2) & (W >> 3) & own;
-                        // GC: valid G/C bases of this group inside the segment
-                        uint32_t sp = W & own;  // spread bit b -> bit 2b
-                        sp = (sp | (sp << 8)) & 0x00FF00FFu;
-                        sp = (sp | (sp << 4)) & 0x0F0F0F0Fu;
-                        sp = (sp | (sp << 2)) & 0x33333333u;
-                        sp = (sp | (sp << 1)) & 0x55555555u;
-                        gcl += __popc((cw ^ (cw >> 1)) & sp);
-#pragma unroll
-                        for (int b = 0; b < 16; b++) {
-                            if (K & (1u << b)) {
-                                const uint32_t t = b ? __funnelshift_r(cw, ph, 2 * b - 2) : (cw << 2);
-                                smem_inc(t4 + (t & 0x3FCu));
-                            }
-                        }
+                        uint32_t own;
+                        tnf_range_masks(P, o0, seg_lo, seg_hi, W, own);
+                        gcl += tnf_masked16(cw, ph, W, own, t4);
                     }
                 }
             }
             gcl = __reduce_add_sync(0xffffffffu, gcl);
             if (lane == 0 && gcl) atomicAdd(&gc_counts[c], (unsigned long long)gcl);
-            __syncwarp();
-            // ---- flush: fold 256 codes -> 136 canonical classes, add to the contig's row ----
-#pragma unroll
-            for (int k = lane; k < MP2_NCANON + 24; k += 32) {
-                if (k < MP2_NCANON) {
-                    const uint32_t pr = c_canon_pair[k];
-                    const uint32_t a = pr & 0xFFu, rc = pr >> 8;
-                    uint32_t val = tab[(MODE == 5 ? 1024 : 0) + a];
-                    if (MODE == 5) {
-                        const uint4 q = *reinterpret_cast<const uint4 *>(tab + (a << 2));
-                        val += q.x + q.y + q.z + q.w + tab[a] + tab[256 + a] + tab[512 + a] + tab[768 + a];
-                    }
-                    if (rc != a) {
-                        val += tab[(MODE == 5 ? 1024 : 0) + rc];
-                        if (MODE == 5) {
-                            const uint4 q = *reinterpret_cast<const uint4 *>(tab + (rc << 2));
-                            val += q.x + q.y + q.z + q.w + tab[rc] + tab[256 + rc] + tab[512 + rc] + tab[768 + rc];
-                        }
-                    }
-                    if (val) atomicAdd(&counts[c * MP2_NCANON + k], val);
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < WORDS / 128; i++)
-                *reinterpret_cast<uint4 *>(tab + (i * 32 + lane) * 4) = make_uint4(0, 0, 0, 0);
-            __syncwarp();
+            tnf_flush<MODE>(tab, lane, counts + c * MP2_NCANON);
         }
     }
+}
+
+// ---- 2-bit packed input (north_star layout) ---------------------------------------------------
+// codes: 16 bases per uint32, FIRST base most significant; valid: 32 bases per uint32, first base
+// most significant (0 = any non-ACGT byte).  Same piece / segment / table scheme as tnf_kernel; a
+// lane owns QUADS (4 consecutive groups = 64 bases: one 128-bit load of codes + one 64-bit load of
+// validity), so the halo of groups 1..3 is already in registers and one shuffle serves 64 bases.
+template <int MODE>
+__global__ void __launch_bounds__(TNF_THREADS)
+tnf_packed_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ valid, int64_t n_bases,
+                  const int64_t *__restrict__ offsets, int64_t n, const int32_t *__restrict__ first_contig,
+                  int64_t n_chunks, uint32_t *__restrict__ counts, unsigned long long *__restrict__ gc_counts,
+                  int *__restrict__ work_counter) {
+    constexpr int WORDS = TnfTab<MODE>::WORDS;
+    __shared__ __align__(16) uint32_t tab[WORDS];
+    const int lane = threadIdx.x;
+    const uint32_t t5 = (uint32_t)__cvta_generic_to_shared(tab);
+    const uint32_t t4 = MODE == 5 ? t5 + 4096u : t5;
+    const int src_lane = (lane + 31) & 31;
+    for (int i = lane; i < WORDS; i += 32) tab[i] = 0;
+    __syncwarp();
+
+    for (;;) {
+        int64_t kc = 0;
+        if (lane == 0) kc = atomicAdd(work_counter, 1);
+        kc = __shfl_sync(0xffffffffu, kc, 0);
+        if (kc >= n_chunks) break;
+        const int64_t base = kc * TNF_PIECE;
+        const uint32_t *__restrict__ pc = codes + (base >> 4);
+        const uint32_t *__restrict__ pv = valid + (base >> 5);
+        const int piece_hi = (int)(n_bases - base < TNF_PIECE ? n_bases - base : TNF_PIECE);
+
+        for (int64_t c = first_contig[kc]; c < n; c++) {
+            const int64_t o0_64 = offsets[c] - base;
+            if (o0_64 >= piece_hi) break;
+            const int64_t o1_64 = offsets[c + 1] - base;
+            const int o0 = o0_64 < -64 ? -64 : (int)o0_64;
+            const int seg_lo = o0 > 0 ? o0 : 0;
+            const int seg_hi = o1_64 < piece_hi ? (int)o1_64 : piece_hi;
+            if (seg_hi <= seg_lo) continue;
+
+            uint32_t gcl = 0;
+            const int g_first = seg_lo >> 4, g_last = (seg_hi - 1) >> 4;
+            const int in_lo = o0 + 3 > seg_lo ? o0 + 3 : seg_lo;
+            const int g_in_lo = (in_lo + 15) >> 4;
+            const int g_in_hi = (seg_hi >> 4) > g_in_lo ? (seg_hi >> 4) : g_in_lo;
+            const int q_first = g_first >> 2, q_last = g_last >> 2;
+            // packed halo = 6 code bits | 3 validity bits << 6 of the group before the first quad
+            uint32_t carry = 0;
+            if (lane == 31 && (q_first > 0 || base > 0)) {
+                const int gp = 4 * q_first - 1;
+                const uint32_t cwp = __ldg(pc + gp);
+                const uint32_t vwp = __ldg(pv + (gp >> 1));  // arithmetic shift: gp = -1 -> word -1
+                const uint32_t v16 = (gp & 1) ? (vwp & 0xFFFFu) : (vwp >> 16);
+                carry = (cwp & 0x3Fu) | ((v16 & 7u) << 6);
+            }
+            for (int q0 = q_first; q0 <= q_last; q0 += 32) {
+                const int qd = q0 + lane;
+                uint4 cq = make_uint4(0, 0, 0, 0);
+                uint2 vq = make_uint2(0, 0);
+                if (qd <= q_last) {
+                    cq = __ldg(reinterpret_cast<const uint4 *>(pc) + qd);
+                    vq = __ldg(reinterpret_cast<const uint2 *>(pv) + qd);
+                }
+                const uint32_t cws[4] = {cq.x, cq.y, cq.z, cq.w};
+                const uint32_t v16s[4] = {vq.x >> 16, vq.x & 0xFFFFu, vq.y >> 16, vq.y & 0xFFFFu};
+                const uint32_t mine = (cws[3] & 0x3Fu) | ((v16s[3] & 7u) << 6);
+                const uint32_t give = lane == 31 ? carry : mine;
+                uint32_t halo = __shfl_sync(0xffffffffu, give, src_lane);
+                carry = mine;
+                if (qd > q_last) continue;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int g = 4 * qd + k;
+                    const uint32_t cw = cws[k], v16 = v16s[k];
+                    if (g >= g_first && g <= g_last) {
+                        const bool fast = (v16 == 0xFFFFu) && ((halo >> 6) == 7u) &&
+                                          ((unsigned)(g - g_in_lo) < (unsigned)(g_in_hi - g_in_lo));
+                        if (fast) {
+                            gcl += __popc((cw ^ (cw >> 1)) & 0x55555555u);
+                            tnf_count16<MODE>(cw, halo & 0x3Fu, t5, t4);
+                        } else {
+                            const int P = g << 4;
+                            uint32_t W = ((halo >> 6) << 16) | v16, own;
+                            tnf_range_masks(P, o0, seg_lo, seg_hi, W, own);
+                            gcl += tnf_masked16(cw, halo & 0x3Fu, W, own, t4);
+                        }
+                    }
+                    halo = (cw & 0x3Fu) | ((v16 & 7u) << 6);
+                }
+            }
+            gcl = __reduce_add_sync(0xffffffffu, gcl);
+            if (lane == 0 && gcl) atomicAdd(&gc_counts[c], (unsigned long long)gcl);
+            tnf_flush<MODE>(tab, lane, counts + c * MP2_NCANON);
+        }
+    }
+}
+
+// ASCII -> (codes, valid).  One thread per group of 16 bases; groups are padded to whole quads.
+__global__ void tnf_pack_kernel(const uint8_t *__restrict__ bases, int64_t n_bases, int64_t n_groups,
+                                uint32_t *__restrict__ codes, uint16_t *__restrict__ valid16) {
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const int64_t P = g << 4;
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (P + 16 <= n_bases && ((reinterpret_cast<uintptr_t>(bases + P) & 15) == 0)) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(bases + P));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+        for (int i = 0; i < 16 && P + i < n_bases; i++) w[i >> 2] |= (uint32_t)bases[P + i] << (8 * (i & 3));
+    }
+    uint32_t s0, s1, s2, s3;
+    const uint32_t m0 = decode4_hi(w[0], s0), m1 = decode4_hi(w[1], s1);
+    const uint32_t m2 = decode4_hi(w[2], s2), m3 = decode4_hi(w[3], s3);
+    const uint32_t cw = __byte_perm(__byte_perm(m3, m2, 0x0073), __byte_perm(m1, m0, 0x0073), 0x5410);
+    uint32_t v16 = ~(bad4(s0) << 12 | bad4(s1) << 8 | bad4(s2) << 4 | bad4(s3)) & 0xFFFFu;
+    if (P + 16 > n_bases) {
+        const int keep = n_bases > P ? (int)(n_bases - P) : 0;  // first `keep` bases exist
+        v16 &= keep ? (0xFFFFu << (16 - keep)) & 0xFFFFu : 0u;
+    }
+    // the code bits of an invalid base are cleared so the packed form is canonical
+    uint32_t sp = v16;
+    sp = (sp | (sp << 8)) & 0x00FF00FFu;
+    sp = (sp | (sp << 4)) & 0x0F0F0F0Fu;
+    sp = (sp | (sp << 2)) & 0x33333333u;
+    sp = (sp | (sp << 1)) & 0x55555555u;
+    codes[g] = cw & (sp | (sp << 1));
+    valid16[g ^ 1] = (uint16_t)v16;  // even group = upper half of the little-endian 32-bit word
 }
 
 // ---- finalisation --------------------------------------------------------------------------
 // relative frequencies (src/composition.rs:111-118): u32 -> f32, row sum in f32, divide,
 // NaN -> 0.  The f32 row sum equals the exact integer sum while it is < 2^24; above that the
-// lane-0 fallback reproduces ndarray's 8-way unrolled fold order (see oracle/mp2_oracle.c).
+// lane-0 fallback reproduces the 8-way unrolled fold order of ndarray 0.13 (numeric_util::unrolled_fold).
 __global__ void tnf_rel_kernel(const uint32_t *__restrict__ counts, int64_t n,
                                float *__restrict__ rel) {
     const int lane = threadIdx.x & 31;
@@ -448,5 +600,79 @@ extern "C" int mp2_tnf_device(const void *d_bases, const void *d_offsets, int64_
                              gcc.as<unsigned long long>(), stream));
     MP2_TRY(tnf_finalize((const uint32_t *)d_counts, gcc.as<unsigned long long>(),
                          (const int64_t *)d_offsets, n, (float *)d_rel, (float *)d_gc, stream));
+    return MP2_OK;
+}
+
+extern "C" int mp2_pack_device(const void *d_bases, int64_t n_bases, void *d_codes, void *d_valid, void *stream_) {
+    using namespace mp2;
+    if (n_bases < 0) return fail(MP2_EINVAL, "negative size");
+    if (!d_codes || !d_valid || (n_bases > 0 && !d_bases)) return fail(MP2_EINVAL, "NULL argument");
+    if ((reinterpret_cast<uintptr_t>(d_codes) & 15) || (reinterpret_cast<uintptr_t>(d_valid) & 7))
+        return fail(MP2_EINVAL, "d_codes must be 16-byte and d_valid 8-byte aligned");
+    MP2_TRY(require_device(-1));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t n_groups = ((n_bases + 63) / 64) * 4;
+    if (n_groups == 0) return MP2_OK;
+    {
+        Launch L("tnf_pack_kernel", stream);
+        tnf_pack_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, stream>>>(
+            (const uint8_t *)d_bases, n_bases, n_groups, (uint32_t *)d_codes, (uint16_t *)d_valid);
+    }
+    MP2_CUDA(cudaGetLastError());
+    return MP2_OK;
+}
+
+extern "C" int mp2_tnf_packed_device(const void *d_codes, const void *d_valid, const void *d_offsets, int64_t n,
+                                     int64_t n_bases, void *d_counts, void *d_rel, void *d_gc, void *stream_) {
+    using namespace mp2;
+    if (n < 0 || n_bases < 0) return fail(MP2_EINVAL, "negative size");
+    if (n > INT32_MAX) return fail(MP2_EINVAL, "too many sequences in one call (%lld)", (long long)n);
+    if (!d_offsets || !d_counts || (n_bases > 0 && (!d_codes || !d_valid)))
+        return fail(MP2_EINVAL, "d_codes, d_valid, d_offsets and d_counts are required");
+    if ((reinterpret_cast<uintptr_t>(d_codes) & 15) || (reinterpret_cast<uintptr_t>(d_valid) & 7))
+        return fail(MP2_EINVAL, "d_codes must be 16-byte and d_valid 8-byte aligned");
+    MP2_TRY(require_device(-1));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return MP2_OK;
+    MP2_TRY(upload_tables());
+    Temp gcc, map, ctr;
+    MP2_TRY(gcc.alloc(sizeof(unsigned long long) * n, stream));
+    MP2_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * MP2_NCANON * n, stream));
+    MP2_CUDA(cudaMemsetAsync(gcc.p, 0, sizeof(unsigned long long) * n, stream));
+    const int64_t n_chunks = (n_bases + TNF_PIECE - 1) / TNF_PIECE;
+    if (n_chunks > 0) {
+        MP2_TRY(map.alloc(sizeof(int32_t) * n_chunks, stream));
+        MP2_TRY(ctr.alloc(sizeof(int), stream));
+        MP2_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int), stream));
+        {
+            Launch L("tnf_chunk_map_kernel", stream);
+            tnf_chunk_map_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, stream>>>(
+                (const int64_t *)d_offsets, n, 0, 0, n_chunks, map.as<int32_t>());
+        }
+        MP2_CUDA(cudaGetLastError());
+        const int mode = tnf_mode();
+        int occ = 0;
+        if (mode == 5)
+            MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_packed_kernel<5>, TNF_THREADS, 0));
+        else
+            MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_packed_kernel<4>, TNF_THREADS, 0));
+        if (occ < 1) occ = 1;
+        int64_t grid = (int64_t)num_sms() * occ;
+        if (grid > n_chunks) grid = n_chunks;
+        {
+            Launch L("tnf_packed_kernel", stream);
+            if (mode == 5)
+                tnf_packed_kernel<5><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(
+                    (const uint32_t *)d_codes, (const uint32_t *)d_valid, n_bases, (const int64_t *)d_offsets, n,
+                    map.as<int32_t>(), n_chunks, (uint32_t *)d_counts, gcc.as<unsigned long long>(), ctr.as<int>());
+            else
+                tnf_packed_kernel<4><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(
+                    (const uint32_t *)d_codes, (const uint32_t *)d_valid, n_bases, (const int64_t *)d_offsets, n,
+                    map.as<int32_t>(), n_chunks, (uint32_t *)d_counts, gcc.as<unsigned long long>(), ctr.as<int>());
+        }
+        MP2_CUDA(cudaGetLastError());
+    }
+    MP2_TRY(tnf_finalize((const uint32_t *)d_counts, gcc.as<unsigned long long>(), (const int64_t *)d_offsets, n,
+                         (float *)d_rel, (float *)d_gc, stream));
     return MP2_OK;
 }

@@ -1,0 +1,161 @@
+"""Mirror of the part of magpurify2/tools.py that sits on the hot paths: the native re-exports
+(tools.py:39-42) and the scoring helpers (tools.py:283-351), same names and argument meaning,
+computed by libmp2 on the GPU."""
+import numpy as np
+
+from . import _scoring
+from ._composition import get_gc, get_tnf  # noqa: F401  (tools.py:40)
+from ._coverage import get_bam_coverages  # noqa: F401  (tools.py:41)
+
+
+def get_weighted_median(data, weights):
+    """Weighted median of `data` (tools.py:283-311): sort by (value, weight); a single weight above
+    half the total wins; an exact split returns the mean of the two straddling values."""
+    data = np.array(data, dtype=np.float32).squeeze().reshape(-1)
+    weights = np.array(weights).squeeze().reshape(-1)
+    _s, med = _scoring.log_ratio_scores_batch(data, weights, [0, len(data)], 2.0, min_rows=1, want_medians=True)
+    return med[0, 0]
+
+
+def get_log_ratio_scores(data, weights, base, pseudo=1e-5, min=0.0, max=1.0):
+    """1 - |log_base((x + pseudo) / (weighted median + pseudo))|, averaged over columns for 2-D
+    input, clipped to [min, max] (tools.py:314-351)."""
+    data = np.asarray(data, dtype=np.float32)
+    return _scoring.log_ratio_scores_batch(data, weights, [0, data.shape[0]], base, pseudo=pseudo,
+                                           clip=(min, max), min_rows=1)
+
+
+# ---- helpers either side of the hot paths (same names / behaviour as magpurify2/tools.py) ----
+import hashlib
+import logging
+import os
+import struct
+import sys
+import zlib
+from enum import Enum, auto
+
+logger = logging.getLogger("timestamp")
+
+
+class Compression(Enum):  # tools.py:45-49
+    bzip2 = auto()
+    gzip = auto()
+    xz = auto()
+    noncompressed = auto()
+
+
+def validade_input(value, parameter_name, interval):
+    """Clamp a numeric option into `interval` with a warning (tools.py:54-82)."""
+    interval = sorted(interval)
+    if value > interval[1] or value < interval[0]:
+        value = min(max(value, interval[0]), interval[1])
+        logger.warning(
+            f"The value of the `{parameter_name}` parameter must be between {interval[0]} and "
+            f"{interval[1]}. Setting it to {value}."
+        )
+    return value
+
+
+def check_output_directory(output_directory):  # tools.py:85-97
+    if not output_directory.is_dir():
+        logger.warning("Output directory does not exist. Creating it now.")
+        output_directory.mkdir()
+
+
+def is_compressed(filepath):  # tools.py:123-147
+    with open(filepath, "rb") as fin:
+        signature = fin.read(8)
+    if signature[:2] == b"\x1f\x8b":
+        return Compression.gzip
+    if signature[:3] == b"BZh":
+        return Compression.bzip2
+    if signature[:7] == b"\xfd7zXZ\x00\x00":
+        return Compression.xz
+    return Compression.noncompressed
+
+
+def get_file_signature(filepath):
+    """SHA-256 of the last 128,000 bytes (tools.py:150-166; OSError on smaller files, as there)."""
+    with open(filepath, "rb") as fin:
+        fin.seek(-128000, os.SEEK_END)
+        return hashlib.sha256(fin.read(128000)).hexdigest()
+
+
+def _bgzf_first_block(filepath):
+    with open(filepath, "rb") as fin:
+        head = fin.read(18)
+        if len(head) < 18 or head[:4] != b"\x1f\x8b\x08\x04":
+            return b""
+        xlen = struct.unpack("<H", head[10:12])[0]
+        fin.seek(12)
+        extra = fin.read(xlen)
+        bsize, o = None, 0
+        while o + 4 <= len(extra):
+            slen = struct.unpack("<H", extra[o + 2:o + 4])[0]
+            if extra[o:o + 2] == b"BC" and slen == 2:
+                bsize = struct.unpack("<H", extra[o + 4:o + 6])[0] + 1
+            o += 4 + slen
+        if bsize is None:
+            return b""
+        comp = fin.read(bsize - 12 - xlen - 8)
+    try:
+        return zlib.decompress(comp, -15)
+    except zlib.error:
+        return b""
+
+
+def is_sorted_bam(filepath):
+    """First line of the decompressed stream contains SO:coordinate (tools.py:169-186)."""
+    data = _bgzf_first_block(filepath)
+    return b"SO:coordinate" in data.split(b"\n", 1)[0].strip()
+
+
+def check_bam_files(bam_files):  # tools.py:189-207
+    if not all(filepath.exists() for filepath in bam_files):
+        logger.error("At least one of the supplied BAM files does not exist.")
+        sys.exit(1)
+    if not all(is_sorted_bam(filepath) for filepath in bam_files):
+        logger.error(
+            "At least one of the supplied BAM files is not sorted by coordinate "
+            "or does not contain a valid header. You can sort it using `samtools sort`."
+        )
+        sys.exit(1)
+
+
+def read_fasta(filepath):
+    """Yields (id with '~' -> '_', description, sequence) per record (tools.py:210-240).
+    gzip / bzip2 / xz detected by magic bytes."""
+    from ._fasta import Fasta
+
+    with Fasta(filepath) as fa:
+        for i in range(len(fa.ids)):
+            yield fa.ids[i], fa.descriptions[i], fa.sequence(i)
+
+
+def get_tsv_coverages(filepath, contig_set=None):
+    """Tabular coverages: first column names, remaining columns per-sample coverage (tools.py:243-280)."""
+    with open(filepath) as fin:
+        ncols = len(fin.readline().split("\t"))
+    if ncols < 2:
+        logger.error("The tabular coverage file must have at least two columns.")
+        sys.exit(1)
+    contig_names_vector = np.genfromtxt(filepath, dtype=str, comments=None, delimiter="\t", usecols=0)
+    coverage_vector = np.genfromtxt(filepath, dtype=float, comments=None, delimiter="\t", usecols=range(1, ncols))
+    contig_names_vector = np.atleast_1d(contig_names_vector)
+    if coverage_vector.ndim <= 1:
+        coverage_vector = coverage_vector.reshape(len(contig_names_vector), -1)
+    if contig_set:
+        mask = np.array([contig in contig_set for contig in contig_names_vector])
+        contig_names_vector = contig_names_vector[mask]
+        coverage_vector = coverage_vector[mask, :]
+    return (contig_names_vector, coverage_vector)
+
+
+def write_module_output(score_list, score_output_file):  # tools.py:607-626
+    with open(score_output_file, "w") as fout:
+        header = "\t".join(score_list[0].attributes)
+        fout.write(f"{header}\n")
+        for mag_score in score_list:
+            for attributes in mag_score:
+                line = "\t".join(map(str, attributes))
+                fout.write(f"{line}\n")

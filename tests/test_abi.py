@@ -61,6 +61,7 @@ def test_product_never_imports_oracle():
         for fn in fns:
             if fn.endswith((".py", ".cu", ".h", ".cpp")):
                 txt = open(os.path.join(dp, fn)).read()
-                if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "mp2_oracle" in txt:
+                if (re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "libmp2_oracle" in txt
+                        or re.search(r"#include\s+[<\"][^>\"]*oracle", txt) or "mp2o_" in txt):
                     bad.append(fn)
     assert not bad, bad

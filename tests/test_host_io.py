@@ -1,0 +1,152 @@
+"""Host-side ingest (no GPU): libmp2's BAM reader against the oracle's per-record restatement of
+the reference filter + CIGAR walk, and the FASTA reader against the
+reference's record rules (tools.py:210-240, core.py:35-50)."""
+import bz2
+import gzip
+import lzma
+import os
+
+import numpy as np
+import pytest
+
+from magpurify2_b200 import _bam, _fasta, _lib, bamio, tools
+
+
+def _random_records(rng, lengths, n):
+    recs = []
+    tids = np.sort(rng.integers(0, len(lengths), n))
+    last_pos = {}
+    for tid in tids.tolist():
+        ln = lengths[tid]
+        if ln < 260:
+            continue
+        pos = int(rng.integers(last_pos.get(tid, 0), max(last_pos.get(tid, 0) + 1, ln - 255)))
+        last_pos[tid] = pos
+        kind = rng.integers(0, 6)
+        if kind == 0:
+            cig = [("M", 150)]
+        elif kind == 1:
+            cig = [("S", 10), ("M", 70), ("I", 2), ("M", 68)]
+        elif kind == 2:
+            cig = [("M", 60), ("D", 3), ("M", 90)]
+        elif kind == 3:
+            cig = [("=", 50), ("X", 1), ("=", 99)]
+        elif kind == 4:
+            cig = [("H", 5), ("M", 40), ("N", 20), ("M", 110), ("P", 1)]
+        else:
+            cig = [("M", int(rng.integers(30, 250)))]
+        flag = int(rng.choice([0, 0, 0, 0, 0x1, 0x2, 0x10, 0x100, 0x800, 0x400, 0x200]))
+        nm = int(rng.binomial(150, 0.012))
+        recs.append(dict(tid=int(tid), pos=pos, cigar=cig, flag=flag, nm=nm,
+                         nm_type=str(rng.choice(["C", "c", "S", "s", "I", "i"])),
+                         extra_aux=b"ASC\x05XSZabc\x00" if rng.random() < 0.3 else b""))
+    recs.append(dict(tid=-1, pos=-1, cigar=[], flag=0x4, nm=None, seq_len=20))
+    return recs
+
+
+@pytest.mark.parametrize("min_identity", [0.97, 0.0, 0.99])
+def test_bam_reader_matches_record_oracle(tmp_path, oracle, min_identity):
+    rng = np.random.default_rng(41)
+    names = [f"contig_{i}" for i in range(40)]
+    lengths = rng.integers(100, 5000, 40).tolist()
+    recs = _random_records(rng, lengths, 3000)
+    path = tmp_path / "x.bam"
+    bamio.write_bam(str(path), names, lengths, recs)
+    want = [[] for _ in names]
+    kept = 0
+    for r in recs:
+        cig = [(ln << 4) | bamio.CIGAR_OPS.index(op) for op, ln in r["cigar"]]
+        ev = oracle.record_events(r.get("flag", 0), r["tid"], r["pos"], cig, r["nm"], min_identity)
+        if ev:
+            kept += 1
+            want[r["tid"]] += ev
+    with _bam.BamEvents(path, min_identity, threads=3) as b:
+        assert b.names == names and b.lengths.tolist() == lengths
+        assert b.n_records == len(recs) and b.n_kept == kept
+        assert "SO:coordinate" in b.header_text
+        for t in range(len(names)):
+            got = list(zip(b.starts[b.ev_off[t]:b.ev_off[t + 1]].tolist(), b.ends[b.ev_off[t]:b.ev_off[t + 1]].tolist()))
+            assert got == want[t], t
+        assert b.max_span >= 150
+
+
+def test_bam_reader_many_blocks_and_threads(tmp_path):
+    """Records straddling BGZF blocks; result independent of the inflate thread count."""
+    rng = np.random.default_rng(42)
+    n = 60000
+    lengths = [200000, 300000]
+    tid = np.sort(rng.integers(0, 2, n))
+    pos = np.concatenate([np.sort(rng.integers(0, lengths[t] - 150, int((tid == t).sum()))) for t in (0, 1)])
+    nm = rng.binomial(150, 0.01, n)
+    path = tmp_path / "big.bam"
+    bamio.write_bam_fixed(str(path), ["a", "b"], lengths, tid, pos, nm)
+    keep = (np.float32(1.0) - nm.astype(np.float32) / np.float32(150)) >= np.float32(0.97)
+    with _bam.BamEvents(path, 0.97, threads=1) as b1, _bam.BamEvents(path, 0.97, threads=4) as b4:
+        assert b1.n_records == n and b1.n_kept == int(keep.sum())
+        assert np.array_equal(b1.starts, pos[keep]) and np.array_equal(b1.ends, pos[keep] + 150)
+        assert np.array_equal(b1.starts, b4.starts) and np.array_equal(b1.ev_off, b4.ev_off)
+        assert b1.ev_off.tolist() == [0, int((keep & (tid == 0)).sum()), int(keep.sum())]
+
+
+def test_bam_reader_errors(tmp_path):
+    p = tmp_path / "nm.bam"
+    bamio.write_bam(str(p), ["c"], [1000], [dict(tid=0, pos=1, cigar=[("M", 50)], nm=None)])
+    with pytest.raises(_lib.Mp2Error) as ei:  # the reference panics on a missing NM tag
+        _bam.BamEvents(p, 0.97)
+    assert ei.value.code == _lib.EFORMAT and "NM" in str(ei.value)
+    with _bam.BamEvents(p, 0.0) as b:  # no identity filter -> NM is not needed
+        assert b.n_kept == 1
+    q = tmp_path / "unsorted.bam"
+    bamio.write_bam(str(q), ["c", "d"], [1000, 1000], [dict(tid=1, pos=1, cigar=[("M", 50)]),
+                                                       dict(tid=0, pos=1, cigar=[("M", 50)])])
+    with pytest.raises(_lib.Mp2Error):
+        _bam.BamEvents(q, 0.97)
+    with pytest.raises(OSError):
+        _bam.BamEvents(tmp_path / "missing.bam")
+    junk = tmp_path / "junk.bam"
+    junk.write_bytes(b"not a bam file at all" * 10)
+    with pytest.raises(OSError):
+        _bam.BamEvents(junk)
+
+
+def test_sorted_header_check(tmp_path):
+    from pathlib import Path
+
+    a, b = tmp_path / "s.bam", tmp_path / "u.bam"
+    bamio.write_bam(str(a), ["c"], [1000], [])
+    bamio.write_bam(str(b), ["c"], [1000], [], sort_order="unsorted")
+    assert tools.is_sorted_bam(Path(a)) and not tools.is_sorted_bam(Path(b))
+
+
+FA = ">c~1 first contig\nACGT\nacgtN\r\n>c2\n\n>c3\tx y\nAC GT\nTT\n"
+
+
+@pytest.mark.parametrize("opener,ext", [(open, ".fa"), (gzip.open, ".fa.gz"), (bz2.open, ".fa.bz2"), (lzma.open, ".fa.xz")])
+def test_fasta_reader(tmp_path, opener, ext):
+    from pathlib import Path
+
+    from magpurify2_b200.core import Mag
+
+    p = tmp_path / ("genome.v1" + ext)
+    with opener(p, "wt") as f:
+        f.write(FA)
+    recs = list(tools.read_fasta(p))
+    assert recs == [("c_1", "c~1 first contig", "ACGTacgtN"), ("c2", "c2", ""), ("c3", "c3\tx y", "ACGTTT")]
+    mag = Mag(Path(p))
+    assert mag.genome == "genome.v1"  # double stem for compressed files (core.py:37-39)
+    assert mag.contigs == ["c_1", "c2", "c3"] and mag.lengths.tolist() == [9, 0, 6]
+    assert mag.sequences == ["ACGTacgtN", "", "ACGTTT"] and len(mag) == 3
+    assert Mag(Path(p), store_sequences=False).sequences == []
+
+
+def test_validade_input_and_signature(tmp_path):
+    assert tools.validade_input(5, "x", [1, 3]) == 3 and tools.validade_input(0.5, "x", [0.0, 1.0]) == 0.5
+    p = tmp_path / "f.bin"
+    p.write_bytes(os.urandom(200000))
+    import hashlib
+
+    assert tools.get_file_signature(p) == hashlib.sha256(p.read_bytes()[-128000:]).hexdigest()
+    small = tmp_path / "s.bin"
+    small.write_bytes(b"x" * 10)
+    with pytest.raises(OSError):  # as the reference: seek(-128000) fails on small files
+        tools.get_file_signature(small)

@@ -1,0 +1,164 @@
+"""GPU parity of the remaining entry points: 2-bit packed composition path, get_bam_coverages on
+real BAM files, and the two module drivers end to end (FASTA + BAM in, TSV out)."""
+import gzip
+import pickle
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_packed_path_matches_ascii_and_oracle(oracle):
+    import torch
+
+    from magpurify2_b200 import _lib, synth
+
+    lib = _lib.load()
+    d = synth.make_mags(3, seed=7, mean_bp=6e5, n_contigs=90)
+    rng = np.random.default_rng(7)
+    bases = d["bases"].copy()
+    bases[rng.integers(0, len(bases), 500)] = ord("N")
+    for off_extra in (0, 1):  # also a stream whose length is not a multiple of 64
+        b = bases[:len(bases) - off_extra * 13]
+        offsets = d["offsets"].copy()
+        offsets[-1] = len(b)
+        n, L = len(offsets) - 1, len(b)
+        want = oracle.get_tnf_concat(b, offsets, relative=False, threads=4)
+        want_gc = oracle.get_gc_concat(b, offsets)
+        nq = (L + 63) // 64
+        d_b = torch.from_numpy(b).cuda()
+        codes = torch.zeros(nq * 4, dtype=torch.int32, device="cuda")
+        valid = torch.zeros(nq * 2, dtype=torch.int32, device="cuda")
+        s = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.mp2_pack_device(d_b.data_ptr(), L, codes.data_ptr(), valid.data_ptr(), s))
+        # the packed form itself: 2 bits per base first-base-most-significant, valid bit per base
+        hb = np.frombuffer(b.tobytes().upper(), dtype=np.uint8)
+        lut = np.full(256, 255, np.uint8)
+        lut[[65, 67, 71, 84]] = [0, 1, 2, 3]
+        c = lut[hb]
+        v = (c != 255)
+        pad = nq * 64 - L
+        c2 = np.concatenate([np.where(v, c, 0), np.zeros(pad, np.uint8)]).reshape(-1, 16).astype(np.uint32)
+        want_codes = (c2 << (2 * (15 - np.arange(16, dtype=np.uint32)))).sum(axis=1).astype(np.uint32)
+        v2 = np.concatenate([v, np.zeros(pad, bool)]).reshape(-1, 32).astype(np.uint64)
+        want_valid = (v2 << (31 - np.arange(32, dtype=np.uint64))).sum(axis=1).astype(np.uint32)
+        assert np.array_equal(codes.cpu().numpy().view(np.uint32), want_codes)
+        assert np.array_equal(valid.cpu().numpy().view(np.uint32), want_valid)
+        off = torch.from_numpy(offsets).cuda()
+        counts = torch.empty((n, 136), dtype=torch.int32, device="cuda")
+        gc = torch.empty(n, dtype=torch.float32, device="cuda")
+        rel = torch.empty((n, 136), dtype=torch.float32, device="cuda")
+        _lib.check(lib.mp2_tnf_packed_device(codes.data_ptr(), valid.data_ptr(), off.data_ptr(), n, L,
+                                             counts.data_ptr(), rel.data_ptr(), gc.data_ptr(), s))
+        torch.cuda.synchronize()
+        assert np.array_equal(counts.cpu().numpy().view(np.uint32), want)
+        assert np.array_equal(gc.cpu().numpy(), want_gc, equal_nan=True)
+
+
+def _write_dataset(tmp, n_mags=4, n_samples=3, seed=9):
+    """FASTA files + coordinate-sorted BAMs of a small synthetic community."""
+    from magpurify2_b200 import bamio, synth
+
+    d = synth.make_mags(n_mags, seed=seed, mean_bp=2.5e5, n_contigs=40)
+    names, genomes = [], []
+    for m in range(n_mags):
+        path = tmp / f"mag{m}.fna" if m % 2 else tmp / f"mag{m}.fna.gz"
+        opener = open if m % 2 else gzip.open
+        with opener(path, "wt") as f:
+            for c in range(d["mag_off"][m], d["mag_off"][m + 1]):
+                nm = f"m{m}_c{c}"
+                names.append(nm)
+                seq = d["bases"][d["offsets"][c]:d["offsets"][c + 1]].tobytes().decode()
+                f.write(f">{nm} len={len(seq)}\n")
+                for o in range(0, len(seq), 80):
+                    f.write(seq[o:o + 80] + "\n")
+        genomes.append(path)
+    bams, events = [], []
+    rng = np.random.default_rng(seed)
+    for s in range(n_samples):
+        st, en, ev_off = synth.make_events(d["lengths"], d["mag_off"], s, seed=seed, depth_scale=0.5)
+        tid = np.repeat(np.arange(len(d["lengths"])), np.diff(ev_off))
+        nm = rng.binomial(150, 0.012, len(st))
+        flag = rng.choice([0, 1, 0x100, 0x800, 0x400], len(st), p=[0.9, 0.05, 0.02, 0.02, 0.01])
+        p = tmp / f"sample{s}.bam"
+        bamio.write_bam_fixed(str(p), names, d["lengths"], tid, st, nm, flag=flag)
+        keep = ((np.float32(1.0) - nm.astype(np.float32) / np.float32(150)) >= np.float32(0.97)) & ((flag & 0x900) == 0)
+        k_off = np.concatenate([[0], np.cumsum(np.bincount(tid[keep], minlength=len(d["lengths"])))])
+        events.append((st[keep], en[keep], k_off))
+        bams.append(p)
+    return d, names, genomes, bams, events
+
+
+def test_get_bam_coverages(tmp_path, oracle):
+    from magpurify2_b200 import tools
+
+    d, names, _g, bams, events = _write_dataset(tmp_path)
+    got_names, mat = tools.get_bam_coverages([str(b) for b in bams], min_identity=0.97, trim_lower=0.05,
+                                             trim_upper=0.05, threads=4)
+    assert got_names == names and mat.dtype == np.float32 and mat.shape == (len(names), len(bams))
+    for s, (st, en, k_off) in enumerate(events):
+        want, _ = oracle.cov_sample(st, en, k_off, d["lengths"], 75, 0.05, 0.05, threads=4)
+        assert np.array_equal(mat[:, s], want)
+    sub = set(names[5:25])
+    n2, m2 = tools.get_bam_coverages([str(bams[0])], contig_set=sub, trim_lower=0.05, trim_upper=0.05)
+    assert n2 == names[5:25] and np.array_equal(m2[:, 0], mat[5:25, 0])
+    with pytest.raises(TypeError):
+        tools.get_bam_coverages(str(bams[0]))
+
+
+def test_cli_composition_and_coverage(tmp_path, oracle):
+    from magpurify2_b200 import cli
+
+    d, names, genomes, bams, events = _write_dataset(tmp_path, n_mags=4, n_samples=3, seed=11)
+    out = tmp_path / "out"
+    assert cli.cli(["composition", *map(str, genomes), str(out), "-q"]) == 0
+    assert cli.cli(["coverage", *map(str, genomes), str(out), "--bam_files", *map(str, bams), "-q", "-t", "4"]) == 0
+    # ---- composition TSV ----
+    rows = [l.rstrip("\n").split("\t") for l in open(out / "scores" / "composition_scores.tsv")]
+    assert rows[0] == ["genome", "contig", "tnf_score", "gc_content_score", "contig_length"]
+    assert [r[1] for r in rows[1:]] == names
+    assert rows[1][0] == "mag0" and rows[-1][0] == "mag3"
+    gc = oracle.get_gc_concat(d["bases"], d["offsets"])
+    for m in range(4):
+        sl = slice(d["mag_off"][m], d["mag_off"][m + 1])
+        want, _ = oracle.log_ratio_scores(gc[sl], d["lengths"][sl], 2)
+        got = np.array([float(r[3]) for r in rows[1:][sl]])
+        assert np.allclose(got, np.round(want, 5), atol=1.1e-5, equal_nan=True)
+        counts = oracle.get_tnf_concat(d["bases"][d["offsets"][sl.start]:d["offsets"][sl.stop]],
+                                       d["offsets"][sl.start:sl.stop + 1] - d["offsets"][sl.start], relative=False)
+        _clr, dist = oracle.clr_centroid(counts, d["lengths"][sl])
+        # tnf_score = 1 - max(0, log4(d / weighted median d)), from the oracle's pieces
+        med = oracle.weighted_median(dist.astype(np.float32), d["lengths"][sl])
+        lg = np.log((dist.astype(np.float32) + np.float32(1e-5)) / (med + np.float32(1e-5))) / np.log(4.0)
+        want_tnf = np.clip(1.0 - np.maximum(lg, 0.0), 0, 1)
+        got_tnf = np.array([float(r[2]) for r in rows[1:][sl]])
+        assert np.allclose(got_tnf, want_tnf, atol=2e-5)
+        assert [int(r[4]) for r in rows[1:][sl]] == d["lengths"][sl].tolist()
+    with gzip.open(out / "tnfs.pickle.gz") as f:
+        tn = pickle.load(f)
+    assert sorted(tn) == ["mag0", "mag1", "mag2", "mag3"] and tn["mag0"].dtype == np.float32
+    assert np.array_equal(np.concatenate([tn[f"mag{m}"] for m in range(4)]),
+                          oracle.get_tnf_concat(d["bases"], d["offsets"], relative=True))
+    # ---- coverage TSV ----
+    rows = [l.rstrip("\n").split("\t") for l in open(out / "scores" / "coverage_scores.tsv")]
+    assert rows[0] == ["genome", "contig", "coverage_score", "coverage_cluster_score", "n_samples"]
+    cov = np.stack([oracle.cov_sample(st, en, k, d["lengths"], 75, 0.05, 0.05)[0] for st, en, k in events], axis=1)
+    for m in range(4):
+        sl = slice(d["mag_off"][m], d["mag_off"][m + 1])
+        sel, _ = oracle.select_samples(cov[sl], d["lengths"][sl], 1.0)
+        got = np.array([float(r[2]) for r in rows[1:][sl]])
+        if sel.any():
+            want, _ = oracle.log_ratio_scores(cov[sl][:, sel], d["lengths"][sl], 25)
+            assert np.allclose(got, np.round(want, 5), atol=1.1e-5)
+        else:
+            assert (got == 1.0).all()
+        assert all(int(r[4]) == int(sel.sum()) for r in rows[1:][sl])
+    with gzip.open(out / "coverages.pickle.gz") as f:
+        sig, cn, mat = pickle.load(f)
+    assert len(sig) == 3 and list(cn) == names and np.array_equal(mat, cov)
+    # second run hits the cache (BAMs are not opened again: remove them to prove it)
+    for b in bams[1:]:
+        b.write_bytes(b.read_bytes())  # same content, same signature
+    assert cli.cli(["coverage", *map(str, genomes), str(out), "--bam_files", *map(str, bams), "-q"]) == 0
