@@ -121,7 +121,7 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     def step():
         for s, (st, en, eo, R) in enumerate(samples):
             _lib.check(lib.mp2_cov_events_device(st.data_ptr(), en.data_ptr(), eo.data_ptr(), d_off.data_ptr(),
-                                                 n, R, L, 75, args.trim, args.trim,
+                                                 n, R, L, args.max_span, 75, args.trim, args.trim,
                                                  cov.data_ptr() + 4 * s, S, None, stream))
 
     for _ in range(args.warmup):
@@ -140,7 +140,8 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     ms = e0.elapsed_time(e1)
     launches = lib.mp2_launch_count() - l0
     kern = {}
-    for name in ("cov_scatter_kernel", "cov_depth_kernel", "cov_deep_kernel", "cov_tile_scan_kernel"):
+    for name in ("cov_tile_kernel", "cov_scatter_kernel", "cov_depth_kernel", "cov_deep_kernel", "cov_check_kernel",
+                 "cov_bounds_kernel", "cov_zero_kernel"):
         k_ms, k_n = C.c_double(0), C.c_int64(0)
         lib.mp2_profile_read(name.encode(), C.byref(k_ms), C.byref(k_n))
         kern[name] = (k_ms.value, k_n.value)
@@ -182,7 +183,8 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     per_launch = lambda k: kern[k][0] / max(1, kern[k][1])
     R_avg = R_total / S
     rl = []
-    for name, bytes_ in (("cov_depth_kernel", 4.0 * (L + 1)), ("cov_scatter_kernel", 8.0 * R_avg + 8.0 * R_avg)):
+    for name, bytes_ in (("cov_tile_kernel", 8.0 * R_avg + 16.0 * (L / 16384.0) + 4.0 * n),
+                         ("cov_depth_kernel", 4.0 * (L + 1)), ("cov_scatter_kernel", 8.0 * R_avg + 8.0 * R_avg)):
         t_ms = per_launch(name)
         ach = bytes_ / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
         rl.append({"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -271,6 +273,7 @@ def main():
     ap.add_argument("--long-contigs", action="store_true", help="C5 shape instead of C3")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--trim", type=float, default=0.05)
+    ap.add_argument("--max-span", type=int, default=150, help="0 = let the library check BAM order on the device")
     ap.add_argument("--depth-scale", type=float, default=1.0)
     args = ap.parse_args()
     if args.impl == "reference":

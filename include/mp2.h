@@ -111,18 +111,24 @@ typedef struct {
  *   d_cov   : float32, element c at d_cov[c*cov_stride] -- cov_stride = n_bams writes column s of
  *             the reference's float32[n_contigs, n_bams] matrix in place        (REQUIRED)
  *   d_stats : mp2_cov_stats[n_contigs]    or NULL
+ * max_span: > 0 = the caller guarantees that starts are non-decreasing inside every contig (BAM
+ *           coordinate order) and that end - start <= max_span for every block: the difference
+ *           array is then built tile by tile in shared memory and never touches HBM.
+ *           0 = unknown: the library checks both on the device first and falls back to the
+ *           general path (difference array in HBM, any order) when the starts are not sorted.
+ * Contigs that reach depth >= 1023 also go through the general path (exact for any depth).
  * trim_lower + trim_upper must be < 1 (the CLI clamps both, magpurify2/modules/coverage.py:39-49). */
 int mp2_cov_events_device(const void *d_starts, const void *d_ends, const void *d_ev_off,
                           const void *d_contig_off, int64_t n_contigs, int64_t n_events,
-                          int64_t n_positions, uint32_t end_excl, float trim_lower,
-                          float trim_upper, void *d_cov, int64_t cov_stride, void *d_stats,
-                          void *stream);
+                          int64_t n_positions, uint32_t max_span, uint32_t end_excl,
+                          float trim_lower, float trim_upper, void *d_cov, int64_t cov_stride,
+                          void *d_stats, void *stream);
 
 /* Host-buffer form of the same call (stages H2D/D2H itself). */
 int mp2_cov_events(const uint32_t *starts, const uint32_t *ends, const int64_t *ev_off,
                    const int64_t *contig_off, int64_t n_contigs, int64_t n_events,
-                   uint32_t end_excl, float trim_lower, float trim_upper, int device, float *cov,
-                   int64_t cov_stride, mp2_cov_stats *stats);
+                   uint32_t max_span, uint32_t end_excl, float trim_lower, float trim_upper,
+                   int device, float *cov, int64_t cov_stride, mp2_cov_stats *stats);
 
 /* ---- scoring: replaces tools.get_log_ratio_scores / get_weighted_median ----------------- */
 /* (magpurify2/tools.py:283-351; callers magpurify2/core.py:261-263 base 2, :310-312 base 25) */

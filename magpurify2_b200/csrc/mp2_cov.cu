@@ -19,6 +19,9 @@
 //                        the last contributor.  D is read exactly once (4 B/position).
 //   cov_deep_kernel      exact fallback for contigs that reach depth >= 1023 (multi-pass over
 //                        depth ranges; rare).
+#include <climits>
+#include <cstdlib>
+
 #include "mp2_common.h"
 
 namespace mp2 {
@@ -42,6 +45,11 @@ struct RowMeta {
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ void smem_inc(uint32_t saddr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory");
+}
+
+// predicated form: no branch around the reduction
+__device__ __forceinline__ void smem_inc_if(uint32_t saddr, uint32_t cond) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(saddr), "r"(cond) : "memory");
 }
 
 // upper_bound(a[lo..hi), x) - 1 : largest i in [lo, hi) with a[i] <= x (lo if none)
@@ -123,10 +131,11 @@ __device__ __forceinline__ void write_result(int64_t c, uint64_t N, uint64_t cov
 // ---- per-contig initialisation: contigs without a window get their final answer here --------
 __global__ void cov_init_kernel(const int64_t *__restrict__ off, int64_t n, uint32_t excl,
                                 float *__restrict__ cov, int64_t cov_stride,
-                                mp2_cov_stats *__restrict__ stats) {
+                                mp2_cov_stats *__restrict__ stats, int *__restrict__ gate) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= n) return;
     const int64_t len = off[c + 1] - off[c];
+    if (len >= (1ll << 30)) *gate = 1;  // the tile path keeps 32-bit tile-relative coordinates
     if (2ll * excl >= len) write_result(c, 0, 0, 0, 0, 0, 0, 0, cov, cov_stride, stats);
 }
 
@@ -143,7 +152,8 @@ __global__ void __launch_bounds__(256)
 cov_scatter_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends,
                    const int64_t *__restrict__ ev_off, const int64_t *__restrict__ off, int64_t n,
                    int64_t n_events, const int32_t *__restrict__ ev_first, int32_t *__restrict__ D,
-                   int32_t *__restrict__ tile_sum) {
+                   int32_t *__restrict__ tile_sum, const int *__restrict__ gate) {
+    if (gate && *gate == 0) return;  // fallback leg with nothing to do
     const int64_t t0 = (int64_t)blockIdx.x * COV_EV_TILE;
     const int64_t c_lo = ev_first[blockIdx.x];
     const int64_t t_last = t0 + COV_EV_TILE - 1 < n_events - 1 ? t0 + COV_EV_TILE - 1 : n_events - 1;
@@ -180,9 +190,18 @@ cov_scatter_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restri
     }
 }
 
+// gated zero fill of D (general path used as a fallback: skip the 4 B/slot write when not needed)
+__global__ void cov_zero_kernel(int4 *__restrict__ p, int64_t n16, const int *__restrict__ gate) {
+    if (gate && *gate == 0) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = make_int4(0, 0, 0, 0);
+}
+
 // ---- exclusive scan of the tile sums (n_tiles is small: L / 65536) -------------------------------
 __global__ void __launch_bounds__(1024)
-cov_tile_scan_kernel(const int32_t *__restrict__ tile_sum, int64_t n_tiles, int32_t *__restrict__ tile_pre) {
+cov_tile_scan_kernel(const int32_t *__restrict__ tile_sum, int64_t n_tiles, int32_t *__restrict__ tile_pre,
+                     const int *__restrict__ gate) {
+    if (gate && *gate == 0) return;
     __shared__ int s_w[32];
     __shared__ int s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -230,6 +249,7 @@ struct DepthArgs {
     int32_t *deep_list;       // contigs needing the exact fallback
     int *deep_count;
     int *work_counter;
+    const int *gate;          // general path as a fallback: run only when *gate != 0 (NULL = always)
     float *cov;
     int64_t cov_stride;
     mp2_cov_stats *stats;
@@ -254,6 +274,7 @@ __device__ __forceinline__ void finish_contig(const DepthArgs &a, int64_t c, uin
 
 __global__ void __launch_bounds__(COV_THREADS)
 cov_depth_kernel(const DepthArgs a) {
+    if (a.gate && *a.gate == 0) return;
     __shared__ uint32_t s_hist[COV_BINS];
     __shared__ int s_wsum[COV_THREADS / 32];
     __shared__ unsigned int s_maxd;
@@ -433,6 +454,7 @@ cov_depth_kernel(const DepthArgs a) {
 // re-scanning the contig's slice of D (the prefix restarts at 0 at a contig start).
 __global__ void __launch_bounds__(COV_THREADS)
 cov_deep_kernel(const DepthArgs a, int *__restrict__ deep_next) {
+    if (a.gate && *a.gate == 0) return;
     __shared__ uint32_t s_hist[COV_DEEP_BINS];
     __shared__ int s_wsum[COV_THREADS / 32];
     __shared__ unsigned int s_maxd;
@@ -514,15 +536,473 @@ cov_deep_kernel(const DepthArgs a, int *__restrict__ deep_next) {
     }
 }
 
+
+// =====================================================================================================
+// Fast path: the difference array never leaves shared memory.
+//
+// Precondition (checked by cov_check_kernel unless the caller vouches for it with max_span > 0):
+// starts are non-decreasing inside every contig and end - start <= max_span.  Then the blocks that
+// can touch the slots [lo, hi) of the concatenated coordinate space are one contiguous range of
+// the event arrays (global start in [lo - max_span, hi)), found by two binary searches.
+// One CTA owns a tile of 16384 slots: zero a 68 KB shared array, apply the range's +1 / -1 with
+// shared-memory reductions, count the blocks that are open at the tile start (= the depth just
+// before the tile), then run the same scan / window histogram / trimmed-mean code as the
+// general path, reading the differences from shared memory.  HBM traffic: the events, once
+// (plus max_span/16384 of them twice), and the results.
+// =====================================================================================================
+constexpr int CT_TILE = 16384;
+constexpr int CT_NSUB = CT_TILE / COV_SUB;        // 4
+constexpr int CT_WORDS = CT_TILE + CT_TILE / 16;  // one pad word per 16: a thread's 16 slots are conflict-free
+constexpr size_t CT_SMEM = sizeof(int32_t) * CT_WORDS;
+
+__device__ __forceinline__ int ct_phys(int i) { return i + (i >> 4); }
+
+// first event whose global start (off[contig] + start) is >= X
+__device__ __forceinline__ int64_t first_event_ge(const uint32_t *__restrict__ starts, const int64_t *__restrict__ ev_off,
+                                                  const int64_t *__restrict__ off, int64_t n, int64_t X) {
+    if (X <= 0) return 0;
+    if (X >= off[n]) return ev_off[n];
+    const int64_t c = last_le(off, 0, n, X);  // contig holding slot X
+    const int64_t want = X - off[c];
+    int64_t lo = ev_off[c], hi = ev_off[c + 1];
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)starts[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void cov_bounds_kernel(const uint32_t *__restrict__ starts, const int64_t *__restrict__ ev_off,
+                                  const int64_t *__restrict__ off, int64_t n, int64_t n_tiles, uint32_t max_span,
+                                  const unsigned int *__restrict__ d_span, int64_t *__restrict__ e_lo,
+                                  int64_t *__restrict__ e_hi, int32_t *__restrict__ c_lo,
+                                  int32_t *__restrict__ c_hi) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n_tiles) return;
+    if (d_span) max_span = *d_span;  // measured by cov_check_kernel
+    const int64_t A = k * CT_TILE - (int64_t)max_span, B = (k + 1) * CT_TILE;
+    e_lo[k] = first_event_ge(starts, ev_off, off, n, A);
+    e_hi[k] = first_event_ge(starts, ev_off, off, n, B);
+    // every event of [e_lo, e_hi) belongs to a contig overlapping the slots [A, B)
+    c_lo[k] = (int32_t)last_le(off, 0, n, A > 0 ? A : 0);
+    c_hi[k] = (int32_t)last_le(off, 0, n, B - 1 < off[n] ? B - 1 : off[n]);
+}
+
+// sortedness + span check: flag[0] = 1 when some contig's starts decrease, flag[1] = max(end - start)
+__global__ void cov_check_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends,
+                                 const int64_t *__restrict__ ev_off, int64_t n, int64_t n_events,
+                                 const int32_t *__restrict__ ev_first, unsigned int *__restrict__ flag) {
+    const int64_t t0 = (int64_t)blockIdx.x * COV_EV_TILE;
+    unsigned int bad = 0, span = 0;
+    for (int k = 0; k < COV_EV_TILE / 256; k++) {
+        const int64_t e = t0 + k * 256 + threadIdx.x;
+        if (e < n_events) {
+            const uint32_t s = starts[e], en = ends[e];
+            if (en > s && en - s > span) span = en - s;
+            if (e > 0 && starts[e - 1] > s) {
+                // a decrease is fine only at a contig boundary: e must be the first event of its contig
+                const int64_t c = last_le(ev_off, ev_first[blockIdx.x], n, e);
+                if (ev_off[c] != e) bad = 1;
+            }
+        }
+    }
+    span = __reduce_max_sync(0xffffffffu, span);
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicOr(&flag[0], 1u);
+        if (span) atomicMax(&flag[1], span);
+    }
+}
+
+constexpr int CT_CTAB = 96;  // contigs of a tile whose offsets are staged in shared memory
+constexpr int CT_DEEP_ROWS = 256;     // contigs per sample that may exceed the shared histogram's depth range
+constexpr int CT_DEEP_BINS = 32768;   // depths COV_BINS-1 .. COV_BINS-2+32768 are counted in the deep pool
+
+struct TileArgs {
+    const uint32_t *starts, *ends;
+    const int64_t *ev_off, *off;
+    int64_t n, n_pos, n_tiles;
+    const int64_t *e_lo, *e_hi;
+    const int32_t *c_lo, *c_hi;  // contigs the tile's events can belong to
+    uint32_t *rows;              // [n_tiles][COV_BINS]
+    RowMeta *meta;
+    int32_t *deep_list;
+    int *deep_count;
+    int *work_counter;
+    int32_t *deep_row_of;       // [n] -1 = none; row of the deep pool claimed by the contig
+    uint32_t *deep_pool;        // [CT_DEEP_ROWS][CT_DEEP_BINS] counts of depths >= COV_BINS - 1
+    int *deep_rows_used;
+    const unsigned int *check;  // NULL, or check[0] != 0 => the precondition failed: do nothing
+    int *gate_out;              // set to 1 when the general path has to run instead
+    float *cov;
+    int64_t cov_stride;
+    mp2_cov_stats *stats;
+    TrimParams tp;
+};
+
+// Finish contig c by warp 0.  Depths 0..COV_BINS-2 come from `load` (shared histogram or the
+// contig's global row); deeper positions were counted in the contig's row of the deep pool.
+template <class Load>
+__device__ __forceinline__ void finish_contig_t(const TileArgs &a, int64_t c, uint64_t N, uint32_t maxd, Load load) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t *deep = nullptr;
+    if (maxd >= COV_BINS - 1) {
+        const int r = *((volatile int32_t *)&a.deep_row_of[c]);
+        if (r < 0 || maxd >= (uint32_t)(COV_BINS - 1 + CT_DEEP_BINS)) {  // pool exhausted / beyond its range
+            if (lane == 0) {
+                a.deep_list[atomicAdd(a.deep_count, 1)] = (int32_t)c;
+                *a.gate_out = 1;  // the exact general path redoes this sample
+            }
+            return;
+        }
+        deep = a.deep_pool + (size_t)r * CT_DEEP_BINS;
+    }
+    uint64_t mn, mx;
+    trim_indices(N, a.tp, mn, mx);
+    const uint64_t covered = N - (uint64_t)load(0);
+    unsigned long long acc = 0, total = 0;
+    if (covered) {
+        const uint32_t top = maxd + 1 < COV_BINS - 1 ? maxd + 1 : COV_BINS - 1;
+        trim_walk_warp(load, 0, top, mn, mx, acc, total);
+        if (deep)
+            trim_walk_warp([&](uint32_t i) { return __ldcg(deep + (i - (COV_BINS - 1))); }, COV_BINS - 1, maxd + 1, mn, mx,
+                           acc, total);
+    }
+    if (lane == 0) write_result(c, N, covered, mn, mx, total, maxd, 0, a.cov, a.cov_stride, a.stats);
+}
+
+// Rare: depths beyond the shared histogram's range are counted in the contig's row of the deep pool
+// (claimed on first use).  Called by the lanes of a warp that hold such positions.
+__device__ __noinline__ void ct_deep_positions(const TileArgs &a, int64_t c, const int *d, uint32_t m) {
+    const int lane = threadIdx.x & 31;
+    int r = 0;
+    const unsigned grp = __activemask();
+    const int leader = __ffs(grp) - 1;
+    if (lane == leader) {
+        r = atomicAdd(&a.deep_row_of[c], 0);
+        if (r == -1) {
+            const int old = atomicCAS(&a.deep_row_of[c], -1, -2);
+            if (old == -1) {
+                const int k2 = atomicAdd(a.deep_rows_used, 1);
+                r = k2 < CT_DEEP_ROWS ? k2 : -3;
+                atomicExch(&a.deep_row_of[c], r);
+            } else {
+                r = old;
+            }
+        }
+        while (r == -2) r = atomicAdd(&a.deep_row_of[c], 0);
+    }
+    r = __shfl_sync(grp, r, leader);
+    if (r >= 0) {
+        uint32_t *dr = a.deep_pool + (size_t)r * CT_DEEP_BINS;
+        for (int k = 0; k < COV_ITEMS; k++) {
+            const int v = d[k] - (COV_BINS - 1);
+            if ((m & (1u << k)) && v >= 0 && v < CT_DEEP_BINS) atomicAdd(&dr[v], 1u);
+        }
+        __threadfence();
+    }
+}
+
+__device__ __forceinline__ int clamp_rel(int64_t v) {  // tile-relative coordinate, saturated
+    return v < -(1ll << 30) ? -(1 << 30) : (v > (1ll << 30) ? (1 << 30) : (int)v);
+}
+
+// All coordinates inside the kernel are 32-bit and relative to the tile start (or to the tile's
+// first event); the contigs a tile can see are staged in shared memory (offset, length, first
+// event), CT_CTAB at a time -- a tile crowded with more (tiny) contigs walks them in batches.
+__global__ void __launch_bounds__(COV_THREADS, 3)
+cov_tile_kernel(const TileArgs a) {
+    extern __shared__ __align__(16) int32_t s_T[];  // CT_WORDS
+    __shared__ uint32_t s_hist[COV_BINS];
+    __shared__ int s_wsum[COV_THREADS / 32];
+    __shared__ unsigned int s_maxd;
+    __shared__ int s_tile, s_last, s_carry;
+    __shared__ int s_crel[CT_CTAB + 1];  // contig start - tile_lo (saturated)
+    __shared__ int s_cev[CT_CTAB + 1];   // contig's first event - E0 (saturated)
+
+    if (a.check && a.check[0] != 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *a.gate_out = 1;
+        return;
+    }
+    if (*((volatile int *)a.gate_out)) return;  // the general path redoes the whole sample anyway
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t h0 = (uint32_t)__cvta_generic_to_shared(s_hist);
+    const int excl = (int)a.tp.excl;
+    for (int i = tid; i < COV_BINS; i += COV_THREADS) s_hist[i] = 0;
+    if (tid == 0) s_maxd = 0;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= a.n_tiles) break;
+        const int64_t tile_lo = tile * CT_TILE;
+        const int tlen = (int)(tile_lo + CT_TILE < a.n_pos ? CT_TILE : a.n_pos - tile_lo);
+        const int64_t E0 = a.e_lo[tile], E1 = a.e_hi[tile];
+        const int nev = (int)(E1 - E0);
+        const int64_t ca = a.c_lo[tile], cb = a.c_hi[tile];
+
+        // ---- zero the tile, stage the contig table ----
+        for (int i = tid; i < CT_WORDS / 4; i += COV_THREADS) reinterpret_cast<int4 *>(s_T)[i] = make_int4(0, 0, 0, 0);
+        if (tid == 0) s_carry = 0;
+        int open = 0;
+        // ---- events: +1 at the start, -1 at the end, blocks open across the tile start ----
+        for (int64_t cbase = ca; cbase <= cb; cbase += CT_CTAB) {
+            const int nc = (int)(cb - cbase + 1 < CT_CTAB ? cb - cbase + 1 : CT_CTAB);
+            __syncthreads();
+            for (int i = tid; i <= nc; i += COV_THREADS) {
+                s_crel[i] = clamp_rel(a.off[cbase + i] - tile_lo);
+                s_cev[i] = clamp_rel(a.ev_off[cbase + i] - E0);
+            }
+            __syncthreads();
+            // events of this batch of contigs: [max(0, cev[0]), min(nev, cev[nc]))
+            const int eb0 = s_cev[0] > 0 ? s_cev[0] : 0, eb1 = s_cev[nc] < nev ? s_cev[nc] : nev;
+            const int cv1 = nc > 1 ? s_cev[1] : INT_MAX, cv2 = nc > 2 ? s_cev[2] : INT_MAX, cv3 = nc > 3 ? s_cev[3] : INT_MAX;
+            for (int e0 = eb0 + tid; e0 < eb1; e0 += 4 * COV_THREADS) {
+                uint32_t sv[4], ev[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int e = e0 + u * COV_THREADS;
+                    sv[u] = e < eb1 ? __ldg(a.starts + E0 + e) : 0u;
+                    ev[u] = e < eb1 ? __ldg(a.ends + E0 + e) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int e = e0 + u * COV_THREADS;
+                    if (e >= eb1) break;
+                    int j = 0;
+                    if (nc <= 4) {
+                        j = (e >= cv1) + (e >= cv2) + (e >= cv3);
+                    } else {
+                        int lo = 0, hi = nc;  // largest j in [0, nc) with s_cev[j] <= e
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (s_cev[mid] <= e) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        j = lo > 0 ? lo - 1 : 0;
+                    }
+                    const int crel = s_crel[j];
+                    const uint32_t len = (uint32_t)(s_crel[j + 1] - crel);  // exact unless saturated (then irrelevant)
+                    const uint32_t s = sv[u];
+                    const uint32_t en = ev[u] < len ? ev[u] : len;
+                    if (s < len && en > s) {
+                        const uint32_t gs = (uint32_t)crel + s, ge = (uint32_t)crel + en;  // mod 2^32
+                        const uint32_t ncrel = crel < 0 ? (uint32_t)(-crel) : 0u;
+                        if (s >= ncrel) {
+                            if (gs < (uint32_t)tlen) atomicAdd(&s_T[ct_phys((int)gs)], 1);
+                        } else if (en >= ncrel) {
+                            open++;  // started before the tile and still covers slot tile_lo - 1
+                        }
+                        if (en >= ncrel && ge < (uint32_t)tlen) atomicAdd(&s_T[ct_phys((int)ge)], -1);
+                    }
+                }
+            }
+        }
+        open = __reduce_add_sync(0xffffffffu, open);
+        if (lane == 0 && open) atomicAdd(&s_carry, open);
+        __syncthreads();
+        int carry = s_carry;
+
+        // ---- scan + windows; contigs intersecting the tile are a sub-range of [ca, cb] ----
+        int64_t cbase = ca;                       // contig table currently staged: [cbase, cbase + nct]
+        int nct = (int)(cb - cbase + 1 < CT_CTAB ? cb - cbase + 1 : CT_CTAB);
+        if (cb - ca + 1 > CT_CTAB) {              // the event loop left the LAST batch staged: restage the first
+            __syncthreads();
+            for (int i = tid; i <= nct; i += COV_THREADS) s_crel[i] = clamp_rel(a.off[cbase + i] - tile_lo);
+            __syncthreads();
+        }
+        int64_t c = ca;
+        int wlo = 0, whi = -1;
+        bool have = false;
+        int in_tile = 0;
+
+        for (int sub = 0; sub < CT_NSUB; sub++) {
+            const int p0 = sub * COV_SUB;
+            if (p0 >= tlen) break;
+            const int p1 = p0 + COV_SUB < tlen ? p0 + COV_SUB : tlen;
+            const int q = p0 + tid * COV_ITEMS;
+            int d[COV_ITEMS];
+            {
+                const int b = ct_phys(q);
+#pragma unroll
+                for (int k = 0; k < COV_ITEMS; k++) d[k] = s_T[b + k];
+            }
+#pragma unroll
+            for (int k = 1; k < COV_ITEMS; k++) d[k] += d[k - 1];
+            int incl = d[COV_ITEMS - 1];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int wpre = 0, sub_total = 0;
+#pragma unroll
+            for (int w = 0; w < COV_THREADS / 32; w++) {
+                const int v = s_wsum[w];
+                if (w < warp) wpre += v;
+                sub_total += v;
+            }
+            const int tpre = carry + wpre + incl - d[COV_ITEMS - 1];
+#pragma unroll
+            for (int k = 0; k < COV_ITEMS; k++) d[k] += tpre;
+            carry += sub_total;
+
+            for (;;) {
+                if (!have) {
+                    if (c > cb) break;
+                    if (c - cbase >= nct) {  // next batch of the contig table
+                        __syncthreads();
+                        cbase = c;
+                        nct = (int)(cb - cbase + 1 < CT_CTAB ? cb - cbase + 1 : CT_CTAB);
+                        for (int i = tid; i <= nct; i += COV_THREADS) s_crel[i] = clamp_rel(a.off[cbase + i] - tile_lo);
+                        __syncthreads();
+                    }
+                    const int o0 = s_crel[c - cbase], o1 = s_crel[c - cbase + 1];
+                    if (o0 >= p1) break;
+                    if (o1 - o0 > 2 * excl) { wlo = o0 + excl; whi = o1 - excl - 1; }  // saturated ends stay far outside
+                    else { wlo = 0; whi = -1; }
+                    have = true;
+                    in_tile = 0;
+                }
+                if (whi < wlo || whi < 0) { c++; have = false; continue; }
+                if (wlo >= p1) break;
+                const int lo = wlo > p0 ? wlo : p0, hi = whi + 1 < p1 ? whi + 1 : p1;
+                if (hi > lo) {
+                    const int ja = lo - q > 0 ? (lo - q > COV_ITEMS ? COV_ITEMS : lo - q) : 0;
+                    const int jb = hi - q < COV_ITEMS ? (hi - q < 0 ? 0 : hi - q) : COV_ITEMS;
+                    if (jb > ja) {
+                        const uint32_t m = ((1u << jb) - 1u) & ~((1u << ja) - 1u);
+                        int mx = 0;
+                        if (m == 0xFFFFu) {  // all 16 slots of this thread are inside the window (the common case)
+#pragma unroll
+                            for (int k = 0; k < COV_ITEMS; k++) mx = d[k] > mx ? d[k] : mx;
+                            if (mx < COV_BINS - 1) {
+#pragma unroll
+                                for (int k = 0; k < COV_ITEMS; k++) smem_inc(h0 + 4u * (uint32_t)d[k]);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < COV_ITEMS; k++)
+                                    if (d[k] < COV_BINS - 1) smem_inc(h0 + 4u * (uint32_t)d[k]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < COV_ITEMS; k++) {
+                                const int v = d[k];
+                                const uint32_t in = m & (1u << k);
+                                mx = (in && v > mx) ? v : mx;
+                                if (in && v < COV_BINS - 1) smem_inc(h0 + 4u * (uint32_t)v);
+                            }
+                        }
+                        if (mx >= COV_BINS - 1) {  // rare; the copy keeps d[] itself in registers
+                            int dd[COV_ITEMS];
+#pragma unroll
+                            for (int k = 0; k < COV_ITEMS; k++) dd[k] = d[k];
+                            ct_deep_positions(a, c, dd, m);
+                        }
+                        mx = __reduce_max_sync(__activemask(), mx);
+                        if (mx > (int)s_maxd) atomicMax(&s_maxd, (unsigned)mx);
+                    }
+                    in_tile += hi - lo;
+                }
+                if (whi >= p1) break;
+                // ---- the window of contig c ends in this sub-tile ----
+                __syncthreads();
+                const int64_t o0g = a.off[c], o1g = a.off[c + 1];
+                const uint64_t N = (uint64_t)(o1g - o0g - 2 * (int64_t)excl);
+                const uint32_t maxd = s_maxd;
+                const uint32_t mtop = maxd < COV_BINS - 1 ? maxd : COV_BINS - 1;
+                if (wlo >= 0) {
+                    if (warp == 0) finish_contig_t(a, c, N, maxd, [&](uint32_t i) { return s_hist[i]; });
+                } else {
+                    const int64_t row = (o0g + excl) / CT_TILE;
+                    uint32_t *r = a.rows + row * COV_BINS;
+                    for (uint32_t i = tid; i <= mtop; i += COV_THREADS) {
+                        const uint32_t v = s_hist[i];
+                        if (v) atomicAdd(&r[i], v);
+                    }
+                    __threadfence();
+                    __syncthreads();
+                    if (tid == 0) {
+                        atomicMax(&a.meta[row].maxd, maxd);
+                        __threadfence();
+                        const unsigned long long old = atomicAdd(&a.meta[row].done, (unsigned long long)in_tile);
+                        s_last = (old + (unsigned long long)in_tile == N);
+                    }
+                    __syncthreads();
+                    if (s_last) {
+                        __threadfence();
+                        const uint32_t gm = *((volatile unsigned int *)&a.meta[row].maxd);
+                        if (warp == 0) finish_contig_t(a, c, N, gm, [&](uint32_t i) { return __ldcg(r + i); });
+                    }
+                }
+                __syncthreads();
+                for (uint32_t i = tid; i <= mtop; i += COV_THREADS) s_hist[i] = 0;
+                if (tid == 0) s_maxd = 0;
+                __syncthreads();
+                c++;
+                have = false;
+            }
+            __syncthreads();
+        }
+        if (have && whi >= wlo && in_tile > 0) {
+            __syncthreads();
+            const int64_t o0g = a.off[c], o1g = a.off[c + 1];
+            const uint64_t N = (uint64_t)(o1g - o0g - 2 * (int64_t)excl);
+            const uint32_t maxd = s_maxd;
+                const uint32_t mtop = maxd < COV_BINS - 1 ? maxd : COV_BINS - 1;
+            const int64_t row = (o0g + excl) / CT_TILE;
+            uint32_t *r = a.rows + row * COV_BINS;
+            for (uint32_t i = tid; i <= mtop; i += COV_THREADS) {
+                const uint32_t v = s_hist[i];
+                if (v) atomicAdd(&r[i], v);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                atomicMax(&a.meta[row].maxd, maxd);
+                __threadfence();
+                const unsigned long long old = atomicAdd(&a.meta[row].done, (unsigned long long)in_tile);
+                s_last = (old + (unsigned long long)in_tile == N);
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                const uint32_t gm = *((volatile unsigned int *)&a.meta[row].maxd);
+                if (warp == 0) finish_contig_t(a, c, N, gm, [&](uint32_t i) { return __ldcg(r + i); });
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i <= mtop; i += COV_THREADS) s_hist[i] = 0;
+            if (tid == 0) s_maxd = 0;
+            __syncthreads();
+        }
+        __syncthreads();  // s_T / s_tile are rewritten by the next tile
+    }
+}
+
 }  // namespace mp2
 
 using namespace mp2;
 
+// MP2_COV_PATH=general forces the difference array through HBM (development / A-B switch).
+static bool cov_force_general() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MP2_COV_PATH");
+        v = (e && e[0] == 'g') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, const void *d_ev_off,
                                      const void *d_contig_off, int64_t n_contigs, int64_t n_events,
-                                     int64_t n_positions, uint32_t end_excl, float trim_lower,
-                                     float trim_upper, void *d_cov, int64_t cov_stride, void *d_stats,
-                                     void *stream_) {
+                                     int64_t n_positions, uint32_t max_span, uint32_t end_excl,
+                                     float trim_lower, float trim_upper, void *d_cov, int64_t cov_stride,
+                                     void *d_stats, void *stream_) {
     if (n_contigs < 0 || n_events < 0 || n_positions < 0) return fail(MP2_EINVAL, "negative size");
     if (n_contigs > INT32_MAX) return fail(MP2_EINVAL, "too many contigs in one call");
     if (!d_contig_off || !d_ev_off || !d_cov || (n_events > 0 && (!d_starts || !d_ends)))
@@ -535,35 +1015,123 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     if (n_contigs == 0) return MP2_OK;
 
     const int64_t n_pos = n_positions + 1;
-    const int64_t n_tiles = (n_pos + COV_TILE - 1) / COV_TILE;
     const int64_t n_ev_tiles = (n_events + COV_EV_TILE - 1) / COV_EV_TILE;
-    if (n_tiles > INT32_MAX / 2) return fail(MP2_EINVAL, "too many positions in one call");
-
-    Temp D, tile_sum, tile_pre, first, ev_first, rows, meta, deep_list, ctrs;
-    MP2_TRY(D.alloc(sizeof(int32_t) * (size_t)n_pos, stream));
-    MP2_TRY(tile_sum.alloc(sizeof(int32_t) * n_tiles, stream));
-    MP2_TRY(tile_pre.alloc(sizeof(int32_t) * n_tiles, stream));
-    MP2_TRY(first.alloc(sizeof(int32_t) * n_tiles, stream));
-    MP2_TRY(ev_first.alloc(sizeof(int32_t) * (n_ev_tiles + 1), stream));
-    MP2_TRY(rows.alloc(sizeof(uint32_t) * COV_BINS * (size_t)n_tiles, stream));
-    MP2_TRY(meta.alloc(sizeof(RowMeta) * n_tiles, stream));
-    MP2_TRY(deep_list.alloc(sizeof(int32_t) * n_contigs, stream));
-    MP2_TRY(ctrs.alloc(sizeof(int) * 4, stream));
-    MP2_CUDA(cudaMemsetAsync(D.p, 0, sizeof(int32_t) * (size_t)n_pos, stream));
-    MP2_CUDA(cudaMemsetAsync(tile_sum.p, 0, sizeof(int32_t) * n_tiles, stream));
-    MP2_CUDA(cudaMemsetAsync(rows.p, 0, sizeof(uint32_t) * COV_BINS * (size_t)n_tiles, stream));
-    MP2_CUDA(cudaMemsetAsync(meta.p, 0, sizeof(RowMeta) * n_tiles, stream));
-    MP2_CUDA(cudaMemsetAsync(ctrs.p, 0, sizeof(int) * 4, stream));
-
     const int64_t *off = (const int64_t *)d_contig_off;
+    const int64_t *ev_off = (const int64_t *)d_ev_off;
+    const uint32_t *starts = (const uint32_t *)d_starts, *ends = (const uint32_t *)d_ends;
     TrimParams tp;
     tp.lo = trim_lower;
     tp.hi = 1.0f - trim_upper;  // src/coverage.rs:99
     tp.excl = end_excl;
+
+    // ctrs: [0] deep count (tile path) [1] tile work counter [2] gate [3] deep count (general) [4] general
+    // work counter [5] deep next; flags: [0] starts not sorted [1] measured max span
+    Temp ctrs, flags, ev_first;
+    MP2_TRY(ctrs.alloc(sizeof(int) * 8, stream));
+    MP2_TRY(flags.alloc(sizeof(unsigned int) * 2, stream));
+    MP2_TRY(ev_first.alloc(sizeof(int32_t) * (n_ev_tiles + 1), stream));
+    MP2_CUDA(cudaMemsetAsync(ctrs.p, 0, sizeof(int) * 8, stream));
+    MP2_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(unsigned int) * 2, stream));
+    int *gate = ctrs.as<int>() + 2;
     {
         Launch L("cov_init_kernel", stream);
         cov_init_kernel<<<(unsigned)((n_contigs + 255) / 256), 256, 0, stream>>>(
-            off, n_contigs, end_excl, (float *)d_cov, cov_stride, (mp2_cov_stats *)d_stats);
+            off, n_contigs, end_excl, (float *)d_cov, cov_stride, (mp2_cov_stats *)d_stats, gate);
+    }
+    MP2_CUDA(cudaGetLastError());
+    if (n_events > 0) {
+        Launch L("cov_map_kernel", stream);
+        cov_map_kernel<<<(unsigned)((n_ev_tiles + 255) / 256), 256, 0, stream>>>(ev_off, n_contigs, COV_EV_TILE,
+                                                                               n_ev_tiles, ev_first.as<int32_t>());
+    }
+    MP2_CUDA(cudaGetLastError());
+
+    const bool general_only = cov_force_general();
+    // ---------------- fast path: difference array in shared memory ----------------
+    Temp t_first, e_lo, e_hi, c_lo, c_hi, t_rows, t_meta, t_deep, t_drow, t_dpool;
+    if (!general_only) {
+        const int64_t n_tiles = (n_pos + CT_TILE - 1) / CT_TILE;
+        if (n_tiles > INT32_MAX / 2) return fail(MP2_EINVAL, "too many positions in one call");
+        MP2_TRY(t_first.alloc(sizeof(int32_t) * n_tiles, stream));
+        MP2_TRY(e_lo.alloc(sizeof(int64_t) * n_tiles, stream));
+        MP2_TRY(e_hi.alloc(sizeof(int64_t) * n_tiles, stream));
+        MP2_TRY(c_lo.alloc(sizeof(int32_t) * n_tiles, stream));
+        MP2_TRY(c_hi.alloc(sizeof(int32_t) * n_tiles, stream));
+        MP2_TRY(t_rows.alloc(sizeof(uint32_t) * COV_BINS * (size_t)n_tiles, stream));
+        MP2_TRY(t_meta.alloc(sizeof(RowMeta) * n_tiles, stream));
+        MP2_TRY(t_deep.alloc(sizeof(int32_t) * n_contigs, stream));
+        MP2_CUDA(cudaMemsetAsync(t_rows.p, 0, sizeof(uint32_t) * COV_BINS * (size_t)n_tiles, stream));
+        MP2_CUDA(cudaMemsetAsync(t_meta.p, 0, sizeof(RowMeta) * n_tiles, stream));
+        MP2_TRY(t_drow.alloc(sizeof(int32_t) * n_contigs, stream));
+        MP2_TRY(t_dpool.alloc(sizeof(uint32_t) * (size_t)CT_DEEP_ROWS * CT_DEEP_BINS, stream));
+        MP2_CUDA(cudaMemsetAsync(t_drow.p, 0xFF, sizeof(int32_t) * n_contigs, stream));
+        MP2_CUDA(cudaMemsetAsync(t_dpool.p, 0, sizeof(uint32_t) * (size_t)CT_DEEP_ROWS * CT_DEEP_BINS, stream));
+        if (n_events > 0 && max_span == 0) {
+            Launch L("cov_check_kernel", stream);
+            cov_check_kernel<<<(unsigned)n_ev_tiles, 256, 0, stream>>>(starts, ends, ev_off, n_contigs, n_events,
+                                                                     ev_first.as<int32_t>(), flags.as<unsigned int>());
+        }
+        MP2_CUDA(cudaGetLastError());
+        {
+            Launch L("cov_map_kernel", stream);
+            cov_map_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(off, n_contigs, CT_TILE, n_tiles,
+                                                                                t_first.as<int32_t>());
+        }
+        MP2_CUDA(cudaGetLastError());
+        {
+            Launch L("cov_bounds_kernel", stream);
+            cov_bounds_kernel<<<(unsigned)((n_tiles + 127) / 128), 128, 0, stream>>>(
+                starts, ev_off, off, n_contigs, n_tiles, max_span,
+                max_span == 0 ? flags.as<unsigned int>() + 1 : nullptr, e_lo.as<int64_t>(), e_hi.as<int64_t>(),
+                c_lo.as<int32_t>(), c_hi.as<int32_t>());
+        }
+        MP2_CUDA(cudaGetLastError());
+        TileArgs t;
+        t.starts = starts; t.ends = ends; t.ev_off = ev_off; t.off = off;
+        t.n = n_contigs; t.n_pos = n_pos; t.n_tiles = n_tiles;
+        t.e_lo = e_lo.as<int64_t>(); t.e_hi = e_hi.as<int64_t>();
+        t.c_lo = c_lo.as<int32_t>(); t.c_hi = c_hi.as<int32_t>();
+        t.rows = t_rows.as<uint32_t>(); t.meta = t_meta.as<RowMeta>();
+        t.deep_list = t_deep.as<int32_t>(); t.deep_count = ctrs.as<int>() + 0;
+        t.work_counter = ctrs.as<int>() + 1;
+        t.deep_row_of = t_drow.as<int32_t>(); t.deep_pool = t_dpool.as<uint32_t>(); t.deep_rows_used = ctrs.as<int>() + 6;
+        t.check = max_span == 0 ? flags.as<unsigned int>() : nullptr;
+        t.gate_out = gate;
+        t.cov = (float *)d_cov; t.cov_stride = cov_stride; t.stats = (mp2_cov_stats *)d_stats; t.tp = tp;
+        static bool attr_done = false;
+        if (!attr_done) {
+            MP2_CUDA(cudaFuncSetAttribute(cov_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
+            attr_done = true;
+        }
+        int occ = 0;
+        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_tile_kernel, COV_THREADS, CT_SMEM));
+        if (occ < 1) occ = 1;
+        int64_t grid = (int64_t)num_sms() * occ;
+        if (grid > n_tiles) grid = n_tiles;
+        {
+            Launch L("cov_tile_kernel", stream);
+            cov_tile_kernel<<<(unsigned)grid, COV_THREADS, CT_SMEM, stream>>>(t);
+        }
+        MP2_CUDA(cudaGetLastError());
+    }
+
+    // ---------------- general path: difference array in HBM (gated fallback, or forced) ----------------
+    const int64_t n_tiles = (n_pos + COV_TILE - 1) / COV_TILE;
+    const int *g = general_only ? nullptr : gate;
+    Temp D, tile_sum, tile_pre, first, rows, meta, deep_list;
+    MP2_TRY(D.alloc(sizeof(int32_t) * (size_t)(n_pos + 4), stream));
+    MP2_TRY(tile_sum.alloc(sizeof(int32_t) * n_tiles, stream));
+    MP2_TRY(tile_pre.alloc(sizeof(int32_t) * n_tiles, stream));
+    MP2_TRY(first.alloc(sizeof(int32_t) * n_tiles, stream));
+    MP2_TRY(rows.alloc(sizeof(uint32_t) * COV_BINS * (size_t)n_tiles, stream));
+    MP2_TRY(meta.alloc(sizeof(RowMeta) * n_tiles, stream));
+    MP2_TRY(deep_list.alloc(sizeof(int32_t) * n_contigs, stream));
+    MP2_CUDA(cudaMemsetAsync(tile_sum.p, 0, sizeof(int32_t) * n_tiles, stream));
+    MP2_CUDA(cudaMemsetAsync(rows.p, 0, sizeof(uint32_t) * COV_BINS * (size_t)n_tiles, stream));
+    MP2_CUDA(cudaMemsetAsync(meta.p, 0, sizeof(RowMeta) * n_tiles, stream));
+    {
+        Launch L("cov_zero_kernel", stream);
+        cov_zero_kernel<<<(unsigned)(num_sms() * 8), 256, 0, stream>>>(D.as<int4>(), (n_pos + 3) / 4, g);
     }
     MP2_CUDA(cudaGetLastError());
     {
@@ -573,23 +1141,15 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     }
     MP2_CUDA(cudaGetLastError());
     if (n_events > 0) {
-        {
-            Launch L("cov_map_kernel", stream);
-            cov_map_kernel<<<(unsigned)((n_ev_tiles + 255) / 256), 256, 0, stream>>>(
-                (const int64_t *)d_ev_off, n_contigs, COV_EV_TILE, n_ev_tiles, ev_first.as<int32_t>());
-        }
-        MP2_CUDA(cudaGetLastError());
-        {
-            Launch L("cov_scatter_kernel", stream);
-            cov_scatter_kernel<<<(unsigned)n_ev_tiles, 256, 0, stream>>>(
-                (const uint32_t *)d_starts, (const uint32_t *)d_ends, (const int64_t *)d_ev_off, off, n_contigs,
-                n_events, ev_first.as<int32_t>(), D.as<int32_t>(), tile_sum.as<int32_t>());
-        }
-        MP2_CUDA(cudaGetLastError());
+        Launch L("cov_scatter_kernel", stream);
+        cov_scatter_kernel<<<(unsigned)n_ev_tiles, 256, 0, stream>>>(starts, ends, ev_off, off, n_contigs, n_events,
+                                                                   ev_first.as<int32_t>(), D.as<int32_t>(),
+                                                                   tile_sum.as<int32_t>(), g);
     }
+    MP2_CUDA(cudaGetLastError());
     {
         Launch L("cov_tile_scan_kernel", stream);
-        cov_tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_sum.as<int32_t>(), n_tiles, tile_pre.as<int32_t>());
+        cov_tile_scan_kernel<<<1, 1024, 0, stream>>>(tile_sum.as<int32_t>(), n_tiles, tile_pre.as<int32_t>(), g);
     }
     MP2_CUDA(cudaGetLastError());
     DepthArgs a;
@@ -603,8 +1163,9 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     a.rows = rows.as<uint32_t>();
     a.meta = meta.as<RowMeta>();
     a.deep_list = deep_list.as<int32_t>();
-    a.deep_count = ctrs.as<int>() + 0;
-    a.work_counter = ctrs.as<int>() + 1;
+    a.deep_count = ctrs.as<int>() + 3;
+    a.work_counter = ctrs.as<int>() + 4;
+    a.gate = g;
     a.cov = (float *)d_cov;
     a.cov_stride = cov_stride;
     a.stats = (mp2_cov_stats *)d_stats;
@@ -621,7 +1182,7 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     MP2_CUDA(cudaGetLastError());
     {
         Launch L("cov_deep_kernel", stream);
-        cov_deep_kernel<<<(unsigned)(num_sms() * 2), COV_THREADS, 0, stream>>>(a, ctrs.as<int>() + 2);
+        cov_deep_kernel<<<(unsigned)(num_sms() * 2), COV_THREADS, 0, stream>>>(a, ctrs.as<int>() + 5);
     }
     MP2_CUDA(cudaGetLastError());
     return MP2_OK;

@@ -161,7 +161,7 @@ def test_device_entry_strided_columns(covmod, oracle):
         d_en = torch.from_numpy(en.view(np.int32)).cuda()
         d_eo = torch.from_numpy(ev_off).cuda()
         _lib.check(lib.mp2_cov_events_device(d_st.data_ptr(), d_en.data_ptr(), d_eo.data_ptr(), d_off.data_ptr(),
-                                             n, len(st), int(off[-1]), 75, 0.05, 0.05,
+                                             n, len(st), int(off[-1]), 150, 75, 0.05, 0.05,
                                              mat.data_ptr() + 4 * s, S, None,
                                              torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
@@ -171,3 +171,34 @@ def test_device_entry_strided_columns(covmod, oracle):
 def test_rejects_bad_trim(covmod):
     with pytest.raises(ValueError):
         covmod.cov_from_events([], [], [0, 0], [0, 1000], 75, 0.6, 0.5)
+
+
+def test_unsorted_events_take_the_general_path(covmod, oracle):
+    """Blocks in arbitrary order inside a contig (allowed by the ABI): the device check notices and
+    the difference array goes through HBM instead of shared memory; same integers either way."""
+    from magpurify2_b200 import synth
+
+    lengths, mag_off, _gc = synth.mag_layout(3, seed=6, mean_bp=6e5, n_contigs=70)
+    st, en, ev_off = synth.make_events(lengths, mag_off, 0, seed=6, variable=True)
+    rng = np.random.default_rng(6)
+    st2, en2 = st.copy(), en.copy()
+    for c in range(len(lengths)):
+        p = rng.permutation(ev_off[c + 1] - ev_off[c]) + ev_off[c]
+        st2[ev_off[c]:ev_off[c + 1]] = st[p]
+        en2[ev_off[c]:ev_off[c + 1]] = en[p]
+    a, sa = check_sample(covmod, oracle, st, en, ev_off, lengths, 75, 0.05, 0.05)
+    b, sb = check_sample(covmod, oracle, st2, en2, ev_off, lengths, 75, 0.05, 0.05)
+    assert np.array_equal(a, b) and np.array_equal(sa["total"], sb["total"])
+
+
+def test_vouched_max_span_matches_checked(covmod):
+    from magpurify2_b200 import synth
+
+    lengths, mag_off, _gc = synth.mag_layout(4, seed=8, mean_bp=8e5, n_contigs=50)
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    st, en, ev_off = synth.make_events(lengths, mag_off, 1, seed=8, variable=True)
+    span = int((en - st).max())
+    a = covmod.cov_from_events(st, en, ev_off, off, 75, 0.05, 0.05, max_span=0)
+    b = covmod.cov_from_events(st, en, ev_off, off, 75, 0.05, 0.05, max_span=span)
+    c = covmod.cov_from_events(st, en, ev_off, off, 75, 0.05, 0.05, max_span=span + 5000)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
