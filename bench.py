@@ -117,12 +117,23 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
         samples.append((st, en, eo, R))
         R_total += R
     cov = torch.empty((n, S), dtype=torch.float32, device=dev)
+    n_mags = len(mag_off) - 1
+    d_len = torch.from_numpy(lengths.astype(np.int64)).to(dev)
+    d_mag_off = torch.from_numpy(mag_off.astype(np.int64)).to(dev)
+    d_sel = torch.empty((n_mags, S), dtype=torch.uint8, device=dev)
+    d_score = torch.empty(n, dtype=torch.float64, device=dev)
 
     def step():
         for s, (st, en, eo, R) in enumerate(samples):
             _lib.check(lib.mp2_cov_events_device(st.data_ptr(), en.data_ptr(), eo.data_ptr(), d_off.data_ptr(),
                                                  n, R, L, args.max_span, 75, args.trim, args.trim,
                                                  cov.data_ptr() + 4 * s, S, None, stream))
+        # core.Coverage: samples with length-weighted mean coverage >= 1, then base-25 log-ratio score
+        _lib.check(lib.mp2_select_samples_device(cov.data_ptr(), d_len.data_ptr(), d_mag_off.data_ptr(), n_mags, n, S,
+                                                 1.0, d_sel.data_ptr(), None, stream))
+        _lib.check(lib.mp2_logratio_device(cov.data_ptr(), d_len.data_ptr(), d_mag_off.data_ptr(), n_mags, n, S,
+                                           d_sel.data_ptr(), 25.0, 1e-5, 0.0, 1.0, 3, 0, d_score.data_ptr(), None,
+                                           stream))
 
     for _ in range(args.warmup):
         step()
@@ -215,6 +226,13 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
         c_cov, _ = oracle.cov_sample(a_st[:e1_], a_en[:e1_], h_eo[:c1 + 1], lengths[:c1], 75, args.trim, args.trim, threads=1)
         dt = time.perf_counter() - t0
         ok = bool(np.array_equal(c_cov, h_cov[:c1], equal_nan=True))
+        # scores of the first MAG against the oracle (all samples)
+        m0 = slice(0, int(mag_off[1]))
+        cov0 = cov[m0].cpu().numpy()
+        sel0, _ = oracle.select_samples(cov0, lengths[m0], 1.0)
+        if sel0.any() and cov0.shape[0] > 2:
+            want0, _ = oracle.log_ratio_scores(cov0[:, sel0], lengths[m0], 25)
+            ok = ok and bool(np.allclose(d_score[m0].cpu().numpy(), want0, atol=1e-6))
         rec["cpu_baseline"] = {"value": e1_ / dt, "unit": "reads/s", "cores": 1, "kind": "port",
                                "sample": f"sample 0, first {m} MAGs ({e1_ / 1e6:.1f} M blocks, {int(offsets[c1]) / 1e6:.0f} Mbp); "
                                          "single thread per sample as coverm's record loop is (events already decoded)",
@@ -245,6 +263,27 @@ def run_reference(args):
     t = float(np.sum(times))
     val = L * len(times) / t / 1e9
     sample = f"{n_mags} of {args.mags} MAGs per step ({L / 1e6:.1f} Mbp): get_tnf with {threads} threads over contigs + serial 5-pass get_gc"
+    # coverage leg of the reference arm: coverm's record loop is single-threaded per BAM and the BAMs
+    # are processed one after the other; events are already decoded here
+    cov_rec = None
+    if args.samples > 0:
+        m = max(1, n_mags // 5)
+        c1 = int(d["mag_off"][m])
+        st, en, eo = synth.make_events(d["lengths"][:c1], d["mag_off"][:m + 1], 0, seed=args.seed,
+                                       depth_scale=args.depth_scale)
+        ctimes = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            oracle.cov_sample(st, en, eo, d["lengths"][:c1], 75, args.trim, args.trim, threads=1)
+            if it >= args.warmup:
+                ctimes.append(time.perf_counter() - t0)
+        cval = len(st) * len(ctimes) / float(np.sum(ctimes))
+        cs = (f"1 sample x first {m} MAGs per step ({len(st) / 1e6:.1f} M aligned blocks, "
+              f"{int(d['offsets'][c1]) / 1e6:.0f} Mbp), single thread as coverm's record loop")
+        cov_rec = {"metric": "aligned reads/s coverage", "value": cval, "unit": "reads/s",
+                   "ms_per_step": float(np.mean(ctimes)) * 1e3,
+                   "cpu_baseline": {"value": cval, "unit": "reads/s", "cores": 1, "kind": "port", "sample": cs},
+                   "e2e": {"value": cval, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / len(times) * 1e3,
@@ -256,6 +295,8 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if cov_rec:
+        line["coverage"] = cov_rec
     print(json.dumps(line), flush=True)
     return 0
 
@@ -305,14 +346,34 @@ def main():
     d_counts = torch.empty((n, 136), dtype=torch.int32, device=dev)
     d_rel = torch.empty((n, 136), dtype=torch.float32, device=dev)
     d_gc = torch.empty(n, dtype=torch.float32, device=dev)
+    d_len = torch.from_numpy(d["lengths"].astype(np.int64)).to(dev)
+    d_mag_off = torch.from_numpy(mag_off.astype(np.int64)).to(dev)
+    n_mags = len(mag_off) - 1
+    d_dist = torch.empty(n, dtype=torch.float64, device=dev)
+    d_scores = torch.empty((2, n), dtype=torch.float64, device=dev)  # tnf_score, gc_content_score
     stream = torch.cuda.current_stream().cuda_stream
+    if world > 1:
+        nmax = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
+        n_pad = int(nmax.item())
+        g_in = torch.zeros((2, n_pad), dtype=torch.float64, device=dev)
+        g_out = torch.empty((world, 2, n_pad), dtype=torch.float64, device=dev)
 
     def step():
+        # counts + relative TNF + GC of every contig
         _lib.check(lib.mp2_tnf_device(bases.data_ptr(), d_off.data_ptr(), n, L, d_counts.data_ptr(),
                                       d_rel.data_ptr(), d_gc.data_ptr(), stream))
-        if world > 1:  # final gather of the per-contig results that leave the device (GC here)
-            out = [torch.empty_like(d_gc) for _ in range(world)] if False else None
-            del out
+        # per-MAG scores: CLR/centroid distance -> tnf_score, GC log-ratio -> gc_content_score
+        _lib.check(lib.mp2_clr_centroid_device(d_counts.data_ptr(), d_len.data_ptr(), d_mag_off.data_ptr(), n_mags, n,
+                                               None, d_dist.data_ptr(), stream))
+        d32 = d_dist.to(torch.float32)
+        _lib.check(lib.mp2_logratio_device(d32.data_ptr(), d_len.data_ptr(), d_mag_off.data_ptr(), n_mags, n, 1, None,
+                                           4.0, 1e-5, 0.0, 1.0, 3, 1, d_scores[0].data_ptr(), None, stream))
+        _lib.check(lib.mp2_logratio_device(d_gc.data_ptr(), d_len.data_ptr(), d_mag_off.data_ptr(), n_mags, n, 1, None,
+                                           2.0, 1e-5, 0.0, 1.0, 3, 0, d_scores[1].data_ptr(), None, stream))
+        if world > 1:  # the only exchange: final gather of the per-contig scores (NCCL over NVLink)
+            g_in[:, :n] = d_scores
+            dist.all_gather_into_tensor(g_out, g_in)
 
     def barrier():
         torch.cuda.synchronize()
@@ -343,6 +404,12 @@ def main():
 
     k_ms, k_n = C.c_double(0), C.c_int64(0)
     lib.mp2_profile_read(b"tnf_kernel", C.byref(k_ms), C.byref(k_n))
+    comp_kernels = {}
+    for name in ("tnf_kernel", "tnf_chunk_map_kernel", "tnf_rel_kernel", "tnf_gc_kernel", "clr_rowmean_kernel",
+                 "clr_centroid_kernel", "clr_dist_kernel", "wmedian_kernel", "logratio_kernel"):
+        a_ms, a_n = C.c_double(0), C.c_int64(0)
+        lib.mp2_profile_read(name.encode(), C.byref(a_ms), C.byref(a_n))
+        comp_kernels[name] = round(a_ms.value / args.steps, 4)
     lib.mp2_profile_enable(0)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -403,6 +470,8 @@ def main():
             "mags_per_gpu": args.mags, "contigs_per_gpu": n, "bases_per_gpu": L,
             "input": "ASCII, 1 B/base, resident in HBM", "l2": "inputs (GBs) far larger than the 126 MB L2",
             "parallelism": f"mag-shard x{world}",
+            "step": "mp2_tnf_device (counts, relative TNF, GC) + CLR/centroid + 2x weighted-median log-ratio scores"
+                    + (" + all_gather of the scores" if world > 1 else ""),
         },
         "roofline": {"bound": "hbm", "kernel": "tnf_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -410,6 +479,7 @@ def main():
                      "launches_timed": k_n.value, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "magpurify2_b200._composition.tnf_from_concat (mp2_tnf, pinned host buffers)"},
+        "kernel_ms_per_step": comp_kernels,
         "gpu_launches": int(launches) + (cov_rec["gpu_launches"] if cov_rec else 0),
         "clocks": clocks,
     }

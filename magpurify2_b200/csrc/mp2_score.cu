@@ -210,6 +210,31 @@ __global__ void select_samples_kernel(const float *__restrict__ cov, const long 
     sel[t] = mean >= min_avg ? 1 : 0;
 }
 
+// ln(c + 1) for small counts comes from a table (typical contigs hold tens of k-mers per class; the
+// FP64 log was 70 % of the scoring time), larger counts are computed.
+constexpr int LOG_LUT = 8192;
+__device__ double g_log_lut[LOG_LUT];
+
+__device__ __forceinline__ double ln1p_count(uint32_t c) {
+    return c < LOG_LUT - 1 ? __ldg(&g_log_lut[c + 1]) : log((double)c + 1.0);
+}
+
+__global__ void log_lut_kernel() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < LOG_LUT) g_log_lut[i] = i ? log((double)i) : 0.0;
+}
+
+static int ensure_log_lut(cudaStream_t stream) {
+    static bool done[64] = {false};
+    int dev = 0;
+    MP2_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && done[dev]) return MP2_OK;
+    log_lut_kernel<<<LOG_LUT / 256, 256, 0, stream>>>();
+    MP2_CUDA(cudaGetLastError());
+    if (dev < 64) done[dev] = true;
+    return MP2_OK;
+}
+
 // ---- CLR + centroid distance (self-specified: the reference has no such code) -----------------
 // clr_ij = ln(c_ij + 1) - mean_j ln(c_ij + 1); centroid_j = sum_i len_i clr_ij / sum_i len_i;
 // d_i = ||clr_i - centroid||_2.  f64 throughout.
@@ -218,7 +243,7 @@ __global__ void clr_rowmean_kernel(const uint32_t *__restrict__ counts, int64_t 
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (r >= n_rows) return;
     double s = 0.0;
-    for (int j = lane; j < MP2_NCANON; j += 32) s += log((double)counts[r * MP2_NCANON + j] + 1.0);
+    for (int j = lane; j < MP2_NCANON; j += 32) s += ln1p_count(counts[r * MP2_NCANON + j]);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) rowmean[r] = s / (double)MP2_NCANON;
 }
@@ -233,7 +258,7 @@ clr_centroid_kernel(const uint32_t *__restrict__ counts, const long long *__rest
     double acc = 0.0, wsum = 0.0;
     for (int64_t r = mag_off[m]; r < mag_off[m + 1]; r++) {
         const double w = (double)weights[r];
-        acc += w * (log((double)counts[r * MP2_NCANON + j] + 1.0) - rowmean[r]);
+        acc += w * (ln1p_count(counts[r * MP2_NCANON + j]) - rowmean[r]);
         wsum += w;
     }
     centroid[m * MP2_NCANON + j] = wsum > 0.0 ? acc / wsum : 0.0;
@@ -255,7 +280,7 @@ __global__ void clr_dist_kernel(const uint32_t *__restrict__ counts, const long 
     const int64_t m = lo - 1;
     double d2 = 0.0;
     for (int j = lane; j < MP2_NCANON; j += 32) {
-        const double v = log((double)counts[r * MP2_NCANON + j] + 1.0) - rowmean[r];
+        const double v = ln1p_count(counts[r * MP2_NCANON + j]) - rowmean[r];
         if (clr) clr[r * MP2_NCANON + j] = (float)v;
         const double d = v - centroid[m * MP2_NCANON + j];
         d2 += d * d;
@@ -340,6 +365,7 @@ extern "C" int mp2_clr_centroid_device(const void *d_counts, const void *d_weigh
     MP2_TRY(require_device(-1));
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_rows == 0 || n_mags == 0) return MP2_OK;
+    MP2_TRY(ensure_log_lut(stream));
     Temp rowmean, centroid;
     MP2_TRY(rowmean.alloc(sizeof(double) * n_rows, stream));
     MP2_TRY(centroid.alloc(sizeof(double) * MP2_NCANON * n_mags, stream));
