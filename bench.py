@@ -297,11 +297,25 @@ def run_reference(args):
     }
     if cov_rec:
         line["coverage"] = cov_rec
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter
+    written to fd 1) was redirected to stderr at start-up."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -433,11 +447,13 @@ def main():
     torch.cuda.synchronize()
     hb = h_bases.numpy()
     e2e_steps = max(1, min(args.steps, 3))
-    _composition.tnf_from_concat(hb, offsets, relative=True, want_gc=True, device=local)  # warm-up
+    o_rel, o_gc = _composition.pinned_empty((n, 136), np.float32), np.empty(n, dtype=np.float32)
+    _composition.tnf_from_concat(hb, offsets, relative=True, device=local, out_rel=o_rel, out_gc=o_gc)  # warm-up
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        _c, h_rel, h_gc = _composition.tnf_from_concat(hb, offsets, relative=True, want_gc=True, device=local)
+        _c, h_rel, h_gc = _composition.tnf_from_concat(hb, offsets, relative=True, device=local, out_rel=o_rel,
+                                                       out_gc=o_gc)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -478,7 +494,7 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_avg_ms,
                      "launches_timed": k_n.value, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "magpurify2_b200._composition.tnf_from_concat (mp2_tnf, pinned host buffers)"},
+                "steps": e2e_steps, "api": "magpurify2_b200._composition.tnf_from_concat(out_rel=, out_gc=) -> mp2_tnf, pinned host buffers in and out"},
         "kernel_ms_per_step": comp_kernels,
         "gpu_launches": int(launches) + (cov_rec["gpu_launches"] if cov_rec else 0),
         "clocks": clocks,
@@ -501,9 +517,9 @@ def main():
                                           f"get_tnf {threads} threads over contigs + serial 5-pass get_gc",
                                 "parity_with_gpu": ok}
         if not ok:
-            print(json.dumps(line), flush=True)
+            emit(line)
             raise SystemExit("PARITY FAILURE: GPU counts/GC differ from the CPU oracle")
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

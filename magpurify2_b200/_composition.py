@@ -36,15 +36,51 @@ def _concat(seq_list):
     return bases, offsets
 
 
-def tnf_from_concat(bases, offsets, relative=True, want_gc=False, want_counts=False, device=-1):
-    """Batch entry point on one concatenated byte stream (what the scalable drivers call)."""
+def _out(shape, dtype):
+    """Result buffer: page-locked when it is large (the D2H copy of a pageable 160 MB array costs
+    more than the kernels), plain NumPy otherwise.  torch is used as the pinned allocator only."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if nbytes >= (8 << 20):
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.uint32): torch.int32}[np.dtype(dtype)]
+                return torch.empty(shape, dtype=tdt, pin_memory=True).numpy().view(dtype)
+        except Exception:
+            pass
+    return np.empty(shape, dtype=dtype)
+
+
+def pinned_empty(shape, dtype):
+    """Page-locked result buffer to pass as out_* (reuse it across calls of a streaming driver)."""
+    return _out(shape, dtype)
+
+
+def _check_out(a, shape, dtype, name):
+    if not (isinstance(a, np.ndarray) and a.shape == tuple(shape) and a.dtype == np.dtype(dtype) and a.flags.c_contiguous):
+        raise ValueError(f"{name} must be a C-contiguous {np.dtype(dtype).name} array of shape {tuple(shape)}")
+    return a
+
+
+def tnf_from_concat(bases, offsets, relative=True, want_gc=False, want_counts=False, device=-1,
+                    out_counts=None, out_rel=None, out_gc=None):
+    """Batch entry point on one concatenated byte stream (what the scalable drivers call).
+    out_*: optional preallocated result arrays (NumPy `out=` style; page-locked ones from
+    pinned_empty() avoid the staging copy of the device->host transfer)."""
     bases = np.ascontiguousarray(bases, dtype=np.uint8)
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     n = len(offsets) - 1
     lib = _lib.load()
-    counts = np.empty((n, NCANON), dtype=np.uint32) if (want_counts or not relative) else None
-    rel = np.empty((n, NCANON), dtype=np.float32) if relative else None
-    gc = np.empty(n, dtype=np.float32) if want_gc else None
+    counts = rel = gc = None
+    if want_counts or not relative or out_counts is not None:
+        counts = _check_out(out_counts, (n, NCANON), np.uint32, "out_counts") if out_counts is not None \
+            else _out((n, NCANON), np.uint32)
+    if relative or out_rel is not None:
+        rel = _check_out(out_rel, (n, NCANON), np.float32, "out_rel") if out_rel is not None \
+            else _out((n, NCANON), np.float32)
+    if want_gc or out_gc is not None:
+        gc = _check_out(out_gc, (n,), np.float32, "out_gc") if out_gc is not None else np.empty(n, dtype=np.float32)
     _lib.check(lib.mp2_tnf(_lib.ptr(bases), _lib.ptr(offsets), n, device,
                            _lib.ptr(counts), _lib.ptr(rel), _lib.ptr(gc)))
     return counts, rel, gc

@@ -6,6 +6,7 @@
 #include <omp.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -23,7 +24,17 @@ int tnf_finalize(const uint32_t *d_counts, const unsigned long long *d_gc_counts
                  const int64_t *d_offsets, int64_t n, float *d_rel, float *d_gc,
                  cudaStream_t stream);
 
-constexpr size_t SLICE = 16u << 20;
+static size_t slice_bytes() {
+    static size_t v = 0;
+    if (!v) {
+        const char *e = getenv("MP2_SLICE_MB");
+        long mb = e ? atol(e) : 0;
+        v = (size_t)(mb > 0 ? mb : 16) << 20;
+    }
+    return v;
+}
+#define SLICE (slice_bytes())
+constexpr size_t RING_SLICE = 16u << 20;
 constexpr int NRING = 4;
 
 struct Ring {
@@ -37,7 +48,7 @@ static Ring g_ring;
 static int ring_init() {
     if (g_ring.ready) return MP2_OK;
     for (int i = 0; i < NRING; i++) {
-        MP2_CUDA(cudaHostAlloc((void **)&g_ring.buf[i], SLICE, cudaHostAllocPortable));
+        MP2_CUDA(cudaHostAlloc((void **)&g_ring.buf[i], RING_SLICE, cudaHostAllocPortable));
         MP2_CUDA(cudaEventCreateWithFlags(&g_ring.freed[i], cudaEventDisableTiming));
     }
     g_ring.ready = true;
@@ -85,8 +96,8 @@ static int upload(void *d_dst, const void *h_src, size_t bytes, cudaStream_t cop
     std::lock_guard<std::mutex> lk(g_ring.mu);
     MP2_TRY(ring_init());
     int slot = 0;
-    for (size_t o = 0; o < bytes; o += SLICE, slot = (slot + 1) % NRING) {
-        size_t len = std::min(SLICE, bytes - o);
+    for (size_t o = 0; o < bytes; o += RING_SLICE, slot = (slot + 1) % NRING) {
+        size_t len = std::min(RING_SLICE, bytes - o);
         MP2_CUDA(cudaEventSynchronize(g_ring.freed[slot]));  // previous user of the slot is done
         par_memcpy(g_ring.buf[slot], (const char *)h_src + o, len);
         MP2_CUDA(cudaMemcpyAsync((char *)d_dst + o, g_ring.buf[slot], len, cudaMemcpyHostToDevice,
@@ -141,8 +152,14 @@ extern "C" int mp2_tnf(const uint8_t *bases, const int64_t *offsets, int64_t n, 
     MP2_TRY(require_device(device));
     if (n == 0) return MP2_OK;
 
+    const bool trace = getenv("MP2_TRACE") != nullptr;
+    const double t0 = omp_get_wtime();
+    auto stamp = [&](const char *what) {
+        if (trace) fprintf(stderr, "[mp2_tnf] %-28s %8.2f ms\n", what, (omp_get_wtime() - t0) * 1e3);
+    };
     Streams st;
     MP2_TRY(st.init());
+    stamp("streams");
     Temp d_bases, d_off, d_counts, d_gcc, d_rel, d_gc;
     MP2_TRY(d_bases.alloc((size_t)total + 16, st.copy));
     MP2_TRY(d_off.alloc(sizeof(int64_t) * (n + 1), st.copy));
@@ -153,6 +170,7 @@ extern "C" int mp2_tnf(const uint8_t *bases, const int64_t *offsets, int64_t n, 
     MP2_CUDA(cudaMemsetAsync(d_counts.p, 0, sizeof(uint32_t) * MP2_NCANON * n, st.comp));
     MP2_CUDA(cudaMemsetAsync(d_gcc.p, 0, sizeof(unsigned long long) * n, st.comp));
 
+    stamp("alloc + memset enqueued");
     MP2_TRY(upload(d_off.p, offsets, sizeof(int64_t) * (n + 1), st.copy));
     const int64_t n_chunks = tnf_num_chunks(d_bases.p, total);
     int64_t next_chunk = 0;
@@ -170,6 +188,8 @@ extern "C" int mp2_tnf(const uint8_t *bases, const int64_t *offsets, int64_t n, 
         return MP2_OK;
     };
     MP2_TRY(upload(d_bases.p, bases, (size_t)total, st.copy, after));
+    stamp("upload + kernels enqueued");
+    if (trace) { cudaStreamSynchronize(st.copy); stamp("copy stream done"); cudaStreamSynchronize(st.comp); stamp("compute stream done"); }
     MP2_TRY(tnf_finalize(d_counts.as<uint32_t>(), d_gcc.as<unsigned long long>(),
                          d_off.as<int64_t>(), n, d_rel.as<float>(), d_gc.as<float>(), st.comp));
     if (counts) MP2_TRY(download(counts, d_counts.p, sizeof(uint32_t) * MP2_NCANON * n, st.comp));
@@ -177,6 +197,7 @@ extern "C" int mp2_tnf(const uint8_t *bases, const int64_t *offsets, int64_t n, 
     if (gc) MP2_TRY(download(gc, d_gc.p, sizeof(float) * n, st.comp));
     MP2_CUDA(cudaStreamSynchronize(st.comp));
     MP2_CUDA(cudaStreamSynchronize(st.copy));
+    stamp("results on host");
     return MP2_OK;
 }
 
