@@ -248,20 +248,32 @@ __global__ void clr_rowmean_kernel(const uint32_t *__restrict__ counts, int64_t 
     if (lane == 0) rowmean[r] = s / (double)MP2_NCANON;
 }
 
-__global__ void __launch_bounds__(160)
+constexpr int CEN_SLICES = 6;  // row slices per MAG summed in parallel, then combined in slice order
+
+__global__ void __launch_bounds__(160 * CEN_SLICES)
 clr_centroid_kernel(const uint32_t *__restrict__ counts, const long long *__restrict__ weights,
                     const long long *__restrict__ mag_off, const double *__restrict__ rowmean,
                     double *__restrict__ centroid /*[n_mags,136]*/) {
+    __shared__ double s_acc[CEN_SLICES][160];
+    __shared__ double s_w[CEN_SLICES];
     const int64_t m = blockIdx.x;
-    const int j = threadIdx.x;
-    if (j >= MP2_NCANON) return;
+    const int j = threadIdx.x % 160, g = threadIdx.x / 160;
     double acc = 0.0, wsum = 0.0;
-    for (int64_t r = mag_off[m]; r < mag_off[m + 1]; r++) {
-        const double w = (double)weights[r];
-        acc += w * (ln1p_count(counts[r * MP2_NCANON + j]) - rowmean[r]);
-        wsum += w;
+    if (j < MP2_NCANON) {
+        for (int64_t r = mag_off[m] + g; r < mag_off[m + 1]; r += CEN_SLICES) {
+            const double w = (double)weights[r];
+            acc += w * (ln1p_count(counts[r * MP2_NCANON + j]) - rowmean[r]);
+            wsum += w;
+        }
     }
-    centroid[m * MP2_NCANON + j] = wsum > 0.0 ? acc / wsum : 0.0;
+    s_acc[g][j] = acc;
+    if (j == 0) s_w[g] = wsum;
+    __syncthreads();
+    if (g == 0 && j < MP2_NCANON) {
+        double a2 = 0.0, w2 = 0.0;
+        for (int k = 0; k < CEN_SLICES; k++) { a2 += s_acc[k][j]; w2 += s_w[k]; }
+        centroid[m * MP2_NCANON + j] = w2 > 0.0 ? a2 / w2 : 0.0;
+    }
 }
 
 __global__ void clr_dist_kernel(const uint32_t *__restrict__ counts, const long long *__restrict__ mag_off,
@@ -377,7 +389,7 @@ extern "C" int mp2_clr_centroid_device(const void *d_counts, const void *d_weigh
     MP2_CUDA(cudaGetLastError());
     {
         Launch L("clr_centroid_kernel", stream);
-        clr_centroid_kernel<<<(unsigned)n_mags, 160, 0, stream>>>(
+        clr_centroid_kernel<<<(unsigned)n_mags, 160 * CEN_SLICES, 0, stream>>>(
             (const uint32_t *)d_counts, (const long long *)d_weights, (const long long *)d_mag_off,
             rowmean.as<double>(), centroid.as<double>());
     }
