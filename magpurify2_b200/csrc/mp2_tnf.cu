@@ -25,7 +25,14 @@ constexpr int TNF_UNROLL = 4;     // 16-byte groups in flight per lane
 // Table words per warp: MODE 4 counts one 4-mer per base into T4[256]; MODE 5 counts one 5-mer
 // per TWO bases into T5[1024] (a 5-mer b0..b4 stands for the 4-mers b0..b3 and b1..b4) and
 // keeps T4[256] for the odd ones out (segment edges, groups holding non-ACGT bytes).
-template <int MODE> struct TnfTab { static constexpr int WORDS = MODE == 5 ? 1280 : 256; };
+// MODE 7 = MODE 5 with T5 split four ways by lane group (lane>>3): entry idx of group g lives at word
+// idx*4+g, so a group only ever touches the 8 banks congruent to g mod 4 -- 8 lanes into 8 banks
+// instead of 32 into 32 (expected worst bank load 2.5 instead of 3.5) -- and the four copies of an
+// entry are one aligned 16-byte LDS.128 at flush time.
+template <int MODE> struct TnfTab {
+    static constexpr int T5W = MODE == 7 ? 4096 : (MODE == 5 ? 1024 : 0);
+    static constexpr int WORDS = T5W + 256;
+};
 
 __constant__ uint8_t c_lut256[256];             // code -> canonical class
 __constant__ uint16_t c_canon_pair[MP2_NCANON];  // class -> smallest code | revcomp code << 8
@@ -94,6 +101,24 @@ __global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_
 // Fold the warp's table into the contig's row: 256 codes -> 136 canonical classes (MODE 5: first
 // 5-mer counts -> 4-mer counts), integer global reductions, then zero the table.
 template <int MODE>
+__device__ __forceinline__ uint32_t tnf_code_count(const uint32_t *tab, uint32_t a) {
+    constexpr int T5W = TnfTab<MODE>::T5W;
+    uint32_t val = tab[T5W + a];  // T4
+    if (MODE == 5) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(tab + (a << 2));  // 5-mers a.b
+        val += q.x + q.y + q.z + q.w + tab[a] + tab[256 + a] + tab[512 + a] + tab[768 + a];  // and b.a
+    } else if (MODE == 7) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(tab + ((((a << 2) | b)) << 2));
+            const uint4 r = *reinterpret_cast<const uint4 *>(tab + (((b << 8) | a) << 2));
+            val += q.x + q.y + q.z + q.w + r.x + r.y + r.z + r.w;
+        }
+    }
+    return val;
+}
+
+template <int MODE>
 __device__ __forceinline__ void tnf_flush(uint32_t *tab, int lane, uint32_t *__restrict__ row) {
     constexpr int WORDS = TnfTab<MODE>::WORDS;
     __syncwarp();
@@ -102,18 +127,8 @@ __device__ __forceinline__ void tnf_flush(uint32_t *tab, int lane, uint32_t *__r
         if (k < MP2_NCANON) {
             const uint32_t pr = c_canon_pair[k];
             const uint32_t a = pr & 0xFFu, rc = pr >> 8;
-            uint32_t val = tab[(MODE == 5 ? 1024 : 0) + a];
-            if (MODE == 5) {
-                const uint4 q = *reinterpret_cast<const uint4 *>(tab + (a << 2));
-                val += q.x + q.y + q.z + q.w + tab[a] + tab[256 + a] + tab[512 + a] + tab[768 + a];
-            }
-            if (rc != a) {
-                val += tab[(MODE == 5 ? 1024 : 0) + rc];
-                if (MODE == 5) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(tab + (rc << 2));
-                    val += q.x + q.y + q.z + q.w + tab[rc] + tab[256 + rc] + tab[512 + rc] + tab[768 + rc];
-                }
-            }
+            uint32_t val = tnf_code_count<MODE>(tab, a);
+            if (rc != a) val += tnf_code_count<MODE>(tab, rc);
             if (val) atomicAdd(&row[k], val);
         }
     }
@@ -128,7 +143,15 @@ __device__ __forceinline__ void tnf_flush(uint32_t *tab, int lane, uint32_t *__r
 // (MODE 4) increments.  halo = codes of the 3 bases before the group in bits 5:0.
 template <int MODE>
 __device__ __forceinline__ void tnf_count16(uint32_t cw, uint32_t halo, uint32_t t5, uint32_t t4) {
-    if (MODE == 5) {
+    if (MODE == 7) {
+        // as MODE 5, entry idx of this lane's group at byte idx*16 + 4*(lane>>3); t5 already holds the group offset
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            const int sh = 2 * (14 - j);
+            const uint32_t t = sh >= 4 ? __funnelshift_r(cw, halo, sh - 4) : (cw << 4);
+            smem_inc(t5 + (t & 0x3FF0u));
+        }
+    } else if (MODE == 5) {
         // 5-mer ending at base j+1 (j even) = bits [2(14-j)+9 : 2(14-j)] of halo:cw; its counter is
         // word index*4 bytes into T5
 #pragma unroll
@@ -201,8 +224,9 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
     __shared__ __align__(16) uint32_t tab[WORDS];
 
     const int lane = threadIdx.x;
-    const uint32_t t5 = (uint32_t)__cvta_generic_to_shared(tab);  // T5 (MODE 5) or T4 (MODE 4)
-    const uint32_t t4 = MODE == 5 ? t5 + 4096u : t5;
+    const uint32_t t5b = (uint32_t)__cvta_generic_to_shared(tab);  // T5 (MODE 5/7) or T4 (MODE 4)
+    const uint32_t t5 = MODE == 7 ? t5b + 4u * (threadIdx.x >> 3) : t5b;
+    const uint32_t t4 = t5b + 4u * TnfTab<MODE>::T5W;
     const int src_lane = (lane + 31) & 31;
 
     for (int i = lane; i < WORDS; i += 32) tab[i] = 0;
@@ -320,8 +344,9 @@ tnf_packed_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict
     constexpr int WORDS = TnfTab<MODE>::WORDS;
     __shared__ __align__(16) uint32_t tab[WORDS];
     const int lane = threadIdx.x;
-    const uint32_t t5 = (uint32_t)__cvta_generic_to_shared(tab);
-    const uint32_t t4 = MODE == 5 ? t5 + 4096u : t5;
+    const uint32_t t5b = (uint32_t)__cvta_generic_to_shared(tab);
+    const uint32_t t5 = MODE == 7 ? t5b + 4u * (threadIdx.x >> 3) : t5b;
+    const uint32_t t4 = t5b + 4u * TnfTab<MODE>::T5W;
     const int src_lane = (lane + 31) & 31;
     for (int i = lane; i < WORDS; i += 32) tab[i] = 0;
     __syncwarp();
@@ -495,7 +520,7 @@ static int tnf_mode() {
     static int mode = 0;
     if (!mode) {
         const char *e = getenv("MP2_TNF_MODE");
-        mode = (e && e[0] == '4') ? 4 : 5;
+        mode = (e && e[0] == '4') ? 4 : ((e && e[0] == '7') ? 7 : 5);
     }
     return mode;
 }
@@ -520,26 +545,22 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
     }
     MP2_CUDA(cudaGetLastError());
     const int mode = tnf_mode();
-    int occ = 0;
-    if (mode == 5)
-        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_kernel<5>, TNF_THREADS, 0));
-    else
-        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_kernel<4>, TNF_THREADS, 0));
-    if (occ < 1) occ = 1;
-    int64_t grid = (int64_t)num_sms() * occ;
-    const int64_t need = n_chunks;
-    if (grid > need) grid = need;
-    {
-        Launch L("tnf_kernel", stream);
-        if (mode == 5)
-            tnf_kernel<5><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(
-                d_bases - mis, mis, n_bases + mis, d_offsets, n, map.as<int32_t>(), chunk_begin,
-                n_chunks, d_counts, d_gc_counts, ctr.as<int>());
-        else
-            tnf_kernel<4><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(
-                d_bases - mis, mis, n_bases + mis, d_offsets, n, map.as<int32_t>(), chunk_begin,
-                n_chunks, d_counts, d_gc_counts, ctr.as<int>());
-    }
+#define MP2_TNF_LAUNCH(M)                                                                                   \
+    do {                                                                                                    \
+        int occ = 0;                                                                                        \
+        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_kernel<M>, TNF_THREADS, 0));       \
+        if (occ < 1) occ = 1;                                                                               \
+        int64_t grid = (int64_t)num_sms() * occ;                                                            \
+        if (grid > n_chunks) grid = n_chunks;                                                               \
+        Launch L("tnf_kernel", stream);                                                                     \
+        tnf_kernel<M><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(                                          \
+            d_bases - mis, mis, n_bases + mis, d_offsets, n, map.as<int32_t>(), chunk_begin, n_chunks,     \
+            d_counts, d_gc_counts, ctr.as<int>());                                                          \
+    } while (0)
+    if (mode == 7) MP2_TNF_LAUNCH(7);
+    else if (mode == 5) MP2_TNF_LAUNCH(5);
+    else MP2_TNF_LAUNCH(4);
+#undef MP2_TNF_LAUNCH
     MP2_CUDA(cudaGetLastError());
     return MP2_OK;
 }
@@ -651,25 +672,22 @@ extern "C" int mp2_tnf_packed_device(const void *d_codes, const void *d_valid, c
         }
         MP2_CUDA(cudaGetLastError());
         const int mode = tnf_mode();
-        int occ = 0;
-        if (mode == 5)
-            MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_packed_kernel<5>, TNF_THREADS, 0));
-        else
-            MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_packed_kernel<4>, TNF_THREADS, 0));
-        if (occ < 1) occ = 1;
-        int64_t grid = (int64_t)num_sms() * occ;
-        if (grid > n_chunks) grid = n_chunks;
-        {
-            Launch L("tnf_packed_kernel", stream);
-            if (mode == 5)
-                tnf_packed_kernel<5><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(
-                    (const uint32_t *)d_codes, (const uint32_t *)d_valid, n_bases, (const int64_t *)d_offsets, n,
-                    map.as<int32_t>(), n_chunks, (uint32_t *)d_counts, gcc.as<unsigned long long>(), ctr.as<int>());
-            else
-                tnf_packed_kernel<4><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(
-                    (const uint32_t *)d_codes, (const uint32_t *)d_valid, n_bases, (const int64_t *)d_offsets, n,
-                    map.as<int32_t>(), n_chunks, (uint32_t *)d_counts, gcc.as<unsigned long long>(), ctr.as<int>());
-        }
+#define MP2_TNFP_LAUNCH(M)                                                                                      \
+    do {                                                                                                        \
+        int occ = 0;                                                                                            \
+        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_packed_kernel<M>, TNF_THREADS, 0));    \
+        if (occ < 1) occ = 1;                                                                                   \
+        int64_t grid = (int64_t)num_sms() * occ;                                                                \
+        if (grid > n_chunks) grid = n_chunks;                                                                   \
+        Launch L("tnf_packed_kernel", stream);                                                                  \
+        tnf_packed_kernel<M><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(                                       \
+            (const uint32_t *)d_codes, (const uint32_t *)d_valid, n_bases, (const int64_t *)d_offsets, n,       \
+            map.as<int32_t>(), n_chunks, (uint32_t *)d_counts, gcc.as<unsigned long long>(), ctr.as<int>());    \
+    } while (0)
+        if (mode == 7) MP2_TNFP_LAUNCH(7);
+        else if (mode == 5) MP2_TNFP_LAUNCH(5);
+        else MP2_TNFP_LAUNCH(4);
+#undef MP2_TNFP_LAUNCH
         MP2_CUDA(cudaGetLastError());
     }
     MP2_TRY(tnf_finalize((const uint32_t *)d_counts, gcc.as<unsigned long long>(), (const int64_t *)d_offsets, n,

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for m in 4 5; do
+for m in 5 7; do
   MP2_TNF_MODE=$m python -m pytest tests/test_tnf_gpu.py -m gpu -x -q 2>&1 | tail -3
   MP2_TNF_MODE=$m python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_mode$m.json 2> gpurun_out/bench_mode$m.err
   python - <<PY
