@@ -30,6 +30,15 @@ METRIC = "contig Gbp/s k-mer profiling"
 UNIT = "Gbp/s"
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (None if absent)."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p))[kernel]["dram_bytes"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -199,7 +208,9 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
         t_ms = per_launch(name)
         ach = bytes_ / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
         rl.append({"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                   "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": bytes_,
+                   "frac": ach / peak,
+                   "traffic": ncu_traffic(name) if (args.mags == 1000 and args.depth_scale == 1.0) else None,
+                   "algorithmic_bytes_per_launch": bytes_,
                    "kernel_ms": t_ms, "launches_timed": kern[name][1]})
     dom = max(rl, key=lambda r: r["kernel_ms"])
     rec = {
@@ -490,7 +501,8 @@ def main():
                     + (" + all_gather of the scores" if world > 1 else ""),
         },
         "roofline": {"bound": "hbm", "kernel": "tnf_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic("tnf_kernel") if (args.mags == 1000 and not args.long_contigs) else None,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_avg_ms,
                      "launches_timed": k_n.value, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

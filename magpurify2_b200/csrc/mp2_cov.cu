@@ -984,6 +984,297 @@ cov_tile_kernel(const TileArgs a) {
     }
 }
 
+
+// =====================================================================================================
+// cov_tile2_kernel: same algorithm as cov_tile_kernel, reorganised for fewer barriers and
+// instructions: 512 threads, a thread owns 32 consecutive slots (one block scan per tile instead of
+// four), up to four contig windows are histogrammed per pass into four shared histograms and
+// finished by four warps in parallel.
+// =====================================================================================================
+constexpr int C2_THREADS = 512;
+constexpr int C2_PER = CT_TILE / C2_THREADS;            // 32 slots per thread
+constexpr int C2_WORDS = CT_TILE + 4 * C2_THREADS;      // 4 pad words per 32: LDS.128 conflict-free
+constexpr int C2_NW = 4;                                // windows per pass
+constexpr size_t C2_SMEM = sizeof(int32_t) * C2_WORDS + sizeof(uint32_t) * C2_NW * COV_BINS;
+
+__device__ __forceinline__ int c2_phys(int i) { return i + 4 * (i >> 5); }
+
+__global__ void __launch_bounds__(C2_THREADS, 2)
+cov_tile2_kernel(const TileArgs a) {
+    extern __shared__ __align__(16) int32_t s_mem[];
+    int32_t *s_T = s_mem;                                               // C2_WORDS
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_mem + C2_WORDS);  // [C2_NW][COV_BINS]
+    __shared__ int s_wsum[C2_THREADS / 32];
+    __shared__ unsigned int s_maxd[C2_NW];
+    __shared__ int s_tile, s_carry;
+    __shared__ int s_crel[CT_CTAB + 1];
+    __shared__ int s_cev[CT_CTAB + 1];
+    __shared__ int64_t s_wc[C2_NW];
+
+    if (a.check && a.check[0] != 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *a.gate_out = 1;
+        return;
+    }
+    if (*((volatile int *)a.gate_out)) return;  // the general path redoes the whole sample anyway
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t h0 = (uint32_t)__cvta_generic_to_shared(s_hist);
+    const int excl = (int)a.tp.excl;
+    for (int i = tid; i < C2_NW * COV_BINS; i += C2_THREADS) s_hist[i] = 0;
+    if (tid < C2_NW) s_maxd[tid] = 0;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= a.n_tiles) break;
+        const int64_t tile_lo = tile * CT_TILE;
+        const int tlen = (int)(tile_lo + CT_TILE < a.n_pos ? CT_TILE : a.n_pos - tile_lo);
+        const int64_t E0 = a.e_lo[tile], E1 = a.e_hi[tile];
+        const int nev = (int)(E1 - E0);
+        const int64_t ca = a.c_lo[tile], cb = a.c_hi[tile];
+
+        // ---- zero the tile; events: +1 at the start, -1 at the end, blocks open across the tile start ----
+        for (int i = tid; i < C2_WORDS / 4; i += C2_THREADS) reinterpret_cast<int4 *>(s_T)[i] = make_int4(0, 0, 0, 0);
+        if (tid == 0) s_carry = 0;
+        int open = 0;
+        for (int64_t cbase = ca; cbase <= cb; cbase += CT_CTAB) {
+            const int nc = (int)(cb - cbase + 1 < CT_CTAB ? cb - cbase + 1 : CT_CTAB);
+            __syncthreads();
+            for (int i = tid; i <= nc; i += C2_THREADS) {
+                s_crel[i] = clamp_rel(a.off[cbase + i] - tile_lo);
+                s_cev[i] = clamp_rel(a.ev_off[cbase + i] - E0);
+            }
+            __syncthreads();
+            const int eb0 = s_cev[0] > 0 ? s_cev[0] : 0, eb1 = s_cev[nc] < nev ? s_cev[nc] : nev;
+            const int cv1 = nc > 1 ? s_cev[1] : INT_MAX, cv2 = nc > 2 ? s_cev[2] : INT_MAX, cv3 = nc > 3 ? s_cev[3] : INT_MAX;
+            for (int e0 = eb0 + tid; e0 < eb1; e0 += 2 * C2_THREADS) {
+                uint32_t sv[2], ev[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int e = e0 + u * C2_THREADS;
+                    sv[u] = e < eb1 ? __ldg(a.starts + E0 + e) : 0u;
+                    ev[u] = e < eb1 ? __ldg(a.ends + E0 + e) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int e = e0 + u * C2_THREADS;
+                    if (e >= eb1) break;
+                    int j;
+                    if (nc <= 4) {
+                        j = (e >= cv1) + (e >= cv2) + (e >= cv3);
+                    } else {
+                        int lo = 0, hi = nc;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (s_cev[mid] <= e) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        j = lo > 0 ? lo - 1 : 0;
+                    }
+                    const int crel = s_crel[j];
+                    const uint32_t len = (uint32_t)(s_crel[j + 1] - crel);
+                    const uint32_t s = sv[u];
+                    const uint32_t en = ev[u] < len ? ev[u] : len;
+                    if (s < len && en > s) {
+                        const uint32_t gs = (uint32_t)crel + s, ge = (uint32_t)crel + en;  // mod 2^32
+                        const uint32_t ncrel = crel < 0 ? (uint32_t)(-crel) : 0u;
+                        if (s >= ncrel) {
+                            if (gs < (uint32_t)tlen) atomicAdd(&s_T[c2_phys((int)gs)], 1);
+                        } else if (en >= ncrel) {
+                            open++;
+                        }
+                        if (en >= ncrel && ge < (uint32_t)tlen) atomicAdd(&s_T[c2_phys((int)ge)], -1);
+                    }
+                }
+            }
+        }
+        open = __reduce_add_sync(0xffffffffu, open);
+        if (lane == 0 && open) atomicAdd(&s_carry, open);
+        __syncthreads();
+
+        // ---- one block scan: depth just before this thread's 32 slots ----
+        const int myb = 36 * tid;  // c2_phys(32 * tid)
+        int tot = 0;
+        {
+            const int4 *p = reinterpret_cast<const int4 *>(s_T + myb);
+#pragma unroll
+            for (int k = 0; k < C2_PER / 4; k++) {
+                const int4 v = p[k];
+                tot += v.x + v.y + v.z + v.w;
+            }
+        }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int wpre = 0;
+#pragma unroll
+        for (int w = 0; w < C2_THREADS / 32; w++) wpre += w < warp ? s_wsum[w] : 0;
+        const int dstart = s_carry + wpre + incl - tot;  // depth at slot 32*tid - 1
+
+        // ---- contigs whose window intersects the tile, C2_NW windows per pass ----
+        const int q0 = C2_PER * tid;
+        int64_t cbase = ca;
+        int nct = (int)(cb - cbase + 1 < CT_CTAB ? cb - cbase + 1 : CT_CTAB);
+        if (cb - ca + 1 > CT_CTAB) {
+            __syncthreads();
+            for (int i = tid; i <= nct; i += C2_THREADS) s_crel[i] = clamp_rel(a.off[cbase + i] - tile_lo);
+            __syncthreads();
+        }
+        int64_t c = ca;
+        while (c <= cb) {
+            // collect up to C2_NW windows (every thread walks the staged table identically)
+            int wlo[C2_NW], whi[C2_NW];
+            int64_t wck[C2_NW];
+            int nw = 0;
+#pragma unroll
+            for (int k = 0; k < C2_NW; k++) { wlo[k] = 0; whi[k] = -1; wck[k] = 0; }
+            bool restage = false;
+            while (c <= cb && nw < C2_NW) {
+                if (c - cbase >= nct) { restage = true; break; }
+                const int o0 = s_crel[c - cbase], o1 = s_crel[c - cbase + 1];
+                if (o0 >= tlen) { c = cb + 1; break; }
+                if (o1 - o0 > 2 * excl && o1 - excl - 1 >= 0 && o0 + excl < tlen) {
+#pragma unroll
+                    for (int k = 0; k < C2_NW; k++)
+                        if (k == nw) { wlo[k] = o0 + excl; whi[k] = o1 - excl - 1; wck[k] = c; }
+                    if (tid == 0) s_wc[nw] = c;
+                    nw++;
+                }
+                c++;
+            }
+            if (nw > 0) {
+                // ---- histogram pass over this thread's 32 slots ----
+                int mx[C2_NW];
+#pragma unroll
+                for (int k = 0; k < C2_NW; k++) mx[k] = 0;
+                int run = dstart;
+#pragma unroll
+                for (int ch = 0; ch < C2_PER / 16; ch++) {
+                    int d[16];
+                    {
+                        const int4 *p = reinterpret_cast<const int4 *>(s_T + myb + 16 * ch);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int4 v = p[k];
+                            run += v.x; d[4 * k] = run;
+                            run += v.y; d[4 * k + 1] = run;
+                            run += v.z; d[4 * k + 2] = run;
+                            run += v.w; d[4 * k + 3] = run;
+                        }
+                    }
+                    const int q = q0 + 16 * ch;
+#pragma unroll
+                    for (int k = 0; k < C2_NW; k++) {
+                        if (k < nw) {
+                            const int lo = wlo[k] > q ? wlo[k] : q, hi = whi[k] + 1 < q + 16 ? whi[k] + 1 : q + 16;
+                            const int hi2 = hi < tlen ? hi : tlen;
+                            if (hi2 > lo) {
+                                const uint32_t m = ((hi2 - q) >= 32 ? 0xFFFFFFFFu : ((1u << (hi2 - q)) - 1u)) & ~((1u << (lo - q)) - 1u);
+                                const uint32_t hb = h0 + 4u * COV_BINS * k;
+                                int mk = 0;
+                                if (m == 0xFFFFu) {
+#pragma unroll
+                                    for (int i = 0; i < 16; i++) mk = d[i] > mk ? d[i] : mk;
+                                    if (mk < COV_BINS - 1) {
+#pragma unroll
+                                        for (int i = 0; i < 16; i++) smem_inc(hb + 4u * (uint32_t)d[i]);
+                                    } else {
+#pragma unroll
+                                        for (int i = 0; i < 16; i++)
+                                            if (d[i] < COV_BINS - 1) smem_inc(hb + 4u * (uint32_t)d[i]);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 16; i++) {
+                                        const uint32_t in = m & (1u << i);
+                                        mk = (in && d[i] > mk) ? d[i] : mk;
+                                        if (in && d[i] < COV_BINS - 1) smem_inc(hb + 4u * (uint32_t)d[i]);
+                                    }
+                                }
+                                if (mk >= COV_BINS - 1) {  // rare
+                                    int dd[COV_ITEMS];
+#pragma unroll
+                                    for (int i = 0; i < 16; i++) dd[i] = d[i];
+                                    ct_deep_positions(a, wck[k], dd, m & 0xFFFFu);
+                                }
+                                mx[k] = mk > mx[k] ? mk : mx[k];
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < C2_NW; k++) {
+                    if (k < nw) {
+                        const int m2 = __reduce_max_sync(0xffffffffu, mx[k]);
+                        if (lane == 0 && m2 > (int)s_maxd[k]) atomicMax(&s_maxd[k], (unsigned)m2);
+                    }
+                }
+                __syncthreads();
+                // ---- finish: warp k owns window k ----
+                if (warp < nw) {
+                    const int k = warp;
+                    const int64_t cc = s_wc[k];
+                    int wl = 0, wh = -1;
+#pragma unroll
+                    for (int kk = 0; kk < C2_NW; kk++)
+                        if (kk == k) { wl = wlo[kk]; wh = whi[kk]; }
+                    const int64_t o0g = a.off[cc], o1g = a.off[cc + 1];
+                    const uint64_t N = (uint64_t)(o1g - o0g - 2 * (int64_t)excl);
+                    const uint32_t maxd = s_maxd[k];
+                    const uint32_t mtop = maxd < COV_BINS - 1 ? maxd : COV_BINS - 1;
+                    uint32_t *hk = s_hist + COV_BINS * k;
+                    if (wl >= 0 && wh < tlen) {
+                        finish_contig_t(a, cc, N, maxd, [&](uint32_t i) { return hk[i]; });
+                    } else {
+                        // window spans tiles: merge into the row of the tile it starts in; last contributor finishes
+                        const int64_t row = (o0g + excl) / CT_TILE;
+                        uint32_t *r = a.rows + row * COV_BINS;
+                        const int lo = wl > 0 ? wl : 0, hi = wh + 1 < tlen ? wh + 1 : tlen;
+                        const unsigned long long mine = (unsigned long long)(hi - lo);
+                        for (uint32_t i = lane; i <= mtop; i += 32) {
+                            const uint32_t v = hk[i];
+                            if (v) atomicAdd(&r[i], v);
+                        }
+                        __threadfence();
+                        __syncwarp();
+                        int last = 0;
+                        if (lane == 0) {
+                            atomicMax(&a.meta[row].maxd, maxd);
+                            __threadfence();
+                            const unsigned long long old = atomicAdd(&a.meta[row].done, mine);
+                            last = (old + mine == N);
+                        }
+                        last = __shfl_sync(0xffffffffu, last, 0);
+                        if (last) {
+                            __threadfence();
+                            const uint32_t gm = *((volatile unsigned int *)&a.meta[row].maxd);
+                            finish_contig_t(a, cc, N, gm, [&](uint32_t i) { return __ldcg(r + i); });
+                        }
+                    }
+                    __syncwarp();
+                    for (uint32_t i = lane; i <= mtop; i += 32) hk[i] = 0;
+                    if (lane == 0) s_maxd[k] = 0;
+                }
+                __syncthreads();
+            }
+            if (restage) {
+                __syncthreads();
+                cbase = c;
+                nct = (int)(cb - cbase + 1 < CT_CTAB ? cb - cbase + 1 : CT_CTAB);
+                for (int i = tid; i <= nct; i += C2_THREADS) s_crel[i] = clamp_rel(a.off[cbase + i] - tile_lo);
+                __syncthreads();
+            }
+        }
+        __syncthreads();  // s_T / s_tile / s_wsum are rewritten by the next tile
+    }
+}
+
 }  // namespace mp2
 
 using namespace mp2;
@@ -1101,16 +1392,29 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
         static bool attr_done = false;
         if (!attr_done) {
             MP2_CUDA(cudaFuncSetAttribute(cov_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
+            MP2_CUDA(cudaFuncSetAttribute(cov_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2_SMEM));
             attr_done = true;
         }
+        static int tile_ver = 0;  // MP2_COV_TILE=1 selects the first version of the tile kernel (A/B)
+        if (!tile_ver) {
+            const char *e = getenv("MP2_COV_TILE");
+            tile_ver = (e && e[0] == '1') ? 1 : 2;
+        }
         int occ = 0;
-        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_tile_kernel, COV_THREADS, CT_SMEM));
-        if (occ < 1) occ = 1;
-        int64_t grid = (int64_t)num_sms() * occ;
-        if (grid > n_tiles) grid = n_tiles;
-        {
+        if (tile_ver == 1) {
+            MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_tile_kernel, COV_THREADS, CT_SMEM));
+            if (occ < 1) occ = 1;
+            int64_t grid = (int64_t)num_sms() * occ;
+            if (grid > n_tiles) grid = n_tiles;
             Launch L("cov_tile_kernel", stream);
             cov_tile_kernel<<<(unsigned)grid, COV_THREADS, CT_SMEM, stream>>>(t);
+        } else {
+            MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_tile2_kernel, C2_THREADS, C2_SMEM));
+            if (occ < 1) occ = 1;
+            int64_t grid = (int64_t)num_sms() * occ;
+            if (grid > n_tiles) grid = n_tiles;
+            Launch L("cov_tile_kernel", stream);
+            cov_tile2_kernel<<<(unsigned)grid, C2_THREADS, C2_SMEM, stream>>>(t);
         }
         MP2_CUDA(cudaGetLastError());
     }
