@@ -160,8 +160,8 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     ms = e0.elapsed_time(e1)
     launches = lib.mp2_launch_count() - l0
     kern = {}
-    for name in ("cov_tile_kernel", "cov_scatter_kernel", "cov_depth_kernel", "cov_deep_kernel", "cov_check_kernel",
-                 "cov_bounds_kernel", "cov_zero_kernel"):
+    for name in ("cov_stream_kernel", "cov_tile_kernel", "cov_scatter_kernel", "cov_depth_kernel", "cov_deep_kernel",
+                 "cov_check_kernel", "cov_bounds_kernel", "cov_zero_kernel"):
         k_ms, k_n = C.c_double(0), C.c_int64(0)
         lib.mp2_profile_read(name.encode(), C.byref(k_ms), C.byref(k_n))
         kern[name] = (k_ms.value, k_n.value)
@@ -203,7 +203,8 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     per_launch = lambda k: kern[k][0] / max(1, kern[k][1])
     R_avg = R_total / S
     rl = []
-    for name, bytes_ in (("cov_tile_kernel", 8.0 * R_avg + 16.0 * (L / 16384.0) + 4.0 * n),
+    for name, bytes_ in (("cov_stream_kernel", 8.0 * R_avg + 24.0 * (L / 65536.0) + 4.0 * n),
+                         ("cov_tile_kernel", 8.0 * R_avg + 24.0 * (L / 16384.0) + 4.0 * n),
                          ("cov_depth_kernel", 4.0 * (L + 1)), ("cov_scatter_kernel", 8.0 * R_avg + 8.0 * R_avg)):
         t_ms = per_launch(name)
         ach = bytes_ / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0

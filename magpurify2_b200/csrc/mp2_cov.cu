@@ -674,7 +674,7 @@ __device__ __forceinline__ void finish_contig_t(const TileArgs &a, int64_t c, ui
 
 // Rare: depths beyond the shared histogram's range are counted in the contig's row of the deep pool
 // (claimed on first use).  Called by the lanes of a warp that hold such positions.
-__device__ __noinline__ void ct_deep_positions(const TileArgs &a, int64_t c, const int *d, uint32_t m) {
+__device__ __forceinline__ void ct_deep_positions(const TileArgs &a, int64_t c, const int *d, uint32_t m) {
     const int lane = threadIdx.x & 31;
     int r = 0;
     const unsigned grp = __activemask();
@@ -986,292 +986,324 @@ cov_tile_kernel(const TileArgs a) {
 
 
 // =====================================================================================================
-// cov_tile2_kernel: same algorithm as cov_tile_kernel, reorganised for fewer barriers and
-// instructions: 512 threads, a thread owns 32 consecutive slots (one block scan per tile instead of
-// four), up to four contig windows are histogrammed per pass into four shared histograms and
-// finished by four warps in parallel.
+// cov_stream_kernel: the tile algorithm with NO block barrier.  A warp (= CTA) owns a run of 65536
+// slots and streams through it in windows of 2048 slots held in its own shared memory: events are
+// consumed in order, 32 per batch (one per lane); an end that falls beyond the current window lands
+// in a 512-slot overflow region that becomes the head of the next window, so the running depth is
+// simply carried from window to window (only the first window of a run looks back max_span slots).
+// The contig histogram stays in the warp's shared memory across windows until the contig ends; only
+// contigs crossing a RUN boundary go through the global rows.  Needs max_span <= 512.
 // =====================================================================================================
-constexpr int C2_THREADS = 512;
-constexpr int C2_PER = CT_TILE / C2_THREADS;            // 32 slots per thread
-constexpr int C2_WORDS = CT_TILE + 4 * C2_THREADS;      // 4 pad words per 32: LDS.128 conflict-free
-constexpr int C2_NW = 4;                                // windows per pass
-constexpr size_t C2_SMEM = sizeof(int32_t) * C2_WORDS + sizeof(uint32_t) * C2_NW * COV_BINS;
+constexpr int C3_W = 2048;                   // slots per window (64 per lane)
+constexpr int C3_S = 512;                    // overflow region = largest block span of the fast path
+constexpr int C3_RUN = 65536;                // slots per run
+constexpr int C3_TPR = C3_RUN / C3_W;        // 32 windows per run
+constexpr int C3_WORDS = (C3_W + C3_S) + 4 * ((C3_W + C3_S) / 64);  // 4 pad words per 64 slots
+constexpr int C3_HEAD = C3_S + 4 * (C3_S / 64);                     // words of the overflow region
 
-__device__ __forceinline__ int c2_phys(int i) { return i + 4 * (i >> 5); }
+__device__ __forceinline__ int c3_phys(int i) { return i + 4 * (i >> 6); }
 
-__global__ void __launch_bounds__(C2_THREADS, 2)
-cov_tile2_kernel(const TileArgs a) {
-    extern __shared__ __align__(16) int32_t s_mem[];
-    int32_t *s_T = s_mem;                                               // C2_WORDS
-    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_mem + C2_WORDS);  // [C2_NW][COV_BINS]
-    __shared__ int s_wsum[C2_THREADS / 32];
-    __shared__ unsigned int s_maxd[C2_NW];
-    __shared__ int s_tile, s_carry;
-    __shared__ int s_crel[CT_CTAB + 1];
-    __shared__ int s_cev[CT_CTAB + 1];
-    __shared__ int64_t s_wc[C2_NW];
+__global__ void cov_bounds_run_kernel(const uint32_t *__restrict__ starts, const int64_t *__restrict__ ev_off,
+                                      const int64_t *__restrict__ off, int64_t n, int64_t n_runs, uint32_t max_span,
+                                      const unsigned int *__restrict__ d_span, int64_t *__restrict__ e_lo,
+                                      int64_t *__restrict__ e_hi, int32_t *__restrict__ c_lo,
+                                      int32_t *__restrict__ c_hi, int *__restrict__ gate) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n_runs) return;
+    if (d_span) max_span = *d_span;
+    if (max_span > (uint32_t)C3_S) {  // blocks longer than the overflow region: general path
+        if (k == 0) *gate = 1;
+        return;
+    }
+    const int64_t A = k * C3_RUN - (int64_t)max_span, B = (k + 1) * C3_RUN;
+    e_lo[k] = first_event_ge(starts, ev_off, off, n, A);
+    e_hi[k] = first_event_ge(starts, ev_off, off, n, B);
+    c_lo[k] = (int32_t)last_le(off, 0, n, k * C3_RUN);  // contig holding the run's first slot
+    c_hi[k] = (int32_t)last_le(off, 0, n, B - 1 < off[n] ? B - 1 : off[n]);
+}
 
+// Out-of-line pieces of cov_stream_kernel: they run once per contig (or never), keeping them out of the
+// streaming loop keeps the loop inside the instruction cache.
+__device__ __noinline__ void c3_deep_chunk(const TileArgs &a, int64_t c, const int32_t *chunk, int depth_before,
+                                           uint32_t m) {
+    int dd[COV_ITEMS];
+    int run_d = depth_before;
+    for (int i = 0; i < 16; i++) { run_d += chunk[i]; dd[i] = run_d; }
+    ct_deep_positions(a, c, dd, m);
+}
+
+// The window of contig c is complete (or the run ends): finish it from the warp's histogram when it
+// lies inside this run, else merge into the row of the run it started in (last contributor finishes).
+__device__ __noinline__ void c3_close_window(const TileArgs &a, int64_t c, bool local, int maxd, int in_run,
+                                             uint32_t *s_hist) {
+    const int lane = threadIdx.x & 31;
+    const int64_t excl = a.tp.excl;
+    const int64_t o0g = a.off[c], o1g = a.off[c + 1];
+    const uint64_t N = (uint64_t)(o1g - o0g - 2 * excl);
+    const uint32_t mtop = (uint32_t)(maxd < COV_BINS - 1 ? maxd : COV_BINS - 1);
+    __syncwarp();
+    if (local) {
+        finish_contig_t(a, c, N, (uint32_t)maxd, [&](uint32_t i) { return s_hist[i]; });
+    } else {
+        const int64_t row = (o0g + excl) / C3_RUN;
+        uint32_t *r = a.rows + row * COV_BINS;
+        for (uint32_t i = lane; i <= mtop; i += 32) {
+            const uint32_t v = s_hist[i];
+            if (v) atomicAdd(&r[i], v);
+        }
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+            atomicMax(&a.meta[row].maxd, (unsigned)maxd);
+            __threadfence();
+            const unsigned long long old = atomicAdd(&a.meta[row].done, (unsigned long long)in_run);
+            last = (old + (unsigned long long)in_run == N);
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence();
+            const uint32_t gm = *((volatile unsigned int *)&a.meta[row].maxd);
+            finish_contig_t(a, c, N, gm, [&](uint32_t i) { return __ldcg(r + i); });
+        }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i <= mtop; i += 32) s_hist[i] = 0;
+    __syncwarp();
+}
+
+// contig cursor of the event stream as a register quad: x = contig index, y = first event of the following
+// contig (relative to the run's first event, saturated), z = contig start - run_lo (saturated), w = length
+__device__ __noinline__ int4 c3_seek(const int64_t *__restrict__ ev_off, const int64_t *__restrict__ off, int ec,
+                                     int c_hi_excl, int64_t e_abs, int64_t e_base, int64_t run_lo) {
+    const int64_t c = last_le(ev_off, ec, c_hi_excl, e_abs);
+    const int64_t o0 = off[c];
+    return make_int4((int)c, clamp_rel(ev_off[c + 1] - e_base), clamp_rel(o0 - run_lo), (int)(off[c + 1] - o0));
+}
+
+__global__ void __launch_bounds__(32)
+cov_stream_kernel(const __grid_constant__ TileArgs a) {
+    __shared__ __align__(16) int32_t s_T[C3_WORDS];
+    __shared__ uint32_t s_hist[COV_BINS];
     if (a.check && a.check[0] != 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) *a.gate_out = 1;
         return;
     }
-    if (*((volatile int *)a.gate_out)) return;  // the general path redoes the whole sample anyway
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (*((volatile int *)a.gate_out)) return;
+    const int lane = threadIdx.x;
     const uint32_t h0 = (uint32_t)__cvta_generic_to_shared(s_hist);
     const int excl = (int)a.tp.excl;
-    for (int i = tid; i < C2_NW * COV_BINS; i += C2_THREADS) s_hist[i] = 0;
-    if (tid < C2_NW) s_maxd[tid] = 0;
-    __syncthreads();
+    for (int i = lane; i < COV_BINS; i += 32) s_hist[i] = 0;
+    __syncwarp();
 
     for (;;) {
-        if (tid == 0) s_tile = atomicAdd(a.work_counter, 1);
-        __syncthreads();
-        const int64_t tile = s_tile;
-        if (tile >= a.n_tiles) break;
-        const int64_t tile_lo = tile * CT_TILE;
-        const int tlen = (int)(tile_lo + CT_TILE < a.n_pos ? CT_TILE : a.n_pos - tile_lo);
-        const int64_t E0 = a.e_lo[tile], E1 = a.e_hi[tile];
-        const int nev = (int)(E1 - E0);
-        const int64_t ca = a.c_lo[tile], cb = a.c_hi[tile];
+        int64_t run = 0;
+        if (lane == 0) run = atomicAdd(a.work_counter, 1);
+        run = __shfl_sync(0xffffffffu, run, 0);
+        if (run >= a.n_tiles) break;
+        const int64_t run_lo = run * C3_RUN;
+        const int rlen = (int)(run_lo + C3_RUN < a.n_pos ? C3_RUN : a.n_pos - run_lo);
+        const int64_t e_base = a.e_lo[run];                 // first event this run looks at
+        const int n_ev = (int)(a.e_hi[run] - e_base);        // events of the run (fits 32 bits)
+        const uint32_t *__restrict__ ev_s = a.starts + e_base;
+        const uint32_t *__restrict__ ev_e = a.ends + e_base;
+        int e_cur = 0;                                       // next event to consume, relative to e_base
+        const int64_t c_last = a.c_hi[run];
+        const int c_hi_excl = (int)(c_last + 1 < a.n ? c_last + 1 : a.n);
+        int4 cur = make_int4(0, 0, 0, 0);
+        if (n_ev > 0) cur = c3_seek(a.ev_off, a.off, 0, (int)a.n, e_base, e_base, run_lo);
+        // events are fetched in groups of 128 (4 coalesced batches of 32), one group ahead of the one being
+        // applied: 16 loads in flight per lane cover the HBM latency without relying on occupancy
+        uint32_t cs[4], ce[4], ns[4], ne[4];
+#define C3_LOAD_GROUP(S, E, BASE)                                               \
+    _Pragma("unroll") for (int j_ = 0; j_ < 4; j_++) {                          \
+        const int i_ = (BASE) + 32 * j_ + lane;                                 \
+        S[j_] = 0; E[j_] = 0;                                                   \
+        if (i_ < n_ev) { S[j_] = __ldg(ev_s + i_); E[j_] = __ldg(ev_e + i_); }  \
+    }
+        C3_LOAD_GROUP(cs, ce, e_cur);
+        C3_LOAD_GROUP(ns, ne, e_cur + 128);
+        for (int i = lane; i < C3_WORDS / 4; i += 32) reinterpret_cast<int4 *>(s_T)[i] = make_int4(0, 0, 0, 0);
+        __syncwarp();
 
-        // ---- zero the tile; events: +1 at the start, -1 at the end, blocks open across the tile start ----
-        for (int i = tid; i < C2_WORDS / 4; i += C2_THREADS) reinterpret_cast<int4 *>(s_T)[i] = make_int4(0, 0, 0, 0);
-        if (tid == 0) s_carry = 0;
-        int open = 0;
-        for (int64_t cbase = ca; cbase <= cb; cbase += CT_CTAB) {
-            const int nc = (int)(cb - cbase + 1 < CT_CTAB ? cb - cbase + 1 : CT_CTAB);
-            __syncthreads();
-            for (int i = tid; i <= nc; i += C2_THREADS) {
-                s_crel[i] = clamp_rel(a.off[cbase + i] - tile_lo);
-                s_cev[i] = clamp_rel(a.ev_off[cbase + i] - E0);
-            }
-            __syncthreads();
-            const int eb0 = s_cev[0] > 0 ? s_cev[0] : 0, eb1 = s_cev[nc] < nev ? s_cev[nc] : nev;
-            const int cv1 = nc > 1 ? s_cev[1] : INT_MAX, cv2 = nc > 2 ? s_cev[2] : INT_MAX, cv3 = nc > 3 ? s_cev[3] : INT_MAX;
-            for (int e0 = eb0 + tid; e0 < eb1; e0 += 2 * C2_THREADS) {
-                uint32_t sv[2], ev[2];
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int e = e0 + u * C2_THREADS;
-                    sv[u] = e < eb1 ? __ldg(a.starts + E0 + e) : 0u;
-                    ev[u] = e < eb1 ? __ldg(a.ends + E0 + e) : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int e = e0 + u * C2_THREADS;
-                    if (e >= eb1) break;
-                    int j;
-                    if (nc <= 4) {
-                        j = (e >= cv1) + (e >= cv2) + (e >= cv3);
-                    } else {
-                        int lo = 0, hi = nc;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (s_cev[mid] <= e) lo = mid + 1;
-                            else hi = mid;
-                        }
-                        j = lo > 0 ? lo - 1 : 0;
-                    }
-                    const int crel = s_crel[j];
-                    const uint32_t len = (uint32_t)(s_crel[j + 1] - crel);
-                    const uint32_t s = sv[u];
-                    const uint32_t en = ev[u] < len ? ev[u] : len;
-                    if (s < len && en > s) {
-                        const uint32_t gs = (uint32_t)crel + s, ge = (uint32_t)crel + en;  // mod 2^32
-                        const uint32_t ncrel = crel < 0 ? (uint32_t)(-crel) : 0u;
-                        if (s >= ncrel) {
-                            if (gs < (uint32_t)tlen) atomicAdd(&s_T[c2_phys((int)gs)], 1);
-                        } else if (en >= ncrel) {
-                            open++;
-                        }
-                        if (en >= ncrel && ge < (uint32_t)tlen) atomicAdd(&s_T[c2_phys((int)ge)], -1);
-                    }
-                }
-            }
-        }
-        open = __reduce_add_sync(0xffffffffu, open);
-        if (lane == 0 && open) atomicAdd(&s_carry, open);
-        __syncthreads();
+        // window state of the contig being histogrammed
+        int64_t c = a.c_lo[run];
+        bool have = false;
+        int wlo = 0, whi = -1;      // run-relative window of contig c
+        int in_run = 0;             // window slots of c accumulated in this run
+        int maxd = 0;               // largest depth of c seen in this run (warp-uniform)
+        int carry = 0;              // depth just before the current window
 
-        // ---- one block scan: depth just before this thread's 32 slots ----
-        const int myb = 36 * tid;  // c2_phys(32 * tid)
-        int tot = 0;
-        {
-            const int4 *p = reinterpret_cast<const int4 *>(s_T + myb);
+        for (int k = 0; k < C3_TPR; k++) {
+            const int t_lo = k * C3_W;
+            if (t_lo >= rlen) break;
+            const int t_hi = t_lo + C3_W < rlen ? t_lo + C3_W : rlen;
+            // ---- events whose start lies before t_hi ----
+            int open = 0;
+            for (;;) {
+                bool partial = false;
 #pragma unroll
-            for (int k = 0; k < C2_PER / 4; k++) {
-                const int4 v = p[k];
-                tot += v.x + v.y + v.z + v.w;
-            }
-        }
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        int wpre = 0;
-#pragma unroll
-        for (int w = 0; w < C2_THREADS / 32; w++) wpre += w < warp ? s_wsum[w] : 0;
-        const int dstart = s_carry + wpre + incl - tot;  // depth at slot 32*tid - 1
-
-        // ---- contigs whose window intersects the tile, C2_NW windows per pass ----
-        const int q0 = C2_PER * tid;
-        int64_t cbase = ca;
-        int nct = (int)(cb - cbase + 1 < CT_CTAB ? cb - cbase + 1 : CT_CTAB);
-        if (cb - ca + 1 > CT_CTAB) {
-            __syncthreads();
-            for (int i = tid; i <= nct; i += C2_THREADS) s_crel[i] = clamp_rel(a.off[cbase + i] - tile_lo);
-            __syncthreads();
-        }
-        int64_t c = ca;
-        while (c <= cb) {
-            // collect up to C2_NW windows (every thread walks the staged table identically)
-            int wlo[C2_NW], whi[C2_NW];
-            int64_t wck[C2_NW];
-            int nw = 0;
-#pragma unroll
-            for (int k = 0; k < C2_NW; k++) { wlo[k] = 0; whi[k] = -1; wck[k] = 0; }
-            bool restage = false;
-            while (c <= cb && nw < C2_NW) {
-                if (c - cbase >= nct) { restage = true; break; }
-                const int o0 = s_crel[c - cbase], o1 = s_crel[c - cbase + 1];
-                if (o0 >= tlen) { c = cb + 1; break; }
-                if (o1 - o0 > 2 * excl && o1 - excl - 1 >= 0 && o0 + excl < tlen) {
-#pragma unroll
-                    for (int k = 0; k < C2_NW; k++)
-                        if (k == nw) { wlo[k] = o0 + excl; whi[k] = o1 - excl - 1; wck[k] = c; }
-                    if (tid == 0) s_wc[nw] = c;
-                    nw++;
-                }
-                c++;
-            }
-            if (nw > 0) {
-                // ---- histogram pass over this thread's 32 slots ----
-                int mx[C2_NW];
-#pragma unroll
-                for (int k = 0; k < C2_NW; k++) mx[k] = 0;
-                int run = dstart;
-#pragma unroll
-                for (int ch = 0; ch < C2_PER / 16; ch++) {
-                    int d[16];
-                    {
-                        const int4 *p = reinterpret_cast<const int4 *>(s_T + myb + 16 * ch);
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int4 v = p[k];
-                            run += v.x; d[4 * k] = run;
-                            run += v.y; d[4 * k + 1] = run;
-                            run += v.z; d[4 * k + 2] = run;
-                            run += v.w; d[4 * k + 3] = run;
+                for (int j = 0; j < 4; j++) {
+                    if (!partial) {
+                        const int e = e_cur + lane;
+                        const bool live = e < n_ev;
+                        const uint32_t sv = cs[j], ev = ce[j];
+                        int crel = cur.z;
+                        uint32_t len = (uint32_t)cur.w;
+                        if (live && e >= cur.y) {  // this lane's event belongs to a later contig (rare)
+                            const int4 mine = c3_seek(a.ev_off, a.off, cur.x, c_hi_excl, e_base + e, e_base, run_lo);
+                            crel = mine.z;
+                            len = (uint32_t)mine.w;
                         }
+                        const uint32_t en = ev < len ? ev : len;
+                        const bool ok = live && sv < len && en > sv;
+                        const int gs = (int)((uint32_t)crel + sv), ge = (int)((uint32_t)crel + en);  // run-relative
+                        // consumed now: start < t_hi (a start beyond its contig is dropped at once, like the general path)
+                        const bool before = live && (sv >= len || gs < t_hi);
+                        const unsigned nb = ~__ballot_sync(0xffffffffu, before);
+                        const int cnt = nb ? __ffs(nb) - 1 : 32;  // leading lanes only (starts are sorted)
+                        if (ok && lane < cnt) {
+                            if (gs >= t_lo) atomicAdd(&s_T[c3_phys(gs - t_lo)], 1);
+                            else if (ge >= t_lo) open++;  // first window of a run: block open across run_lo
+                            if (ge >= t_lo) atomicAdd(&s_T[c3_phys(ge - t_lo)], -1);  // ge - t_lo < W + S
+                        }
+                        e_cur += cnt;
+                        if (cnt && e_cur < n_ev && e_cur >= cur.y)  // advance the warp's contig cursor
+                            cur = c3_seek(a.ev_off, a.off, cur.x, c_hi_excl, e_base + e_cur, e_base, run_lo);
+                        if (cnt < 32) partial = true;
                     }
-                    const int q = q0 + 16 * ch;
+                }
+                if (!partial) {  // steady state: the prefetched group becomes current, fetch the next one
 #pragma unroll
-                    for (int k = 0; k < C2_NW; k++) {
-                        if (k < nw) {
-                            const int lo = wlo[k] > q ? wlo[k] : q, hi = whi[k] + 1 < q + 16 ? whi[k] + 1 : q + 16;
-                            const int hi2 = hi < tlen ? hi : tlen;
-                            if (hi2 > lo) {
-                                const uint32_t m = ((hi2 - q) >= 32 ? 0xFFFFFFFFu : ((1u << (hi2 - q)) - 1u)) & ~((1u << (lo - q)) - 1u);
-                                const uint32_t hb = h0 + 4u * COV_BINS * k;
+                    for (int j = 0; j < 4; j++) { cs[j] = ns[j]; ce[j] = ne[j]; }
+                    C3_LOAD_GROUP(ns, ne, e_cur + 128);
+                } else {         // window done: restart at the first unconsumed event; loads overlap the scan below
+                    C3_LOAD_GROUP(cs, ce, e_cur);
+                    C3_LOAD_GROUP(ns, ne, e_cur + 128);
+                    break;
+                }
+            }
+            open = __reduce_add_sync(0xffffffffu, open);
+            carry += open;
+            __syncwarp();
+
+            // ---- this lane's 64 slots: total, exclusive warp scan ----
+            const int myb = 68 * lane;
+            int tot = 0;
+            {
+                const int4 *p = reinterpret_cast<const int4 *>(s_T + myb);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int4 v = p[j];
+                    tot += v.x + v.y + v.z + v.w;
+                }
+            }
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int dstart = carry + incl - tot;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+
+            // ---- contig windows intersecting [t_lo, t_hi) ----
+            const int q0 = t_lo + 64 * lane;
+            for (;;) {
+                if (!have) {
+                    if (c > c_last) break;
+                    const int64_t o0 = a.off[c], o1 = a.off[c + 1];
+                    const int r0 = clamp_rel(o0 - run_lo);
+                    if (r0 >= t_hi) break;
+                    const int r1 = clamp_rel(o1 - run_lo);
+                    if (o1 - o0 > 2 * (int64_t)excl) { wlo = r0 + excl; whi = r1 - excl - 1; }
+                    else { wlo = 0; whi = -1; }
+                    have = true;
+                    in_run = 0;
+                    maxd = 0;
+                }
+                if (whi < wlo || whi < 0) { c++; have = false; continue; }  // no window / ended before this run
+                if (wlo >= t_hi) break;
+                const int lo = wlo > t_lo ? wlo : t_lo, hi = whi + 1 < t_hi ? whi + 1 : t_hi;
+                if (hi > lo) {
+                    int mxl = 0;
+                    if (lo < q0 + 64 && hi > q0) {  // this lane's slots intersect the window
+                        int run_d = dstart;
+#pragma unroll 1
+                        for (int ch = 0; ch < 4; ch++) {
+                            const int q = q0 + 16 * ch;
+                            const int d_before = run_d;
+                            int d[16];
+                            const int4 *p = reinterpret_cast<const int4 *>(s_T + myb + 16 * ch);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const int4 v = p[j];
+                                run_d += v.x; d[4 * j] = run_d;
+                                run_d += v.y; d[4 * j + 1] = run_d;
+                                run_d += v.z; d[4 * j + 2] = run_d;
+                                run_d += v.w; d[4 * j + 3] = run_d;
+                            }
+                            const int l2 = lo > q ? lo : q, h2 = hi < q + 16 ? hi : q + 16;
+                            if (h2 > l2) {
+                                const uint32_t m = ((1u << (h2 - q)) - 1u) & ~((1u << (l2 - q)) - 1u);
                                 int mk = 0;
                                 if (m == 0xFFFFu) {
 #pragma unroll
                                     for (int i = 0; i < 16; i++) mk = d[i] > mk ? d[i] : mk;
                                     if (mk < COV_BINS - 1) {
 #pragma unroll
-                                        for (int i = 0; i < 16; i++) smem_inc(hb + 4u * (uint32_t)d[i]);
+                                        for (int i = 0; i < 16; i++) smem_inc(h0 + 4u * (uint32_t)d[i]);
                                     } else {
 #pragma unroll
                                         for (int i = 0; i < 16; i++)
-                                            if (d[i] < COV_BINS - 1) smem_inc(hb + 4u * (uint32_t)d[i]);
+                                            if (d[i] < COV_BINS - 1) smem_inc(h0 + 4u * (uint32_t)d[i]);
                                     }
                                 } else {
 #pragma unroll
                                     for (int i = 0; i < 16; i++) {
                                         const uint32_t in = m & (1u << i);
                                         mk = (in && d[i] > mk) ? d[i] : mk;
-                                        if (in && d[i] < COV_BINS - 1) smem_inc(hb + 4u * (uint32_t)d[i]);
+                                        if (in && d[i] < COV_BINS - 1) smem_inc(h0 + 4u * (uint32_t)d[i]);
                                     }
                                 }
-                                if (mk >= COV_BINS - 1) {  // rare
-                                    int dd[COV_ITEMS];
-#pragma unroll
-                                    for (int i = 0; i < 16; i++) dd[i] = d[i];
-                                    ct_deep_positions(a, wck[k], dd, m & 0xFFFFu);
-                                }
-                                mx[k] = mk > mx[k] ? mk : mx[k];
+                                if (mk >= COV_BINS - 1) c3_deep_chunk(a, c, s_T + myb + 16 * ch, d_before, m);  // rare
+                                mxl = mk > mxl ? mk : mxl;
                             }
                         }
                     }
+                    mxl = __reduce_max_sync(0xffffffffu, mxl);
+                    maxd = mxl > maxd ? mxl : maxd;
+                    in_run += hi - lo;
                 }
-#pragma unroll
-                for (int k = 0; k < C2_NW; k++) {
-                    if (k < nw) {
-                        const int m2 = __reduce_max_sync(0xffffffffu, mx[k]);
-                        if (lane == 0 && m2 > (int)s_maxd[k]) atomicMax(&s_maxd[k], (unsigned)m2);
-                    }
-                }
-                __syncthreads();
-                // ---- finish: warp k owns window k ----
-                if (warp < nw) {
-                    const int k = warp;
-                    const int64_t cc = s_wc[k];
-                    int wl = 0, wh = -1;
-#pragma unroll
-                    for (int kk = 0; kk < C2_NW; kk++)
-                        if (kk == k) { wl = wlo[kk]; wh = whi[kk]; }
-                    const int64_t o0g = a.off[cc], o1g = a.off[cc + 1];
-                    const uint64_t N = (uint64_t)(o1g - o0g - 2 * (int64_t)excl);
-                    const uint32_t maxd = s_maxd[k];
-                    const uint32_t mtop = maxd < COV_BINS - 1 ? maxd : COV_BINS - 1;
-                    uint32_t *hk = s_hist + COV_BINS * k;
-                    if (wl >= 0 && wh < tlen) {
-                        finish_contig_t(a, cc, N, maxd, [&](uint32_t i) { return hk[i]; });
-                    } else {
-                        // window spans tiles: merge into the row of the tile it starts in; last contributor finishes
-                        const int64_t row = (o0g + excl) / CT_TILE;
-                        uint32_t *r = a.rows + row * COV_BINS;
-                        const int lo = wl > 0 ? wl : 0, hi = wh + 1 < tlen ? wh + 1 : tlen;
-                        const unsigned long long mine = (unsigned long long)(hi - lo);
-                        for (uint32_t i = lane; i <= mtop; i += 32) {
-                            const uint32_t v = hk[i];
-                            if (v) atomicAdd(&r[i], v);
-                        }
-                        __threadfence();
-                        __syncwarp();
-                        int last = 0;
-                        if (lane == 0) {
-                            atomicMax(&a.meta[row].maxd, maxd);
-                            __threadfence();
-                            const unsigned long long old = atomicAdd(&a.meta[row].done, mine);
-                            last = (old + mine == N);
-                        }
-                        last = __shfl_sync(0xffffffffu, last, 0);
-                        if (last) {
-                            __threadfence();
-                            const uint32_t gm = *((volatile unsigned int *)&a.meta[row].maxd);
-                            finish_contig_t(a, cc, N, gm, [&](uint32_t i) { return __ldcg(r + i); });
-                        }
-                    }
-                    __syncwarp();
-                    for (uint32_t i = lane; i <= mtop; i += 32) hk[i] = 0;
-                    if (lane == 0) s_maxd[k] = 0;
-                }
-                __syncthreads();
+                if (whi >= t_hi) break;  // the window continues in the next 2048 slots
+                // ---- the window of contig c ends here ----
+                c3_close_window(a, c, wlo >= 0, maxd, in_run, s_hist);
+                c++;
+                have = false;
             }
-            if (restage) {
-                __syncthreads();
-                cbase = c;
-                nct = (int)(cb - cbase + 1 < CT_CTAB ? cb - cbase + 1 : CT_CTAB);
-                for (int i = tid; i <= nct; i += C2_THREADS) s_crel[i] = clamp_rel(a.off[cbase + i] - tile_lo);
-                __syncthreads();
+            // ---- slide: the overflow region becomes the head of the next window ----
+            __syncwarp();
+            if (k + 1 < C3_TPR && t_hi < rlen) {
+                const int src = c3_phys(C3_W);  // 2176
+                int4 keep[(C3_HEAD / 4 + 31) / 32];
+#pragma unroll
+                for (int j = 0; j < (C3_HEAD / 4 + 31) / 32; j++) {
+                    const int i = lane + 32 * j;
+                    keep[j] = i < C3_HEAD / 4 ? reinterpret_cast<const int4 *>(s_T + src)[i] : make_int4(0, 0, 0, 0);
+                }
+                __syncwarp();
+                for (int i = lane; i < C3_WORDS / 4; i += 32) reinterpret_cast<int4 *>(s_T)[i] = make_int4(0, 0, 0, 0);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < (C3_HEAD / 4 + 31) / 32; j++) {
+                    const int i = lane + 32 * j;
+                    if (i < C3_HEAD / 4) reinterpret_cast<int4 *>(s_T)[i] = keep[j];
+                }
+                __syncwarp();
             }
         }
-        __syncthreads();  // s_T / s_tile / s_wsum are rewritten by the next tile
+        // ---- run end: a window still open is merged into the row of the run it started in ----
+        if (have && whi >= wlo && in_run > 0) c3_close_window(a, c, false, maxd, in_run, s_hist);
     }
 }
 
@@ -1339,22 +1371,27 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
 
     const bool general_only = cov_force_general();
     // ---------------- fast path: difference array in shared memory ----------------
-    Temp t_first, e_lo, e_hi, c_lo, c_hi, t_rows, t_meta, t_deep, t_drow, t_dpool;
+    static int fast_ver = 0;  // MP2_COV_TILE=1 selects the block-per-tile kernel (A/B), default = streaming warps
+    if (!fast_ver) {
+        const char *e = getenv("MP2_COV_TILE");
+        fast_ver = (e && e[0] == '1') ? 1 : 3;
+    }
+    Temp e_lo, e_hi, c_lo, c_hi, t_rows, t_meta, t_deep, t_drow, t_dpool;
     if (!general_only) {
-        const int64_t n_tiles = (n_pos + CT_TILE - 1) / CT_TILE;
-        if (n_tiles > INT32_MAX / 2) return fail(MP2_EINVAL, "too many positions in one call");
-        MP2_TRY(t_first.alloc(sizeof(int32_t) * n_tiles, stream));
-        MP2_TRY(e_lo.alloc(sizeof(int64_t) * n_tiles, stream));
-        MP2_TRY(e_hi.alloc(sizeof(int64_t) * n_tiles, stream));
-        MP2_TRY(c_lo.alloc(sizeof(int32_t) * n_tiles, stream));
-        MP2_TRY(c_hi.alloc(sizeof(int32_t) * n_tiles, stream));
-        MP2_TRY(t_rows.alloc(sizeof(uint32_t) * COV_BINS * (size_t)n_tiles, stream));
-        MP2_TRY(t_meta.alloc(sizeof(RowMeta) * n_tiles, stream));
+        const int64_t unit = fast_ver == 1 ? CT_TILE : C3_RUN;
+        const int64_t n_units = (n_pos + unit - 1) / unit;
+        if (n_units > INT32_MAX / 2) return fail(MP2_EINVAL, "too many positions in one call");
+        MP2_TRY(e_lo.alloc(sizeof(int64_t) * n_units, stream));
+        MP2_TRY(e_hi.alloc(sizeof(int64_t) * n_units, stream));
+        MP2_TRY(c_lo.alloc(sizeof(int32_t) * n_units, stream));
+        MP2_TRY(c_hi.alloc(sizeof(int32_t) * n_units, stream));
+        MP2_TRY(t_rows.alloc(sizeof(uint32_t) * COV_BINS * (size_t)n_units, stream));
+        MP2_TRY(t_meta.alloc(sizeof(RowMeta) * n_units, stream));
         MP2_TRY(t_deep.alloc(sizeof(int32_t) * n_contigs, stream));
-        MP2_CUDA(cudaMemsetAsync(t_rows.p, 0, sizeof(uint32_t) * COV_BINS * (size_t)n_tiles, stream));
-        MP2_CUDA(cudaMemsetAsync(t_meta.p, 0, sizeof(RowMeta) * n_tiles, stream));
         MP2_TRY(t_drow.alloc(sizeof(int32_t) * n_contigs, stream));
         MP2_TRY(t_dpool.alloc(sizeof(uint32_t) * (size_t)CT_DEEP_ROWS * CT_DEEP_BINS, stream));
+        MP2_CUDA(cudaMemsetAsync(t_rows.p, 0, sizeof(uint32_t) * COV_BINS * (size_t)n_units, stream));
+        MP2_CUDA(cudaMemsetAsync(t_meta.p, 0, sizeof(RowMeta) * n_units, stream));
         MP2_CUDA(cudaMemsetAsync(t_drow.p, 0xFF, sizeof(int32_t) * n_contigs, stream));
         MP2_CUDA(cudaMemsetAsync(t_dpool.p, 0, sizeof(uint32_t) * (size_t)CT_DEEP_ROWS * CT_DEEP_BINS, stream));
         if (n_events > 0 && max_span == 0) {
@@ -1363,23 +1400,22 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
                                                                      ev_first.as<int32_t>(), flags.as<unsigned int>());
         }
         MP2_CUDA(cudaGetLastError());
-        {
-            Launch L("cov_map_kernel", stream);
-            cov_map_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(off, n_contigs, CT_TILE, n_tiles,
-                                                                                t_first.as<int32_t>());
-        }
-        MP2_CUDA(cudaGetLastError());
+        const unsigned int *d_span = max_span == 0 ? flags.as<unsigned int>() + 1 : nullptr;
         {
             Launch L("cov_bounds_kernel", stream);
-            cov_bounds_kernel<<<(unsigned)((n_tiles + 127) / 128), 128, 0, stream>>>(
-                starts, ev_off, off, n_contigs, n_tiles, max_span,
-                max_span == 0 ? flags.as<unsigned int>() + 1 : nullptr, e_lo.as<int64_t>(), e_hi.as<int64_t>(),
-                c_lo.as<int32_t>(), c_hi.as<int32_t>());
+            if (fast_ver == 1)
+                cov_bounds_kernel<<<(unsigned)((n_units + 127) / 128), 128, 0, stream>>>(
+                    starts, ev_off, off, n_contigs, n_units, max_span, d_span, e_lo.as<int64_t>(), e_hi.as<int64_t>(),
+                    c_lo.as<int32_t>(), c_hi.as<int32_t>());
+            else
+                cov_bounds_run_kernel<<<(unsigned)((n_units + 127) / 128), 128, 0, stream>>>(
+                    starts, ev_off, off, n_contigs, n_units, max_span, d_span, e_lo.as<int64_t>(), e_hi.as<int64_t>(),
+                    c_lo.as<int32_t>(), c_hi.as<int32_t>(), gate);
         }
         MP2_CUDA(cudaGetLastError());
         TileArgs t;
         t.starts = starts; t.ends = ends; t.ev_off = ev_off; t.off = off;
-        t.n = n_contigs; t.n_pos = n_pos; t.n_tiles = n_tiles;
+        t.n = n_contigs; t.n_pos = n_pos; t.n_tiles = n_units;
         t.e_lo = e_lo.as<int64_t>(); t.e_hi = e_hi.as<int64_t>();
         t.c_lo = c_lo.as<int32_t>(); t.c_hi = c_hi.as<int32_t>();
         t.rows = t_rows.as<uint32_t>(); t.meta = t_meta.as<RowMeta>();
@@ -1389,32 +1425,26 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
         t.check = max_span == 0 ? flags.as<unsigned int>() : nullptr;
         t.gate_out = gate;
         t.cov = (float *)d_cov; t.cov_stride = cov_stride; t.stats = (mp2_cov_stats *)d_stats; t.tp = tp;
-        static bool attr_done = false;
-        if (!attr_done) {
-            MP2_CUDA(cudaFuncSetAttribute(cov_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
-            MP2_CUDA(cudaFuncSetAttribute(cov_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2_SMEM));
-            attr_done = true;
-        }
-        static int tile_ver = 0;  // MP2_COV_TILE=1 selects the first version of the tile kernel (A/B)
-        if (!tile_ver) {
-            const char *e = getenv("MP2_COV_TILE");
-            tile_ver = (e && e[0] == '1') ? 1 : 2;
-        }
         int occ = 0;
-        if (tile_ver == 1) {
+        if (fast_ver == 1) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                MP2_CUDA(cudaFuncSetAttribute(cov_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
+                attr_done = true;
+            }
             MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_tile_kernel, COV_THREADS, CT_SMEM));
             if (occ < 1) occ = 1;
             int64_t grid = (int64_t)num_sms() * occ;
-            if (grid > n_tiles) grid = n_tiles;
+            if (grid > n_units) grid = n_units;
             Launch L("cov_tile_kernel", stream);
             cov_tile_kernel<<<(unsigned)grid, COV_THREADS, CT_SMEM, stream>>>(t);
         } else {
-            MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_tile2_kernel, C2_THREADS, C2_SMEM));
+            MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_stream_kernel, 32, 0));
             if (occ < 1) occ = 1;
             int64_t grid = (int64_t)num_sms() * occ;
-            if (grid > n_tiles) grid = n_tiles;
-            Launch L("cov_tile_kernel", stream);
-            cov_tile2_kernel<<<(unsigned)grid, C2_THREADS, C2_SMEM, stream>>>(t);
+            if (grid > n_units) grid = n_units;
+            Launch L("cov_stream_kernel", stream);
+            cov_stream_kernel<<<(unsigned)grid, 32, 0, stream>>>(t);
         }
         MP2_CUDA(cudaGetLastError());
     }
