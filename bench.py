@@ -448,6 +448,39 @@ def main():
         L_all = float(L)
     value = L_all * args.steps / (ms * 1e-3) / 1e9
 
+    # ---- the same counts from the north-star 2-bit packed layout (codes + validity bits) ----
+    packed = None
+    try:
+        nq = (L + 63) // 64
+        d_codes = torch.empty(nq * 4, dtype=torch.int32, device=dev)
+        d_valid = torch.empty(nq * 2, dtype=torch.int32, device=dev)
+        d_counts2 = torch.empty((n, 136), dtype=torch.int32, device=dev)
+        pe0, pe1, pe2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        for _ in range(2):
+            _lib.check(lib.mp2_pack_device(bases.data_ptr(), L, d_codes.data_ptr(), d_valid.data_ptr(), stream))
+            _lib.check(lib.mp2_tnf_packed_device(d_codes.data_ptr(), d_valid.data_ptr(), d_off.data_ptr(), n, L,
+                                                 d_counts2.data_ptr(), None, None, stream))
+        torch.cuda.synchronize()
+        pe0.record()
+        for _ in range(args.steps):
+            _lib.check(lib.mp2_pack_device(bases.data_ptr(), L, d_codes.data_ptr(), d_valid.data_ptr(), stream))
+        pe1.record()
+        for _ in range(args.steps):
+            _lib.check(lib.mp2_tnf_packed_device(d_codes.data_ptr(), d_valid.data_ptr(), d_off.data_ptr(), n, L,
+                                                 d_counts2.data_ptr(), None, None, stream))
+        pe2.record()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(d_counts2, d_counts))
+        t_pack, t_cnt = pe0.elapsed_time(pe1) / args.steps, pe1.elapsed_time(pe2) / args.steps
+        pk_bytes = (L + 3) // 4 + (L + 7) // 8 + n * 560
+        packed = {"pack_ms": t_pack, "pack_gbs": (L + pk_bytes - n * 560) / (t_pack * 1e-3) / 1e9,
+                  "count_ms": t_cnt, "count_gbp_s": L / (t_cnt * 1e-3) / 1e9,
+                  "count_algorithmic_gbs": pk_bytes / (t_cnt * 1e-3) / 1e9,
+                  "counts_identical_to_ascii_path": same}
+        del d_codes, d_valid, d_counts2
+    except Exception as ex:  # noqa: BLE001 -- informative only
+        packed = {"error": str(ex)}
+
     # ---- coverage phase: S samples of device-resident alignment blocks ----
     cov_rec = None
     if args.samples > 0:
@@ -509,6 +542,7 @@ def main():
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "magpurify2_b200._composition.tnf_from_concat(out_rel=, out_gc=) -> mp2_tnf, pinned host buffers in and out"},
         "kernel_ms_per_step": comp_kernels,
+        "packed_2bit_path": packed,
         "gpu_launches": int(launches) + (cov_rec["gpu_launches"] if cov_rec else 0),
         "clocks": clocks,
     }
