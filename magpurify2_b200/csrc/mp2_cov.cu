@@ -634,6 +634,8 @@ struct TileArgs {
     uint32_t *deep_pool;        // [CT_DEEP_ROWS][CT_DEEP_BINS] counts of depths >= COV_BINS - 1
     int *deep_rows_used;
     const unsigned int *check;  // NULL, or check[0] != 0 => the precondition failed: do nothing
+    uint32_t span_host;         // max_span the bounds were computed with (vouched by the caller) ...
+    const unsigned int *span_dev;  // ... or measured on the device (then span_host is ignored)
     int *gate_out;              // set to 1 when the general path has to run instead
     float *cov;
     int64_t cov_stride;
@@ -1093,6 +1095,7 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
     const int lane = threadIdx.x;
     const uint32_t h0 = (uint32_t)__cvta_generic_to_shared(s_hist);
     const int excl = (int)a.tp.excl;
+    const uint32_t span = a.span_dev ? *a.span_dev : a.span_host;  // <= C3_S (cov_bounds_run_kernel gates otherwise)
     for (int i = lane; i < COV_BINS; i += 32) s_hist[i] = 0;
     __syncwarp();
 
@@ -1133,6 +1136,7 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
         int in_run = 0;             // window slots of c accumulated in this run
         int maxd = 0;               // largest depth of c seen in this run (warp-uniform)
         int carry = 0;              // depth just before the current window
+        bool viol = false;          // a block longer than the span the event ranges were computed with
 
         for (int k = 0; k < C3_TPR; k++) {
             const int t_lo = k * C3_W;
@@ -1157,6 +1161,7 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
                         }
                         const uint32_t en = ev < len ? ev : len;
                         const bool ok = live && sv < len && en > sv;
+                        viol |= ok && (en - sv > span);  // a vouched max_span that does not hold (checked per run)
                         const int gs = (int)((uint32_t)crel + sv), ge = (int)((uint32_t)crel + en);  // run-relative
                         // consumed now: start < t_hi (a start beyond its contig is dropped at once, like the general path)
                         const bool before = live && (sv >= len || gs < t_hi);
@@ -1165,7 +1170,7 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
                         if (ok && lane < cnt) {
                             if (gs >= t_lo) atomicAdd(&s_T[c3_phys(gs - t_lo)], 1);
                             else if (ge >= t_lo) open++;  // first window of a run: block open across run_lo
-                            if (ge >= t_lo) atomicAdd(&s_T[c3_phys(ge - t_lo)], -1);  // ge - t_lo < W + S
+                            if (ge >= t_lo && ge - t_lo < C3_W + C3_S) atomicAdd(&s_T[c3_phys(ge - t_lo)], -1);
                         }
                         e_cur += cnt;
                         if (cnt && e_cur < n_ev && e_cur >= cur.y)  // advance the warp's contig cursor
@@ -1304,6 +1309,7 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
         }
         // ---- run end: a window still open is merged into the row of the run it started in ----
         if (have && whi >= wlo && in_run > 0) c3_close_window(a, c, false, maxd, in_run, s_hist);
+        if (__any_sync(0xffffffffu, viol) && lane == 0) *a.gate_out = 1;  // unreliable ranges: general path redoes the sample
     }
 }
 
@@ -1423,6 +1429,8 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
         t.work_counter = ctrs.as<int>() + 1;
         t.deep_row_of = t_drow.as<int32_t>(); t.deep_pool = t_dpool.as<uint32_t>(); t.deep_rows_used = ctrs.as<int>() + 6;
         t.check = max_span == 0 ? flags.as<unsigned int>() : nullptr;
+        t.span_host = max_span;
+        t.span_dev = d_span;
         t.gate_out = gate;
         t.cov = (float *)d_cov; t.cov_stride = cov_stride; t.stats = (mp2_cov_stats *)d_stats; t.tp = tp;
         int occ = 0;

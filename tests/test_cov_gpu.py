@@ -202,3 +202,24 @@ def test_vouched_max_span_matches_checked(covmod):
     b = covmod.cov_from_events(st, en, ev_off, off, 75, 0.05, 0.05, max_span=span)
     c = covmod.cov_from_events(st, en, ev_off, off, 75, 0.05, 0.05, max_span=span + 5000)
     assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_wrong_vouched_span_is_caught(covmod, oracle):
+    """A caller that vouches for max_span=100 while blocks are 150 long must still get exact results
+    (the kernel notices and the general path redoes the sample)."""
+    from magpurify2_b200 import synth
+
+    lengths, mag_off, _gc = synth.mag_layout(2, seed=9, mean_bp=4e5, n_contigs=30)
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    st, en, ev_off = synth.make_events(lengths, mag_off, 0, seed=9)
+    want, _ = oracle.cov_sample(st, en, ev_off, lengths, 75, 0.05, 0.05, threads=4)
+    got = covmod.cov_from_events(st, en, ev_off, off, 75, 0.05, 0.05, max_span=100)
+    assert np.array_equal(got, want)
+    # long blocks (> 512, the streaming kernel's overflow region): general path, same integers
+    rng = np.random.default_rng(9)
+    ln = 300000
+    s = np.sort(rng.integers(0, ln - 5000, 2000)).astype(np.uint32)
+    e = (s + rng.integers(600, 5000, 2000)).astype(np.uint32)
+    want, _ = oracle.cov_sample(s, e, [0, 2000], [ln], 75, 0.05, 0.05)
+    assert np.array_equal(covmod.cov_from_events(s, e, [0, 2000], [0, ln], 75, 0.05, 0.05), want)
+    assert np.array_equal(covmod.cov_from_events(s, e, [0, 2000], [0, ln], 75, 0.05, 0.05, max_span=5000), want)
