@@ -19,6 +19,7 @@
 //                        the last contributor.  D is read exactly once (4 B/position).
 //   cov_deep_kernel      exact fallback for contigs that reach depth >= 1023 (multi-pass over
 //                        depth ranges; rare).
+#include <algorithm>
 #include <climits>
 #include <cstdlib>
 
@@ -154,8 +155,9 @@ cov_scatter_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restri
                    int64_t n_events, const int32_t *__restrict__ ev_first, int32_t *__restrict__ D,
                    int32_t *__restrict__ tile_sum, const int *__restrict__ gate) {
     if (gate && *gate == 0) return;  // fallback leg with nothing to do
-    const int64_t t0 = (int64_t)blockIdx.x * COV_EV_TILE;
-    const int64_t c_lo = ev_first[blockIdx.x];
+    for (int64_t tile = blockIdx.x; tile * COV_EV_TILE < n_events; tile += gridDim.x) {
+    const int64_t t0 = tile * COV_EV_TILE;
+    const int64_t c_lo = ev_first[tile];
     const int64_t t_last = t0 + COV_EV_TILE - 1 < n_events - 1 ? t0 + COV_EV_TILE - 1 : n_events - 1;
     __shared__ int64_t s_chi;
     if (threadIdx.x == 0) s_chi = last_le(ev_off, c_lo, n, t_last);
@@ -187,6 +189,8 @@ cov_scatter_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restri
                 atomicAdd(&tile_sum[te], -1);
             }
         }
+    }
+    __syncthreads();  // s_chi is rewritten by the next tile
     }
 }
 
@@ -1484,7 +1488,7 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     MP2_CUDA(cudaGetLastError());
     if (n_events > 0) {
         Launch L("cov_scatter_kernel", stream);
-        cov_scatter_kernel<<<(unsigned)n_ev_tiles, 256, 0, stream>>>(starts, ends, ev_off, off, n_contigs, n_events,
+        cov_scatter_kernel<<<(unsigned)std::min<int64_t>(n_ev_tiles, (int64_t)num_sms() * 16), 256, 0, stream>>>(starts, ends, ev_off, off, n_contigs, n_events,
                                                                    ev_first.as<int32_t>(), D.as<int32_t>(),
                                                                    tile_sum.as<int32_t>(), g);
     }
