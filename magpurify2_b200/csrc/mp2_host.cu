@@ -19,7 +19,7 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
                      int64_t chunk_begin, int64_t chunk_end, uint32_t *d_counts,
                      unsigned long long *d_gc_counts, cudaStream_t stream);
 int64_t tnf_num_chunks(const void *d_bases, int64_t n_bases);
-int64_t tnf_chunks_ready(const void *d_bases, int64_t done);
+int64_t tnf_chunks_ready(const void *d_bases, int64_t done, int64_t n_bases);
 int tnf_finalize(const uint32_t *d_counts, const unsigned long long *d_gc_counts,
                  const int64_t *d_offsets, int64_t n, float *d_rel, float *d_gc,
                  cudaStream_t stream);
@@ -176,7 +176,7 @@ extern "C" int mp2_tnf(const uint8_t *bases, const int64_t *offsets, int64_t n, 
     int64_t next_chunk = 0;
     auto after = [&](size_t done) -> int {
         // chunks whose bytes have all been enqueued for copy can run behind that copy
-        int64_t upto = ((int64_t)done == total) ? n_chunks : tnf_chunks_ready(d_bases.p, (int64_t)done);
+        int64_t upto = ((int64_t)done == total) ? n_chunks : tnf_chunks_ready(d_bases.p, (int64_t)done, total);
         if (upto > next_chunk) {
             MP2_CUDA(cudaEventRecord(st.ev, st.copy));
             MP2_CUDA(cudaStreamWaitEvent(st.comp, st.ev, 0));

@@ -4,14 +4,16 @@
 // (/root/reference/src/composition.rs:42-63, 67-74, 94-124, 128-132, 148-161).
 //
 // Layout in HBM: all contigs of a batch concatenated as one byte stream (1 B/base) plus
-// int64 offsets[n+1].  The stream is cut into fixed 64 KiB chunks; a chunk owns the k-mers that
-// END inside it, so work per CTA is independent of contig length (a 10 Mbp contig is just 160
-// chunks, a chunk full of tiny contigs is a loop over segments).  Per segment (= chunk ∩ contig)
-// a CTA counts into a 256-code x 32-lane shared-memory histogram: word (code, lane) lives in
-// bank `lane`, so every shared atomic issued by a warp is bank-conflict free no matter which
-// codes the lanes hit.  The flush folds the 32 lane columns with warp reductions, folds
-// 256 codes -> 136 canonical classes and adds the non-zero classes to the contig's row with
-// integer global atomics (order independent => bit exact).
+// int64 offsets[n+1].  The stream is cut into fixed 16 KiB pieces; a piece owns the k-mers that
+// END inside it, so work per warp is independent of contig length (a 10 Mbp contig is just 640
+// pieces, a piece full of tiny contigs is a loop over segments).  A warp is a CTA: per segment
+// (= piece ∩ contig) it counts into its own shared-memory table and flushes the table into the
+// contig's row with integer global reductions (order independent => bit exact).
+//
+// What bounds the kernel is the shared-memory data pipe (1 wavefront/clk/SM): a warp-wide
+// red.shared on 32 random words costs ~3.4 wavefronts (worst bank load), so the design minimises
+// wavefronts: one increment per TWO bases (5-mer table), a flush whose table reads are all
+// conflict-free LDS.128, and an interior row path without divergence (edge rows are out of line).
 #include <cstdlib>
 
 #include "mp2_common.h"
@@ -19,18 +21,25 @@
 namespace mp2 {
 
 constexpr int TNF_THREADS = 32;   // one warp per CTA: the warp's table sits at a fixed shared address
-constexpr int TNF_PIECE = 16384;  // bytes of the stream owned by one work item (one warp)
+// Bytes of the stream owned by one work item (one warp) = 1 << shift.  Every segment costs a table flush
+// and two edge rows, so large inputs use 32 KiB pieces (fewer piece-boundary segments); small inputs
+// keep 16 KiB so that there are enough pieces for all warps.  MP2_TNF_PIECE_SHIFT=14|15 overrides.
+static int tnf_piece_shift(int64_t n_bases) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("MP2_TNF_PIECE_SHIFT");
+        forced = (e && atoi(e) >= 14 && atoi(e) <= 15) ? atoi(e) : 0;
+    }
+    if (forced) return forced;
+    return n_bases >= ((int64_t)1 << 28) ? 15 : 14;
+}
 constexpr int TNF_UNROLL = 4;     // 16-byte groups in flight per lane
 
 // Table words per warp: MODE 4 counts one 4-mer per base into T4[256]; MODE 5 counts one 5-mer
 // per TWO bases into T5[1024] (a 5-mer b0..b4 stands for the 4-mers b0..b3 and b1..b4) and
 // keeps T4[256] for the odd ones out (segment edges, groups holding non-ACGT bytes).
-// MODE 7 = MODE 5 with T5 split four ways by lane group (lane>>3): entry idx of group g lives at word
-// idx*4+g, so a group only ever touches the 8 banks congruent to g mod 4 -- 8 lanes into 8 banks
-// instead of 32 into 32 (expected worst bank load 2.5 instead of 3.5) -- and the four copies of an
-// entry are one aligned 16-byte LDS.128 at flush time.
 template <int MODE> struct TnfTab {
-    static constexpr int T5W = MODE == 7 ? 4096 : (MODE == 5 ? 1024 : 0);
+    static constexpr int T5W = MODE == 5 ? 1024 : 0;
     static constexpr int WORDS = T5W + 256;
 };
 
@@ -82,12 +91,12 @@ __device__ __forceinline__ void smem_inc(uint32_t saddr) {
 }
 
 // ---- piece -> first contig map -----------------------------------------------------------
-__global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_t n, int mis,
+__global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_t n, int mis, int piece_shift,
                                      int64_t chunk_begin, int64_t n_chunks,
                                      int32_t *__restrict__ first_contig) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n_chunks) return;
-    int64_t pos = (chunk_begin + k) * TNF_PIECE - mis;  // stream position of the piece start
+    int64_t pos = ((chunk_begin + k) << piece_shift) - mis;  // stream position of the piece start
     // largest c in [0, n-1] with offsets[c] <= pos (0 if none)
     int64_t lo = 0, hi = n;  // search upper_bound over offsets[0..n)
     while (lo < hi) {
@@ -98,60 +107,95 @@ __global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_
     first_contig[k] = (int32_t)(lo > 0 ? lo - 1 : 0);
 }
 
-// Fold the warp's table into the contig's row: 256 codes -> 136 canonical classes (MODE 5: first
-// 5-mer counts -> 4-mer counts), integer global reductions, then zero the table.
-template <int MODE>
-__device__ __forceinline__ uint32_t tnf_code_count(const uint32_t *tab, uint32_t a) {
-    constexpr int T5W = TnfTab<MODE>::T5W;
-    uint32_t val = tab[T5W + a];  // T4
-    if (MODE == 5) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(tab + (a << 2));  // 5-mers a.b
-        val += q.x + q.y + q.z + q.w + tab[a] + tab[256 + a] + tab[512 + a] + tab[768 + a];  // and b.a
-    } else if (MODE == 7) {
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const uint4 q = *reinterpret_cast<const uint4 *>(tab + ((((a << 2) | b)) << 2));
-            const uint4 r = *reinterpret_cast<const uint4 *>(tab + (((b << 8) | a) << 2));
-            val += q.x + q.y + q.z + q.w + r.x + r.y + r.z + r.w;
-        }
-    }
-    return val;
-}
-
+// Fold the warp's table into the contig's row: 256 codes -> 136 canonical classes, integer global
+// reductions, then zero the table.  MODE 4: T4 is the 4-mer table already.
 template <int MODE>
 __device__ __forceinline__ void tnf_flush(uint32_t *tab, int lane, uint32_t *__restrict__ row) {
-    constexpr int WORDS = TnfTab<MODE>::WORDS;
+    static_assert(MODE == 4, "MODE 5 has its own flush");
     __syncwarp();
 #pragma unroll
     for (int k = lane; k < MP2_NCANON + 24; k += 32) {
         if (k < MP2_NCANON) {
             const uint32_t pr = c_canon_pair[k];
             const uint32_t a = pr & 0xFFu, rc = pr >> 8;
-            uint32_t val = tnf_code_count<MODE>(tab, a);
-            if (rc != a) val += tnf_code_count<MODE>(tab, rc);
+            uint32_t val = tab[a];
+            if (rc != a) val += tab[rc];
             if (val) atomicAdd(&row[k], val);
         }
     }
     __syncwarp();
-#pragma unroll
-    for (int i = 0; i < WORDS / 128; i++)
-        *reinterpret_cast<uint4 *>(tab + (i * 32 + lane) * 4) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4 *>(tab + lane * 4) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4 *>(tab + 128 + lane * 4) = make_uint4(0, 0, 0, 0);
     __syncwarp();
+}
+
+#define MP2_CSWAP(c, x, y) do { const uint32_t _t = (c) ? (y) : (x); (y) = (c) ? (x) : (y); (x) = _t; } while (0)
+
+// MODE 5 flush.  count4[c] = T4[c] + sum_b T5[c.b] + sum_b T5[b.c]; every table read below is a
+// bank-conflict-free LDS.128 (a quarter warp reads 8 distinct 16-byte bank groups):
+//   * lane L owns the codes 8L..8L+7.  Their prefix marginals are the 32 words of T5 row L = the
+//     uint4s 8L..8L+7 (one uint4 per code); all rows start in bank 0, so lane L reads them in the
+//     order j ^ (L&7).
+//   * their suffix marginals are the words b*256 + 8L..8L+7 for b = 0..3 and T4[8L..8L+7]: two
+//     uint4s each, read in the order h ^ ((L>>2)&1).
+// The two read orders leave the registers permuted by the lane number; two conditional-swap stages
+// bring the prefix sums into the order of the suffix sums, whose uint4 halves go back to the T4
+// region at the very address they came from.  The 136 classes are then gathered from T4.
+__device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__restrict__ row) {
+    const uint4 *t5v = reinterpret_cast<const uint4 *>(tab);
+    uint4 *t4v = reinterpret_cast<uint4 *>(tab + 1024);
+    const int sg = lane & 7, hx = (lane >> 2) & 1;
+    __syncwarp();
+    uint32_t P[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint4 q = t5v[8 * lane + (j ^ sg)];
+        P[j] = q.x + q.y + q.z + q.w;  // code 8L + (j ^ sg)
+    }
+    const bool s1 = sg & 1, s2 = sg & 2;
+    MP2_CSWAP(s1, P[0], P[1]); MP2_CSWAP(s1, P[2], P[3]); MP2_CSWAP(s1, P[4], P[5]); MP2_CSWAP(s1, P[6], P[7]);
+    MP2_CSWAP(s2, P[0], P[2]); MP2_CSWAP(s2, P[1], P[3]); MP2_CSWAP(s2, P[4], P[6]); MP2_CSWAP(s2, P[5], P[7]);
+    // now P[4h'+m] belongs to code 8L + 4(h' ^ hx) + m
+#pragma unroll
+    for (int hp = 0; hp < 2; hp++) {
+        const int h = hp ^ hx;
+        uint4 sum = t4v[2 * lane + h];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint4 q = t5v[b * 64 + 2 * lane + h];
+            sum.x += q.x; sum.y += q.y; sum.z += q.z; sum.w += q.w;
+        }
+        sum.x += P[4 * hp + 0]; sum.y += P[4 * hp + 1]; sum.z += P[4 * hp + 2]; sum.w += P[4 * hp + 3];
+        t4v[2 * lane + h] = sum;  // only this lane touches these words
+    }
+    __syncwarp();  // every lane is done reading T5; the 4-mer counts are visible in T4
+#pragma unroll
+    for (int i = 0; i < 8; i++) *reinterpret_cast<uint4 *>(tab + (i * 32 + lane) * 4) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = lane; k < MP2_NCANON + 24; k += 32) {
+        if (k < MP2_NCANON) {
+            const uint32_t pr = c_canon_pair[k];
+            const uint32_t a = pr & 0xFFu, rc = pr >> 8;
+            uint32_t val = tab[1024 + a];
+            if (rc != a) val += tab[1024 + rc];
+            if (val) atomicAdd(&row[k], val);
+        }
+    }
+    __syncwarp();
+    t4v[lane] = make_uint4(0, 0, 0, 0);
+    t4v[32 + lane] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+}
+template <>
+__device__ __forceinline__ void tnf_flush<5>(uint32_t *tab, int lane, uint32_t *__restrict__ row) {
+    tnf_flush5(tab, lane, row);
 }
 
 // Vector path of one group of 16 valid bases whose 3 halo bases are valid too: 8 (MODE 5) or 16
 // (MODE 4) increments.  halo = codes of the 3 bases before the group in bits 5:0.
 template <int MODE>
 __device__ __forceinline__ void tnf_count16(uint32_t cw, uint32_t halo, uint32_t t5, uint32_t t4) {
-    if (MODE == 7) {
-        // as MODE 5, entry idx of this lane's group at byte idx*16 + 4*(lane>>3); t5 already holds the group offset
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-            const int sh = 2 * (14 - j);
-            const uint32_t t = sh >= 4 ? __funnelshift_r(cw, halo, sh - 4) : (cw << 4);
-            smem_inc(t5 + (t & 0x3FF0u));
-        }
-    } else if (MODE == 5) {
+    if (MODE == 5) {
         // 5-mer ending at base j+1 (j even) = bits [2(14-j)+9 : 2(14-j)] of halo:cw; its counter is
         // word index*4 bytes into T5
 #pragma unroll
@@ -172,14 +216,21 @@ __device__ __forceinline__ void tnf_count16(uint32_t cw, uint32_t halo, uint32_t
 
 // Masked path of one group: W has bit (18-i) set when position P-3+i is a valid base of this contig
 // below seg_hi (i = 0..2 halo, 3..18 the group); own has bit (15-j) set when base j is >= seg_lo.
-// Counts single 4-mers into T4 and returns the number of G/C bases owned.
-__device__ __forceinline__ uint32_t tnf_masked16(uint32_t cw, uint32_t ph, uint32_t W, uint32_t own, uint32_t t4) {
-    const uint32_t K = W & (W >> 1) & (W >> 2) & (W >> 3) & own;  // bit (15-j): the 4-mer ENDING at base j counts
+// K gets bit (15-j) set when the 4-mer ENDING at base j counts; returns the number of G/C bases owned.
+__device__ __forceinline__ uint32_t tnf_masked_prep(uint32_t cw, uint32_t W, uint32_t own, uint32_t &K) {
+    K = W & (W >> 1) & (W >> 2) & (W >> 3) & own;
     uint32_t sp = W & own;  // spread bit b -> bit 2b
     sp = (sp | (sp << 8)) & 0x00FF00FFu;
     sp = (sp | (sp << 4)) & 0x0F0F0F0Fu;
     sp = (sp | (sp << 2)) & 0x33333333u;
     sp = (sp | (sp << 1)) & 0x55555555u;
+    return __popc((cw ^ (cw >> 1)) & sp);
+}
+
+// Counts the single 4-mers of K into T4, one lane alone (packed kernel).
+__device__ __forceinline__ uint32_t tnf_masked16(uint32_t cw, uint32_t ph, uint32_t W, uint32_t own, uint32_t t4) {
+    uint32_t K;
+    const uint32_t gcn = tnf_masked_prep(cw, W, own, K);
 #pragma unroll
     for (int b = 0; b < 16; b++) {
         if (K & (1u << b)) {
@@ -187,7 +238,7 @@ __device__ __forceinline__ uint32_t tnf_masked16(uint32_t cw, uint32_t ph, uint3
             smem_inc(t4 + (t & 0x3FCu));
         }
     }
-    return __popc((cw ^ (cw >> 1)) & sp);
+    return gcn;
 }
 
 // range masks shared by the ASCII and the packed kernels (positions relative to the piece)
@@ -204,16 +255,73 @@ __device__ __forceinline__ void tnf_range_masks(int P, int o0, int seg_lo, int s
 // Every warp (= CTA) works alone: it draws a 16 KiB piece of the stream from a global counter,
 // walks the segments (piece ∩ contig) in it, counts each segment into its own shared-memory table
 // with red.shared (ATOMS.POPC.INC: same-address lanes are merged by the hardware) and flushes
-// the table to the contig's row of `counts` with integer global reductions (order independent
-// => bit exact).  No block-level synchronisation anywhere; work per warp is independent of
-// contig length (a 10 Mbp contig is just 640 pieces, a piece full of tiny contigs is a loop).
+// the table to the contig's row of `counts`.  No block-level synchronisation anywhere.
 //
 // A lane owns 16-byte groups, interleaved across the warp so every LDG.128 is a fully coalesced
-// 512-byte request.  The 3-base halo of a group comes from the neighbouring lane by shuffle.
-// Interior groups of 16 valid bases take the vector path (MODE 5: 8 increments for 16 bases);
-// groups touching a segment edge or holding a non-ACGT byte take the masked path, which
-// computes the exact per-base validity and counts single 4-mers.
+// 512-byte request; a ROW is the 32 groups of one such request.  The 3-base halo of a group comes
+// from the neighbouring lane by shuffle.  A row whose 32 groups are all clean (16 valid bases, valid
+// halo, inside the segment) takes the vector path with no divergence at all (MODE 5: 8 increments
+// for 16 bases); any other row goes through tnf_edge_row, which is out of line so that the
+// streaming loop stays small.
+
+// The shared-memory table of the warp.  One warp per CTA => a fixed shared address.
+__shared__ __align__(16) uint32_t tnf_tab[TnfTab<5>::WORDS];
+
+// The last, partial group of the whole stream, byte by byte (bytes beyond the buffer read as 0).
+__device__ __noinline__ uint4 tnf_load_tail(const uint8_t *__restrict__ pb, int P, int safe_hi) {
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 16 && P + i < safe_hi; i++) w[i >> 2] |= (uint32_t)pb[P + i] << (8 * (i & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Row with at least one group that is not clean.  Lanes whose group is clean take the vector path;
+// the others (typically the one or two groups holding a contig end or an N) compute the exact
+// per-base validity of their group, and then the WARP counts each such group together: lane b takes
+// the 4-mer ending at base 15-b, so a masked group costs one shared-memory reduction instead of 16
+// predicated ones.  Called by the whole warp.  Returns the number of G/C bases counted for this lane.
 template <int MODE>
+__device__ __noinline__ uint32_t tnf_edge_row(uint4 v, uint32_t cw, uint32_t halo, bool fast, int g, int g_last,
+                                              int o0, int seg_lo, int seg_hi, const uint8_t *__restrict__ pb,
+                                              bool head_ok) {
+    const uint32_t t5 = (uint32_t)__cvta_generic_to_shared(tnf_tab);
+    const uint32_t t4 = t5 + 4u * TnfTab<MODE>::T5W;
+    const int lane = threadIdx.x;
+    uint32_t gcn = 0, K = 0, ph = 0;
+    if (g <= g_last) {
+        if (fast) {
+            tnf_count16<MODE>(cw, halo, t5, t4);
+            gcn = __popc((cw ^ (cw >> 1)) & 0x55555555u);
+        } else {
+            uint32_t s0, s1, s2, s3;
+            decode4_hi(v.x, s0); decode4_hi(v.y, s1); decode4_hi(v.z, s2); decode4_hi(v.w, s3);
+            const int P = g << 4;
+            uint32_t hw = 0;  // halo bytes straight from memory (positions P-4..P-1)
+            if (P >= 4 || head_ok) hw = __ldg(reinterpret_cast<const uint32_t *>(pb + P - 4));
+            uint32_t sh_;
+            ph = decode4(hw, sh_);
+            // W: bit (18-i) <-> position P-3+i is a valid base of this contig below seg_hi
+            uint32_t W = ~((bad4(sh_) & 7u) << 16 | bad4(s0) << 12 | bad4(s1) << 8 | bad4(s2) << 4 | bad4(s3)) & 0x7FFFFu;
+            if (P < 4 && !head_ok) W &= 0xFFFFu;
+            uint32_t own;
+            tnf_range_masks(P, o0, seg_lo, seg_hi, W, own);
+            gcn = tnf_masked_prep(cw, W, own, K);
+        }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, K != 0);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t cb = __shfl_sync(0xffffffffu, cw, src), hb = __shfl_sync(0xffffffffu, ph, src);
+        const uint32_t kb = __shfl_sync(0xffffffffu, K, src);
+        if ((kb >> lane) & 1u) {  // K has 16 bits: lanes 16..31 never count
+            const uint32_t t = lane ? __funnelshift_r(cb, hb, 2 * lane - 2) : (cb << 2);
+            smem_inc(t4 + (t & 0x3FCu));
+        }
+    }
+    return gcn;
+}
+
+template <int MODE, int PS>
 __global__ void __launch_bounds__(TNF_THREADS)
 tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
            const int64_t *__restrict__ offsets, int64_t n,
@@ -221,12 +329,12 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
            uint32_t *__restrict__ counts, unsigned long long *__restrict__ gc_counts,
            int *__restrict__ work_counter) {
     constexpr int WORDS = TnfTab<MODE>::WORDS;
-    __shared__ __align__(16) uint32_t tab[WORDS];
+    constexpr int TNF_PIECE = 1 << PS;
+    uint32_t *tab = tnf_tab;
 
     const int lane = threadIdx.x;
-    const uint32_t t5b = (uint32_t)__cvta_generic_to_shared(tab);  // T5 (MODE 5/7) or T4 (MODE 4)
-    const uint32_t t5 = MODE == 7 ? t5b + 4u * (threadIdx.x >> 3) : t5b;
-    const uint32_t t4 = t5b + 4u * TnfTab<MODE>::T5W;
+    const uint32_t t5 = (uint32_t)__cvta_generic_to_shared(tnf_tab);  // T5 (MODE 5) or T4 (MODE 4)
+    const uint32_t t4 = t5 + 4u * TnfTab<MODE>::T5W;
     const int src_lane = (lane + 31) & 31;
 
     for (int i = lane; i < WORDS; i += 32) tab[i] = 0;
@@ -260,6 +368,9 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
             const int in_lo = o0 + 3 > seg_lo ? o0 + 3 : seg_lo;
             const int g_in_lo = (in_lo + 15) >> 4;
             const int g_in_hi = (seg_hi >> 4) > g_in_lo ? (seg_hi >> 4) : g_in_lo;  // [g_in_lo, g_in_hi)
+            const unsigned g_in_n = (unsigned)(g_in_hi - g_in_lo);
+            // groups below this one exist and may be read whole
+            const int g_load_hi = (g_last + 1) < (safe_hi >> 4) ? (g_last + 1) : (safe_hi >> 4);
             // packed halo (last 3 codes | bit 8 "not usable") of the group before g_first, kept by
             // lane 31: the piece's first group of a long contig then takes the vector path too
             uint32_t carry = 0x100u;
@@ -270,56 +381,46 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
             }
             for (int g0 = g_first; g0 <= g_last; g0 += 32 * TNF_UNROLL) {
                 uint4 v[TNF_UNROLL];
+                if (g0 + 32 * TNF_UNROLL <= g_load_hi) {  // warp-uniform: the whole tile can be loaded blindly
 #pragma unroll
-                for (int u = 0; u < TNF_UNROLL; u++) {
-                    const int P = (g0 + 32 * u + lane) << 4;
-                    v[u] = make_uint4(0, 0, 0, 0);
-                    if (g0 + 32 * u + lane <= g_last) {
-                        if (P + 16 <= safe_hi) {
+                    for (int u = 0; u < TNF_UNROLL; u++)
+                        v[u] = __ldg(reinterpret_cast<const uint4 *>(pb + ((g0 + 32 * u + lane) << 4)));
+                } else {
+#pragma unroll
+                    for (int u = 0; u < TNF_UNROLL; u++) {
+                        const int g = g0 + 32 * u + lane;
+                        const int P = g << 4;
+                        v[u] = make_uint4(0, 0, 0, 0);
+                        if (g < g_load_hi) {
                             v[u] = __ldg(reinterpret_cast<const uint4 *>(pb + P));
-                        } else {  // last group of the whole stream: never read past the buffer
-                            uint32_t w[4] = {0, 0, 0, 0};
-                            for (int i = 0; i < 16 && P + i < safe_hi; i++)
-                                w[i >> 2] |= (uint32_t)pb[P + i] << (8 * (i & 3));
-                            v[u] = make_uint4(w[0], w[1], w[2], w[3]);
+                        } else if (g <= g_last) {  // last group of the whole stream: never read past the buffer
+                            v[u] = tnf_load_tail(pb, P, safe_hi);
                         }
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < TNF_UNROLL; u++) {
-                    const int g = g0 + 32 * u + lane;
                     if (g0 + 32 * u > g_last) break;  // warp-uniform
+                    const int g = g0 + 32 * u + lane;
                     uint32_t s0, s1, s2, s3;
                     const uint32_t m0 = decode4_hi(v[u].x, s0), m1 = decode4_hi(v[u].y, s1);
                     const uint32_t m2 = decode4_hi(v[u].z, s2), m3 = decode4_hi(v[u].w, s3);
                     // cw = top bytes of m0..m3, first base most significant
                     const uint32_t cw = __byte_perm(__byte_perm(m3, m2, 0x0073), __byte_perm(m1, m0, 0x0073), 0x5410);
-                    // all four signatures equal to 0x41414141 <=> 16 valid bases
-                    const bool clean = (((s0 ^ s1) | (s2 ^ s3) | (s0 ^ s2)) == 0) && (s0 == 0x41414141u) &&
-                                       (g <= g_last);
+                    // all four signatures equal to 0x41414141 <=> 16 valid bases (a group beyond g_last
+                    // was loaded as zeros and is never clean)
+                    const bool clean = (((s0 ^ s1) | (s2 ^ s3) | (s0 ^ s2)) == 0) && (s0 == 0x41414141u);
                     // halo = last 3 codes of the previous group + bit 8 "not usable"
                     const uint32_t mine = (cw & 0x3Fu) | (clean ? 0u : 0x100u);
                     const uint32_t give = lane == 31 ? carry : mine;
                     const uint32_t halo = __shfl_sync(0xffffffffu, give, src_lane);
                     carry = mine;  // only lane 31's copy is ever consumed
-                    if (g > g_last) continue;
-                    const bool fast = clean && (halo < 0x100u) && ((unsigned)(g - g_in_lo) < (unsigned)(g_in_hi - g_in_lo));
-                    if (fast) {
+                    const bool fast = clean && (halo < 0x100u) && ((unsigned)(g - g_in_lo) < g_in_n);
+                    if (__all_sync(0xffffffffu, fast)) {
                         gcl += __popc((cw ^ (cw >> 1)) & 0x55555555u);
                         tnf_count16<MODE>(cw, halo, t5, t4);
                     } else {
-                        // ---- masked path: exact per-base validity, single 4-mers into T4 ----
-                        const int P = g << 4;
-                        uint32_t hw = 0;  // halo bytes straight from memory (positions P-4..P-1)
-                        if (P >= 4 || head_ok) hw = __ldg(reinterpret_cast<const uint32_t *>(pb + P - 4));
-                        uint32_t sh_;
-                        const uint32_t ph = decode4(hw, sh_);
-                        // W: bit (18-i) <-> position P-3+i is a valid base of this contig below seg_hi
-                        uint32_t W = ~((bad4(sh_) & 7u) << 16 | bad4(s0) << 12 | bad4(s1) << 8 | bad4(s2) << 4 | bad4(s3)) & 0x7FFFFu;
-                        if (P < 4 && !head_ok) W &= 0xFFFFu;
-                        uint32_t own;
-                        tnf_range_masks(P, o0, seg_lo, seg_hi, W, own);
-                        gcl += tnf_masked16(cw, ph, W, own, t4);
+                        gcl += tnf_edge_row<MODE>(v[u], cw, halo, fast, g, g_last, o0, seg_lo, seg_hi, pb, head_ok);
                     }
                 }
             }
@@ -335,18 +436,18 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
 // most significant (0 = any non-ACGT byte).  Same piece / segment / table scheme as tnf_kernel; a
 // lane owns QUADS (4 consecutive groups = 64 bases: one 128-bit load of codes + one 64-bit load of
 // validity), so the halo of groups 1..3 is already in registers and one shuffle serves 64 bases.
-template <int MODE>
+template <int MODE, int PS>
 __global__ void __launch_bounds__(TNF_THREADS)
 tnf_packed_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ valid, int64_t n_bases,
                   const int64_t *__restrict__ offsets, int64_t n, const int32_t *__restrict__ first_contig,
                   int64_t n_chunks, uint32_t *__restrict__ counts, unsigned long long *__restrict__ gc_counts,
                   int *__restrict__ work_counter) {
     constexpr int WORDS = TnfTab<MODE>::WORDS;
-    __shared__ __align__(16) uint32_t tab[WORDS];
+    constexpr int TNF_PIECE = 1 << PS;
+    uint32_t *tab = tnf_tab;
     const int lane = threadIdx.x;
-    const uint32_t t5b = (uint32_t)__cvta_generic_to_shared(tab);
-    const uint32_t t5 = MODE == 7 ? t5b + 4u * (threadIdx.x >> 3) : t5b;
-    const uint32_t t4 = t5b + 4u * TnfTab<MODE>::T5W;
+    const uint32_t t5 = (uint32_t)__cvta_generic_to_shared(tnf_tab);
+    const uint32_t t4 = t5 + 4u * TnfTab<MODE>::T5W;
     const int src_lane = (lane + 31) & 31;
     for (int i = lane; i < WORDS; i += 32) tab[i] = 0;
     __syncwarp();
@@ -520,7 +621,7 @@ static int tnf_mode() {
     static int mode = 0;
     if (!mode) {
         const char *e = getenv("MP2_TNF_MODE");
-        mode = (e && e[0] == '4') ? 4 : ((e && e[0] == '7') ? 7 : 5);
+        mode = (e && e[0] == '4') ? 4 : 5;
     }
     return mode;
 }
@@ -534,6 +635,7 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
     const int mis = (int)(reinterpret_cast<uintptr_t>(d_bases) & 15);
     const int64_t n_chunks = chunk_end - chunk_begin;
     if (n_chunks <= 0) return MP2_OK;
+    const int ps = tnf_piece_shift(n_bases);
     Temp map, ctr;
     MP2_TRY(map.alloc(sizeof(int32_t) * n_chunks, stream));
     MP2_TRY(ctr.alloc(sizeof(int), stream));
@@ -541,39 +643,41 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
     {
         Launch L("tnf_chunk_map_kernel", stream);
         tnf_chunk_map_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, stream>>>(
-            d_offsets, n, mis, chunk_begin, n_chunks, map.as<int32_t>());
+            d_offsets, n, mis, ps, chunk_begin, n_chunks, map.as<int32_t>());
     }
     MP2_CUDA(cudaGetLastError());
     const int mode = tnf_mode();
-#define MP2_TNF_LAUNCH(M)                                                                                   \
+#define MP2_TNF_LAUNCH(M, PS)                                                                               \
     do {                                                                                                    \
         int occ = 0;                                                                                        \
-        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_kernel<M>, TNF_THREADS, 0));       \
+        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_kernel<M, PS>, TNF_THREADS, 0));   \
         if (occ < 1) occ = 1;                                                                               \
         int64_t grid = (int64_t)num_sms() * occ;                                                            \
         if (grid > n_chunks) grid = n_chunks;                                                               \
         Launch L("tnf_kernel", stream);                                                                     \
-        tnf_kernel<M><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(                                          \
+        tnf_kernel<M, PS><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(                                      \
             d_bases - mis, mis, n_bases + mis, d_offsets, n, map.as<int32_t>(), chunk_begin, n_chunks,     \
             d_counts, d_gc_counts, ctr.as<int>());                                                          \
     } while (0)
-    if (mode == 7) MP2_TNF_LAUNCH(7);
-    else if (mode == 5) MP2_TNF_LAUNCH(5);
-    else MP2_TNF_LAUNCH(4);
+    if (mode == 5 && ps == 15) MP2_TNF_LAUNCH(5, 15);
+    else if (mode == 5) MP2_TNF_LAUNCH(5, 14);
+    else if (ps == 15) MP2_TNF_LAUNCH(4, 15);
+    else MP2_TNF_LAUNCH(4, 14);
 #undef MP2_TNF_LAUNCH
     MP2_CUDA(cudaGetLastError());
     return MP2_OK;
 }
 
 // Pieces wholly inside the first `done` bytes of the stream (host staging pipelines on this).
-int64_t tnf_chunks_ready(const void *d_bases, int64_t done) {
+int64_t tnf_chunks_ready(const void *d_bases, int64_t done, int64_t n_bases) {
     const int mis = (int)(reinterpret_cast<uintptr_t>(d_bases) & 15);
-    return (done + mis) / TNF_PIECE;
+    return (done + mis) >> tnf_piece_shift(n_bases);
 }
 
 int64_t tnf_num_chunks(const void *d_bases, int64_t n_bases) {
     const int mis = (int)(reinterpret_cast<uintptr_t>(d_bases) & 15);
-    return (n_bases + mis + TNF_PIECE - 1) / TNF_PIECE;
+    const int ps = tnf_piece_shift(n_bases);
+    return (n_bases + mis + ((int64_t)1 << ps) - 1) >> ps;
 }
 
 int tnf_finalize(const uint32_t *d_counts, const unsigned long long *d_gc_counts,
@@ -660,7 +764,8 @@ extern "C" int mp2_tnf_packed_device(const void *d_codes, const void *d_valid, c
     MP2_TRY(gcc.alloc(sizeof(unsigned long long) * n, stream));
     MP2_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * MP2_NCANON * n, stream));
     MP2_CUDA(cudaMemsetAsync(gcc.p, 0, sizeof(unsigned long long) * n, stream));
-    const int64_t n_chunks = (n_bases + TNF_PIECE - 1) / TNF_PIECE;
+    const int ps = tnf_piece_shift(n_bases);
+    const int64_t n_chunks = (n_bases + ((int64_t)1 << ps) - 1) >> ps;
     if (n_chunks > 0) {
         MP2_TRY(map.alloc(sizeof(int32_t) * n_chunks, stream));
         MP2_TRY(ctr.alloc(sizeof(int), stream));
@@ -668,25 +773,26 @@ extern "C" int mp2_tnf_packed_device(const void *d_codes, const void *d_valid, c
         {
             Launch L("tnf_chunk_map_kernel", stream);
             tnf_chunk_map_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, stream>>>(
-                (const int64_t *)d_offsets, n, 0, 0, n_chunks, map.as<int32_t>());
+                (const int64_t *)d_offsets, n, 0, ps, 0, n_chunks, map.as<int32_t>());
         }
         MP2_CUDA(cudaGetLastError());
         const int mode = tnf_mode();
-#define MP2_TNFP_LAUNCH(M)                                                                                      \
+#define MP2_TNFP_LAUNCH(M, PS)                                                                                  \
     do {                                                                                                        \
         int occ = 0;                                                                                            \
-        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_packed_kernel<M>, TNF_THREADS, 0));    \
+        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_packed_kernel<M, PS>, TNF_THREADS, 0));\
         if (occ < 1) occ = 1;                                                                                   \
         int64_t grid = (int64_t)num_sms() * occ;                                                                \
         if (grid > n_chunks) grid = n_chunks;                                                                   \
         Launch L("tnf_packed_kernel", stream);                                                                  \
-        tnf_packed_kernel<M><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(                                       \
+        tnf_packed_kernel<M, PS><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(                                   \
             (const uint32_t *)d_codes, (const uint32_t *)d_valid, n_bases, (const int64_t *)d_offsets, n,       \
             map.as<int32_t>(), n_chunks, (uint32_t *)d_counts, gcc.as<unsigned long long>(), ctr.as<int>());    \
     } while (0)
-        if (mode == 7) MP2_TNFP_LAUNCH(7);
-        else if (mode == 5) MP2_TNFP_LAUNCH(5);
-        else MP2_TNFP_LAUNCH(4);
+        if (mode == 5 && ps == 15) MP2_TNFP_LAUNCH(5, 15);
+        else if (mode == 5) MP2_TNFP_LAUNCH(5, 14);
+        else if (ps == 15) MP2_TNFP_LAUNCH(4, 15);
+        else MP2_TNFP_LAUNCH(4, 14);
 #undef MP2_TNFP_LAUNCH
         MP2_CUDA(cudaGetLastError());
     }
