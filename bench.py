@@ -202,17 +202,32 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     peak, peak_src = peaks()
     per_launch = lambda k: kern[k][0] / max(1, kern[k][1])
     R_avg = R_total / S
+    # Roofline of the coverage kernel.  `achieved` follows SURVEY.md §8(d): algorithmic bytes of one sample
+    # (8 B/base for the int32 difference array written and read once + 20 B/read for the event and its two
+    # updates) over the kernel time.  cov_stream_kernel keeps the difference array in shared memory, so the
+    # bytes it actually has to move (`moved_*`: events once + bounds + results) are ~7x fewer; both are given.
+    sample_bytes = 8.0 * L + 20.0 * R_avg
+    moved = {"cov_stream_kernel": 8.0 * R_avg + 24.0 * (L / 65536.0) + 4.0 * n,
+             "cov_tile_kernel": 8.0 * R_avg + 24.0 * (L / 16384.0) + 4.0 * n,
+             "cov_depth_kernel": 4.0 * (L + 1), "cov_scatter_kernel": 8.0 * R_avg + 8.0 * R_avg}
+    sample_ms = ms / args.steps / S
     rl = []
-    for name, bytes_ in (("cov_stream_kernel", 8.0 * R_avg + 24.0 * (L / 65536.0) + 4.0 * n),
-                         ("cov_tile_kernel", 8.0 * R_avg + 24.0 * (L / 16384.0) + 4.0 * n),
-                         ("cov_depth_kernel", 4.0 * (L + 1)), ("cov_scatter_kernel", 8.0 * R_avg + 8.0 * R_avg)):
+    for name in ("cov_stream_kernel", "cov_tile_kernel", "cov_depth_kernel", "cov_scatter_kernel"):
         t_ms = per_launch(name)
-        ach = bytes_ / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
-        rl.append({"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                   "frac": ach / peak,
-                   "traffic": ncu_traffic(name) if (args.mags == 1000 and args.depth_scale == 1.0) else None,
-                   "algorithmic_bytes_per_launch": bytes_,
-                   "kernel_ms": t_ms, "launches_timed": kern[name][1]})
+        if t_ms < 0.02 * sample_ms:  # not launched, or gated off (exits at once): not on the path of this run
+            continue
+        fused = name in ("cov_stream_kernel", "cov_tile_kernel")  # one kernel does the whole sample
+        bytes_ = sample_bytes if fused else moved[name]
+        ach = bytes_ / (t_ms * 1e-3) / 1e9
+        r = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+             "traffic": ncu_traffic(name) if (args.mags == 1000 and args.depth_scale == 1.0) else None,
+             "algorithmic_bytes_per_launch": bytes_, "kernel_ms": t_ms, "launches_timed": kern[name][1]}
+        if fused:
+            r["algorithmic_bytes"] = "SURVEY 8(d): 8*L + 20*R per sample"
+            r["moved_bytes_per_launch"] = moved[name]
+            r["moved_gbs"] = moved[name] / (t_ms * 1e-3) / 1e9
+            r["moved_frac_of_peak"] = r["moved_gbs"] / peak
+        rl.append(r)
     dom = max(rl, key=lambda r: r["kernel_ms"])
     rec = {
         "metric": "aligned reads/s coverage", "value": value, "unit": "reads/s", "ms_per_step": ms / args.steps,
@@ -220,8 +235,8 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
                    "samples": S, "reads_per_step": R_total, "positions": L, "trim": args.trim, "end_exclusion": 75,
                    "input": "(start,end) uint32 pairs grouped by contig, resident in HBM"},
         "roofline": dict(dom, peak_source=peak_src), "kernels": rl,
-        "sample_bytes_algorithmic": 8.0 * L + 20.0 * R_avg,
-        "sample_gbs": (8.0 * L + 20.0 * R_avg) / (ms / args.steps / S * 1e-3) / 1e9,
+        "sample_bytes_algorithmic": sample_bytes,
+        "sample_gbs": sample_bytes / (sample_ms * 1e-3) / 1e9,
         "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": 8 * R0 + 16 * (n + 1),
                 "d2h_bytes_per_step": 4 * n, "steps": 1,
                 "api": "magpurify2_b200._coverage.cov_from_events (mp2_cov_events, pinned host buffers, 1 sample)"},
@@ -231,7 +246,7 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     if not args.no_cpu:
         import oracle
 
-        m = min(args.mags, max(1, args.ref_mags // 5))
+        m = min(args.mags, max(1, args.ref_mags))
         c1 = int(mag_off[m])
         e1_ = int(h_eo[c1])
         t0 = time.perf_counter()
@@ -279,7 +294,7 @@ def run_reference(args):
     # are processed one after the other; events are already decoded here
     cov_rec = None
     if args.samples > 0:
-        m = max(1, n_mags // 5)
+        m = max(1, n_mags // 2)
         c1 = int(d["mag_off"][m])
         st, en, eo = synth.make_events(d["lengths"][:c1], d["mag_off"][:m + 1], 0, seed=args.seed,
                                        depth_scale=args.depth_scale)
@@ -336,7 +351,7 @@ def main():
     ap.add_argument("--samples", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-mags", type=int, default=100, help="MAGs per step of the CPU arms")
+    ap.add_argument("--ref-mags", type=int, default=300, help="MAGs per step of the CPU arms")
     ap.add_argument("--long-contigs", action="store_true", help="C5 shape instead of C3")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--trim", type=float, default=0.05)
