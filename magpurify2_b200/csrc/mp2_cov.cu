@@ -48,6 +48,17 @@ __device__ __forceinline__ void smem_inc(uint32_t saddr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory");
 }
 
+__device__ __forceinline__ void smem_add(uint32_t saddr, int v) {
+    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+// A shared-window address the compiler cannot see through: a plain cvta result is rematerialised at every use
+// (S2UR SR_CgaCtaId + UMOV + ULEA, and the ULEA waits on the S2UR), this one stays in a register.
+__device__ __forceinline__ uint32_t smem_base_opaque(const void *p) {
+    uint32_t r = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("mov.u32 %0, %0;" : "+r"(r));
+    return r;
+}
+
 // predicated form: no branch around the reduction
 __device__ __forceinline__ void smem_inc_if(uint32_t saddr, uint32_t cond) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(saddr), "r"(cond) : "memory");
@@ -1006,6 +1017,10 @@ constexpr int C3_RUN = 65536;                // slots per run
 constexpr int C3_TPR = C3_RUN / C3_W;        // 32 windows per run
 constexpr int C3_WORDS = (C3_W + C3_S) + 4 * ((C3_W + C3_S) / 64);  // 4 pad words per 64 slots
 constexpr int C3_HEAD = C3_S + 4 * (C3_S / 64);                     // words of the overflow region
+#ifndef MP2_C3_PF
+#define MP2_C3_PF 384
+#endif
+constexpr int C3_PF = MP2_C3_PF;             // events ahead of e_cur that are prefetched into L2
 
 __device__ __forceinline__ int c3_phys(int i) { return i + 4 * (i >> 6); }
 
@@ -1097,7 +1112,7 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
     }
     if (*((volatile int *)a.gate_out)) return;
     const int lane = threadIdx.x;
-    const uint32_t h0 = (uint32_t)__cvta_generic_to_shared(s_hist);
+    const uint32_t h0 = smem_base_opaque(s_hist), sT0 = smem_base_opaque(s_T);
     const int excl = (int)a.tp.excl;
     const uint32_t span = a.span_dev ? *a.span_dev : a.span_host;  // <= C3_S (cov_bounds_run_kernel gates otherwise)
     for (int i = lane; i < COV_BINS; i += 32) s_hist[i] = 0;
@@ -1172,9 +1187,9 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
                         const unsigned nb = ~__ballot_sync(0xffffffffu, before);
                         const int cnt = nb ? __ffs(nb) - 1 : 32;  // leading lanes only (starts are sorted)
                         if (ok && lane < cnt) {
-                            if (gs >= t_lo) atomicAdd(&s_T[c3_phys(gs - t_lo)], 1);
+                            if (gs >= t_lo) smem_inc(sT0 + 4u * (uint32_t)c3_phys(gs - t_lo));
                             else if (ge >= t_lo) open++;  // first window of a run: block open across run_lo
-                            if (ge >= t_lo && ge - t_lo < C3_W + C3_S) atomicAdd(&s_T[c3_phys(ge - t_lo)], -1);
+                            if (ge >= t_lo && ge - t_lo < C3_W + C3_S) smem_add(sT0 + 4u * (uint32_t)c3_phys(ge - t_lo), -1);
                         }
                         e_cur += cnt;
                         if (cnt && e_cur < n_ev && e_cur >= cur.y)  // advance the warp's contig cursor
@@ -1186,6 +1201,15 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) { cs[j] = ns[j]; ce[j] = ne[j]; }
                     C3_LOAD_GROUP(ns, ne, e_cur + 128);
+                    // and pull the group three ahead into L2 (no register, no scoreboard): lanes 0-3 touch the
+                    // four 128-byte lines of its starts, lanes 4-7 those of its ends
+                    if (lane < 8) {
+                        const int i_ = e_cur + C3_PF + 32 * (lane & 3);
+                        if (i_ < n_ev) {
+                            const uint32_t *p_ = (lane < 4 ? ev_s : ev_e) + i_;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p_));
+                        }
+                    }
                 } else {         // window done: restart at the first unconsumed event; loads overlap the scan below
                     C3_LOAD_GROUP(cs, ce, e_cur);
                     C3_LOAD_GROUP(ns, ne, e_cur + 128);

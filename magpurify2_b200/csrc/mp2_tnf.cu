@@ -333,7 +333,9 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
     uint32_t *tab = tnf_tab;
 
     const int lane = threadIdx.x;
-    const uint32_t t5 = (uint32_t)__cvta_generic_to_shared(tnf_tab);  // T5 (MODE 5) or T4 (MODE 4)
+    // opaque to the compiler: a plain cvta result is rematerialised per row (S2UR SR_CgaCtaId + UMOV + ULEA)
+    uint32_t t5 = (uint32_t)__cvta_generic_to_shared(tnf_tab);  // T5 (MODE 5) or T4 (MODE 4)
+    asm volatile("mov.u32 %0, %0;" : "+r"(t5));
     const uint32_t t4 = t5 + 4u * TnfTab<MODE>::T5W;
     const int src_lane = (lane + 31) & 31;
 
@@ -446,7 +448,8 @@ tnf_packed_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict
     constexpr int TNF_PIECE = 1 << PS;
     uint32_t *tab = tnf_tab;
     const int lane = threadIdx.x;
-    const uint32_t t5 = (uint32_t)__cvta_generic_to_shared(tnf_tab);
+    uint32_t t5 = (uint32_t)__cvta_generic_to_shared(tnf_tab);
+    asm volatile("mov.u32 %0, %0;" : "+r"(t5));  // opaque: not rematerialised per use (see tnf_kernel)
     const uint32_t t4 = t5 + 4u * TnfTab<MODE>::T5W;
     const int src_lane = (lane + 31) & 31;
     for (int i = lane; i < WORDS; i += 32) tab[i] = 0;
