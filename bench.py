@@ -446,8 +446,8 @@ def main():
     k_ms, k_n = C.c_double(0), C.c_int64(0)
     lib.mp2_profile_read(b"tnf_kernel", C.byref(k_ms), C.byref(k_n))
     comp_kernels = {}
-    for name in ("tnf_kernel", "tnf_chunk_map_kernel", "tnf_rel_kernel", "tnf_gc_kernel", "clr_rowmean_kernel",
-                 "clr_centroid_kernel", "clr_dist_kernel", "wmedian_kernel", "logratio_kernel"):
+    for name in ("tnf_kernel", "tnf_chunk_map_kernel", "tnf_rel_kernel", "tnf_gc_kernel", "clr_mag_kernel",
+                 "wmedian_kernel", "logratio_kernel"):
         a_ms, a_n = C.c_double(0), C.c_int64(0)
         lib.mp2_profile_read(name.encode(), C.byref(a_ms), C.byref(a_n))
         comp_kernels[name] = round(a_ms.value / args.steps, 4)

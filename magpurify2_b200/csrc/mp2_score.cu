@@ -236,69 +236,99 @@ static int ensure_log_lut(cudaStream_t stream) {
 }
 
 // ---- CLR + centroid distance (self-specified: the reference has no such code) -----------------
-// clr_ij = ln(c_ij + 1) - mean_j ln(c_ij + 1); centroid_j = sum_i len_i clr_ij / sum_i len_i;
+// clr_ij = ln(c_ij + 1) - rm_i, rm_i = mean_j ln(c_ij + 1); centroid_j = sum_i len_i clr_ij / sum_i len_i;
 // d_i = ||clr_i - centroid||_2.  f64 throughout.
-__global__ void clr_rowmean_kernel(const uint32_t *__restrict__ counts, int64_t n_rows, double *__restrict__ rowmean) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (r >= n_rows) return;
-    double s = 0.0;
-    for (int j = lane; j < MP2_NCANON; j += 32) s += ln1p_count(counts[r * MP2_NCANON + j]);
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) rowmean[r] = s / (double)MP2_NCANON;
-}
+//
+// One CTA per MAG, two passes over the MAG's count rows (the second one hits L2):
+//   1. column-parallel: A_j = sum_i len_i ln(c_ij + 1) over 7 row slices x 136 columns, four independent
+//      rows in flight per thread (the chain count -> table -> FMA is latency bound).  The row means are not
+//      needed here: sum_i len_i rm_i = mean_j A_j, so centroid_j = (A_j - mean_j A_j) / sum_i len_i.
+//   2. row-parallel: a warp per row computes rm_i (lane partial sums + xor butterfly), the CLR row and its
+//      distance to the centroid held in shared memory.
+constexpr int CLRM_THREADS = 1024;
+constexpr int CLRM_SLICES = 7;  // 7 x 136 = 952 column threads
 
-constexpr int CEN_SLICES = 6;  // row slices per MAG summed in parallel, then combined in slice order
-
-__global__ void __launch_bounds__(160 * CEN_SLICES)
-clr_centroid_kernel(const uint32_t *__restrict__ counts, const long long *__restrict__ weights,
-                    const long long *__restrict__ mag_off, const double *__restrict__ rowmean,
-                    double *__restrict__ centroid /*[n_mags,136]*/) {
-    __shared__ double s_acc[CEN_SLICES][160];
-    __shared__ double s_w[CEN_SLICES];
+__global__ void __launch_bounds__(CLRM_THREADS)
+clr_mag_kernel(const uint32_t *__restrict__ counts, const long long *__restrict__ weights,
+               const long long *__restrict__ mag_off, float *__restrict__ clr, double *__restrict__ dist) {
+    __shared__ double s_part[CLRM_SLICES][MP2_NCANON];
+    __shared__ double s_w[CLRM_SLICES];
+    __shared__ double s_cen[MP2_NCANON];
+    __shared__ double s_mean_a, s_wsum;
     const int64_t m = blockIdx.x;
-    const int j = threadIdx.x % 160, g = threadIdx.x / 160;
-    double acc = 0.0, wsum = 0.0;
-    if (j < MP2_NCANON) {
-        for (int64_t r = mag_off[m] + g; r < mag_off[m + 1]; r += CEN_SLICES) {
-            const double w = (double)weights[r];
-            acc += w * (ln1p_count(counts[r * MP2_NCANON + j]) - rowmean[r]);
-            wsum += w;
+    const int64_t r0 = mag_off[m], r1 = mag_off[m + 1];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int64_t S = CLRM_SLICES;
+    if (t < CLRM_SLICES * MP2_NCANON) {
+        const int j = t % MP2_NCANON, g = t / MP2_NCANON;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, ws = 0.0;
+        int64_t r = r0 + g;
+        for (; r + 3 * S < r1; r += 4 * S) {
+            const uint32_t c0 = counts[r * MP2_NCANON + j], c1 = counts[(r + S) * MP2_NCANON + j];
+            const uint32_t c2 = counts[(r + 2 * S) * MP2_NCANON + j], c3 = counts[(r + 3 * S) * MP2_NCANON + j];
+            const double w0 = (double)weights[r], w1 = (double)weights[r + S];
+            const double w2 = (double)weights[r + 2 * S], w3 = (double)weights[r + 3 * S];
+            a0 += w0 * ln1p_count(c0);
+            a1 += w1 * ln1p_count(c1);
+            a2 += w2 * ln1p_count(c2);
+            a3 += w3 * ln1p_count(c3);
+            ws += (w0 + w1) + (w2 + w3);  // integers below 2^53: exact in any order
+        }
+        for (; r < r1; r += S) {
+            const double w0 = (double)weights[r];
+            a0 += w0 * ln1p_count(counts[r * MP2_NCANON + j]);
+            ws += w0;
+        }
+        s_part[g][j] = (a0 + a1) + (a2 + a3);
+        if (j == 0) s_w[g] = ws;
+    }
+    __syncthreads();
+    if (t < MP2_NCANON) {
+        double a = 0.0;
+        for (int k = 0; k < CLRM_SLICES; k++) a += s_part[k][t];
+        s_part[0][t] = a;  // only thread t reads column t of the other slices
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double sa = 0.0;
+        for (int j = lane; j < MP2_NCANON; j += 32) sa += s_part[0][j];
+        for (int o = 16; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        if (lane == 0) {
+            double w = 0.0;
+            for (int k = 0; k < CLRM_SLICES; k++) w += s_w[k];
+            s_mean_a = sa / (double)MP2_NCANON;
+            s_wsum = w;
         }
     }
-    s_acc[g][j] = acc;
-    if (j == 0) s_w[g] = wsum;
     __syncthreads();
-    if (g == 0 && j < MP2_NCANON) {
-        double a2 = 0.0, w2 = 0.0;
-        for (int k = 0; k < CEN_SLICES; k++) { a2 += s_acc[k][j]; w2 += s_w[k]; }
-        centroid[m * MP2_NCANON + j] = w2 > 0.0 ? a2 / w2 : 0.0;
+    if (t < MP2_NCANON) s_cen[t] = s_wsum > 0.0 ? (s_part[0][t] - s_mean_a) / s_wsum : 0.0;
+    __syncthreads();
+    for (int64_t r = r0 + warp; r < r1; r += CLRM_THREADS / 32) {
+        double v[5];
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const int j = lane + 32 * k;
+            v[k] = j < MP2_NCANON ? ln1p_count(counts[r * MP2_NCANON + j]) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) s += v[k];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const double rm = s / (double)MP2_NCANON;
+        double d2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const int j = lane + 32 * k;
+            if (j < MP2_NCANON) {
+                const double x = v[k] - rm;
+                if (clr) clr[r * MP2_NCANON + j] = (float)x;
+                const double d = x - s_cen[j];
+                d2 += d * d;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        if (lane == 0) dist[r] = sqrt(d2);
     }
-}
-
-__global__ void clr_dist_kernel(const uint32_t *__restrict__ counts, const long long *__restrict__ mag_off,
-                                int64_t n_mags, int64_t n_rows, const double *__restrict__ rowmean,
-                                const double *__restrict__ centroid, float *__restrict__ clr,
-                                double *__restrict__ dist) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (r >= n_rows) return;
-    int64_t lo = 0, hi = n_mags;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (mag_off[mid] <= r) lo = mid + 1;
-        else hi = mid;
-    }
-    const int64_t m = lo - 1;
-    double d2 = 0.0;
-    for (int j = lane; j < MP2_NCANON; j += 32) {
-        const double v = ln1p_count(counts[r * MP2_NCANON + j]) - rowmean[r];
-        if (clr) clr[r * MP2_NCANON + j] = (float)v;
-        const double d = v - centroid[m * MP2_NCANON + j];
-        d2 += d * d;
-    }
-    for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-    if (lane == 0) dist[r] = sqrt(d2);
 }
 
 }  // namespace mp2
@@ -378,27 +408,12 @@ extern "C" int mp2_clr_centroid_device(const void *d_counts, const void *d_weigh
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_rows == 0 || n_mags == 0) return MP2_OK;
     MP2_TRY(ensure_log_lut(stream));
-    Temp rowmean, centroid;
-    MP2_TRY(rowmean.alloc(sizeof(double) * n_rows, stream));
-    MP2_TRY(centroid.alloc(sizeof(double) * MP2_NCANON * n_mags, stream));
+    (void)n_rows;
     {
-        Launch L("clr_rowmean_kernel", stream);
-        clr_rowmean_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, stream>>>(
-            (const uint32_t *)d_counts, n_rows, rowmean.as<double>());
-    }
-    MP2_CUDA(cudaGetLastError());
-    {
-        Launch L("clr_centroid_kernel", stream);
-        clr_centroid_kernel<<<(unsigned)n_mags, 160 * CEN_SLICES, 0, stream>>>(
-            (const uint32_t *)d_counts, (const long long *)d_weights, (const long long *)d_mag_off,
-            rowmean.as<double>(), centroid.as<double>());
-    }
-    MP2_CUDA(cudaGetLastError());
-    {
-        Launch L("clr_dist_kernel", stream);
-        clr_dist_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, stream>>>(
-            (const uint32_t *)d_counts, (const long long *)d_mag_off, n_mags, n_rows, rowmean.as<double>(),
-            centroid.as<double>(), (float *)d_clr, (double *)d_dist);
+        Launch L("clr_mag_kernel", stream);
+        clr_mag_kernel<<<(unsigned)n_mags, CLRM_THREADS, 0, stream>>>(
+            (const uint32_t *)d_counts, (const long long *)d_weights, (const long long *)d_mag_off, (float *)d_clr,
+            (double *)d_dist);
     }
     MP2_CUDA(cudaGetLastError());
     return MP2_OK;
