@@ -64,6 +64,10 @@ __device__ __forceinline__ void smem_inc_if(uint32_t saddr, uint32_t cond) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(saddr), "r"(cond) : "memory");
 }
 
+__device__ __forceinline__ void smem_dec_if(uint32_t saddr, uint32_t cond) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.s32 [%0], -1;\n\t}" ::"r"(saddr), "r"(cond) : "memory");
+}
+
 // upper_bound(a[lo..hi), x) - 1 : largest i in [lo, hi) with a[i] <= x (lo if none)
 __device__ __forceinline__ int64_t last_le(const int64_t *__restrict__ a, int64_t lo, int64_t hi, int64_t x) {
     int64_t l = lo, h = hi;
@@ -1186,10 +1190,12 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
                         const bool before = live && (sv >= len || gs < t_hi);
                         const unsigned nb = ~__ballot_sync(0xffffffffu, before);
                         const int cnt = nb ? __ffs(nb) - 1 : 32;  // leading lanes only (starts are sorted)
-                        if (ok && lane < cnt) {
-                            if (gs >= t_lo) smem_inc(sT0 + 4u * (uint32_t)c3_phys(gs - t_lo));
-                            else if (ge >= t_lo) open++;  // first window of a run: block open across run_lo
-                            if (ge >= t_lo && ge - t_lo < C3_W + C3_S) smem_add(sT0 + 4u * (uint32_t)c3_phys(ge - t_lo), -1);
+                        {   // predicated reductions: no divergent branches in the streaming loop
+                            const bool act = ok && lane < cnt;
+                            const int rs = gs - t_lo, re = ge - t_lo;
+                            smem_inc_if(sT0 + 4u * (uint32_t)c3_phys(rs), act && rs >= 0);
+                            open += (act && rs < 0 && re >= 0);  // first window of a run: block open across run_lo
+                            smem_dec_if(sT0 + 4u * (uint32_t)c3_phys(re), act && re >= 0 && re < C3_W + C3_S);
                         }
                         e_cur += cnt;
                         if (cnt && e_cur < n_ev && e_cur >= cur.y)  // advance the warp's contig cursor

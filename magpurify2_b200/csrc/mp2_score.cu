@@ -12,7 +12,7 @@
 namespace mp2 {
 
 constexpr int WM_THREADS = 256;
-constexpr int WM_SMEM_CAP = 4096;  // (value, weight) pairs sorted in shared memory; larger MAGs use scratch
+constexpr int WM_SMEM_CAP = 1024;  // (value, weight) pairs sorted in shared memory (16 KB: 8 CTAs per SM); larger MAGs use scratch
 
 struct VW {
     uint32_t key;  // order-preserving image of the f32 value (NaN last)
