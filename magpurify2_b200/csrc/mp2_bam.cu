@@ -214,8 +214,11 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
     } unmap{f, size};
     madvise((void *)f, size, MADV_SEQUENTIAL);
 
+    const bool trace = getenv("MP2_TRACE") != nullptr;
+    double t_idx = omp_get_wtime(), t_inf = 0, t_hop = 0, t_flt = 0, t_mrg = 0, t_res = 0, t_x;
     std::vector<Block> blocks;
     MP2_TRY(index_blocks(f, size, blocks, path));
+    t_idx = omp_get_wtime() - t_idx;
 
     mp2_bam *b = new mp2_bam();
     struct Guard {
@@ -223,10 +226,24 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
         ~Guard() { if (b) mp2_bam_close(b); }
     } guard{b};
 
-    std::vector<uint8_t> buf;          // uncompressed window (leftover + batch)
+    // uncompressed window (leftover + batch); grown with realloc so that nothing is ever zero-filled
+    struct RawBuf {
+        uint8_t *p = nullptr;
+        size_t cap = 0;
+        ~RawBuf() { free(p); }
+        bool reserve(size_t n) {
+            if (n <= cap) return true;
+            const size_t c = n + n / 4 + 4096;
+            uint8_t *q = (uint8_t *)realloc(p, c);
+            if (!q) return false;
+            p = q; cap = c;
+            return true;
+        }
+        uint8_t *data() { return p; }
+    } buf;
     std::vector<uint32_t> ev_s, ev_e;  // accepted blocks in BAM order
     std::vector<int64_t> per_tid;
-    const int64_t BATCH = 256ll << 20;
+    const int64_t BATCH = 64ll << 20;
     size_t bi = 0;
     int64_t have = 0;   // valid bytes in buf
     bool header_done = false;
@@ -241,7 +258,10 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
         size_t bj = bi;
         int64_t add = 0;
         while (bj < blocks.size() && (add == 0 || add + blocks[bj].usize <= BATCH)) add += blocks[bj++].usize;
-        buf.resize(have + add);
+        t_x = omp_get_wtime();
+        if (!buf.reserve((size_t)(have + add))) return fail(MP2_ENOMEM, "%s: out of host memory for the inflate window", path);
+        t_res += omp_get_wtime() - t_x;
+        t_x = omp_get_wtime();
         std::vector<int64_t> uoff(bj - bi + 1, have);
         for (size_t k = bi; k < bj; k++) uoff[k - bi + 1] = uoff[k - bi] + blocks[k].usize;
         std::atomic<int> bad{0};
@@ -249,6 +269,7 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
         for (int64_t k = (int64_t)bi; k < (int64_t)bj; k++)
             if (!inflate_block(f, blocks[k], buf.data() + uoff[k - bi])) bad = 1;
         if (bad) return fail(MP2_EIO, "%s: corrupt BGZF block (inflate failed)", path);
+        t_inf += omp_get_wtime() - t_x;
         const bool last_batch = bj == blocks.size();
         bi = bj;
         have += add;
@@ -291,13 +312,26 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
             o = q;
         }
         // ---- record boundaries (sequential hop), then parallel filter ----
+        t_x = omp_get_wtime();
+        // (the only serial pass over the bytes: it reads 4 bytes per record, a few records ahead are
+        // prefetched because the stride is the record size and the hardware prefetcher does not follow it)
         rec_off.clear();
-        while (o + 4 <= have) {
-            const int64_t bs = rd32(p + o);
-            if (o + 4 + bs > have) break;
-            rec_off.push_back(o);
-            o += 4 + bs;
+        {
+            int64_t stride = 256;
+            while (o + 4 <= have) {
+                const int64_t bs = rd32(p + o);
+                if (o + 4 + bs > have) break;
+                rec_off.push_back(o);
+                stride = 4 + bs;
+                if (o + 12 * stride + 4 <= have) {
+                    __builtin_prefetch(p + o + 8 * stride);
+                    __builtin_prefetch(p + o + 12 * stride);
+                }
+                o += stride;
+            }
         }
+        t_hop += omp_get_wtime() - t_x;
+        t_x = omp_get_wtime();
         const int64_t nr = (int64_t)rec_off.size();
         rec_tid.resize(nr);
         rec_n.resize(nr);
@@ -320,33 +354,53 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
             return fail(MP2_EFORMAT, "%s: a mapped record has no NM tag (needed for the identity filter; "
                         "the reference panics here)", path);
         if (err) return fail(MP2_EIO, "%s: malformed BAM record", path);
+        t_flt += omp_get_wtime() - t_x;
+        t_x = omp_get_wtime();
+        // ---- merge: serial scan of the per-record block counts (order, totals), parallel fill ----
+        std::vector<int64_t> ev_pos((size_t)nr + 1);
+        {
+            int64_t pos = (int64_t)ev_s.size();
+            for (int64_t i = 0; i < nr; i++) {
+                ev_pos[i] = pos;
+                const int k = rec_n[i];
+                if (k <= 0) continue;
+                const int64_t tid = rec_tid[i];
+                if (tid >= (int64_t)b->names.size())
+                    return fail(MP2_EIO, "%s: record refers to an unknown reference", path);
+                if (tid < last_tid)
+                    return fail(MP2_EFORMAT, "%s: records are not sorted by reference (SO:coordinate required)", path);
+                last_tid = tid;
+                b->n_kept++;
+                per_tid[tid] += k;
+                pos += k;
+            }
+            ev_pos[nr] = pos;
+            b->n_records += nr;
+            ev_s.resize((size_t)pos);
+            ev_e.resize((size_t)pos);
+        }
+        uint32_t span_max = b->max_span;
+#pragma omp parallel for schedule(static) num_threads(threads) reduction(max : span_max)
         for (int64_t i = 0; i < nr; i++) {
-            b->n_records++;
             const int k = rec_n[i];
             if (k <= 0) continue;
-            const int64_t tid = rec_tid[i];
-            if (tid >= (int64_t)b->names.size()) return fail(MP2_EIO, "%s: record refers to an unknown reference", path);
-            if (tid < last_tid)
-                return fail(MP2_EFORMAT, "%s: records are not sorted by reference (SO:coordinate required)", path);
-            last_tid = tid;
-            b->n_kept++;
+            const int64_t at = ev_pos[i];
             if (k == 1) {
-                ev_s.push_back(rec_s[i]);
-                ev_e.push_back(rec_e[i]);
+                ev_s[at] = rec_s[i];
+                ev_e[at] = rec_e[i];
                 const uint32_t span = rec_e[i] - rec_s[i];
-                if (span > b->max_span) b->max_span = span;
+                span_max = span > span_max ? span : span_max;
             } else {
-                std::vector<uint32_t> ms(k), me(k);
-                int32_t t2; uint32_t s0, e0;
+                int32_t t2 = 0; uint32_t s0 = 0, e0 = 0;
                 const uint8_t *r = p + rec_off[i];
-                record_blocks(r + 4, rd32(r), min_identity, t2, s0, e0, ms.data(), me.data(), k - 1);
-                ev_s.push_back(s0); ev_e.push_back(e0);
-                for (int x = 0; x < k - 1; x++) { ev_s.push_back(ms[x]); ev_e.push_back(me[x]); }
-                const uint32_t span = me[k - 2] - s0;  // the whole read footprint bounds every block
-                if (span > b->max_span) b->max_span = span;
+                record_blocks(r + 4, rd32(r), min_identity, t2, s0, e0, &ev_s[at + 1], &ev_e[at + 1], k - 1);
+                ev_s[at] = s0; ev_e[at] = e0;
+                const uint32_t span = ev_e[at + k - 1] - s0;  // the whole read footprint bounds every block
+                span_max = span > span_max ? span : span_max;
             }
-            per_tid[tid] += k;
         }
+        b->max_span = span_max;
+        t_mrg += omp_get_wtime() - t_x;
         // ---- keep the partial record for the next batch ----
         const int64_t left = have - o;
         if (left > 0 && last_batch) {
@@ -376,6 +430,9 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
         memcpy(b->starts, ev_s.data(), sizeof(uint32_t) * ev_s.size());
         memcpy(b->ends, ev_e.data(), sizeof(uint32_t) * ev_e.size());
     }
+    if (trace)
+        fprintf(stderr, "[mp2_bam] index %.3f resize %.3f inflate %.3f hop %.3f filter %.3f merge %.3f s (%d threads)\n",
+                t_idx, t_res, t_inf, t_hop, t_flt, t_mrg, threads);
     guard.b = nullptr;
     *out = b;
     return MP2_OK;
