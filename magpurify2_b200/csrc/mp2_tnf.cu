@@ -90,13 +90,33 @@ __device__ __forceinline__ void smem_inc(uint32_t saddr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory");
 }
 
-// ---- piece -> first contig map -----------------------------------------------------------
+// ---- piece map ---------------------------------------------------------------------------------
+// Piece k nominally starts at aligned-stream position k << piece_shift.  With `snap`, a boundary moves
+// forward to the first contig start within half a piece of it: the piece before it then ends with a whole
+// contig and the segment that would have straddled the boundary (one more table flush) does not exist.
+// adj[k] = boundary - (k << piece_shift) in [0, piece/2); first_contig[k] = contig holding the boundary.
+// Entries 0..n_chunks are written (the kernel needs the boundary after its last piece).
 __global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_t n, int mis, int piece_shift,
-                                     int64_t chunk_begin, int64_t n_chunks,
-                                     int32_t *__restrict__ first_contig) {
+                                     int snap, int64_t chunk_begin, int64_t n_chunks,
+                                     int32_t *__restrict__ first_contig, int32_t *__restrict__ adj) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k >= n_chunks) return;
-    int64_t pos = ((chunk_begin + k) << piece_shift) - mis;  // stream position of the piece start
+    if (k > n_chunks) return;
+    const int64_t kabs = chunk_begin + k;
+    int64_t pos = (kabs << piece_shift) - mis;  // stream position of the nominal boundary
+    int32_t d = 0;
+    if (snap && kabs > 0) {
+        int64_t lo = 0, hi = n;  // lower_bound: first c with offsets[c] >= pos
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (offsets[mid] < pos) lo = mid + 1;
+            else hi = mid;
+        }
+        if (lo < n) {
+            const int64_t gap = offsets[lo] - pos;
+            if (gap > 0 && gap < ((int64_t)1 << (piece_shift - 1))) d = (int32_t)gap;
+        }
+    }
+    pos += d;
     // largest c in [0, n-1] with offsets[c] <= pos (0 if none)
     int64_t lo = 0, hi = n;  // search upper_bound over offsets[0..n)
     while (lo < hi) {
@@ -105,6 +125,7 @@ __global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_
         else hi = mid;
     }
     first_contig[k] = (int32_t)(lo > 0 ? lo - 1 : 0);
+    adj[k] = d;
 }
 
 // Fold the warp's table into the contig's row: 256 codes -> 136 canonical classes, integer global
@@ -325,11 +346,12 @@ template <int MODE, int PS>
 __global__ void __launch_bounds__(TNF_THREADS)
 tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
            const int64_t *__restrict__ offsets, int64_t n,
-           const int32_t *__restrict__ first_contig, int64_t chunk_begin, int64_t n_chunks,
+           const int32_t *__restrict__ first_contig, const int32_t *__restrict__ adj, int64_t chunk_begin,
+           int64_t n_chunks, int64_t total_pieces,
            uint32_t *__restrict__ counts, unsigned long long *__restrict__ gc_counts,
            int *__restrict__ work_counter) {
     constexpr int WORDS = TnfTab<MODE>::WORDS;
-    constexpr int TNF_PIECE = 1 << PS;
+    constexpr int64_t TNF_PIECE = 1 << PS;
     uint32_t *tab = tnf_tab;
 
     const int lane = threadIdx.x;
@@ -347,12 +369,21 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
         if (lane == 0) kc = atomicAdd(work_counter, 1);
         kc = __shfl_sync(0xffffffffu, kc, 0);
         if (kc >= n_chunks) break;
-        const int64_t base = (chunk_begin + kc) * TNF_PIECE;  // aligned-stream position of the piece
+        // the piece = aligned-stream positions [lo_abs, hi_abs): nominal boundaries moved to contig starts
+        const int64_t kabs = chunk_begin + kc;
+        int64_t lo_abs = kabs * TNF_PIECE + adj[kc];
+        int64_t hi_abs = kabs + 1 >= total_pieces ? end_q : (kabs + 1) * TNF_PIECE + adj[kc + 1];
+        lo_abs = lo_abs < mis ? mis : lo_abs;
+        hi_abs = hi_abs < end_q ? hi_abs : end_q;
+        const int64_t base = lo_abs & ~(int64_t)15;
         const uint8_t *__restrict__ pb = bases_al + base;     // 16-byte aligned
         // everything below is relative to `base`, in 32 bits
-        const int piece_lo = base < mis ? mis - (int)base : 0;
-        const int piece_hi = (int)(end_q - base < TNF_PIECE ? end_q - base : TNF_PIECE);
-        const int safe_hi = piece_hi;  // bytes at or beyond this offset may not be read
+        const int piece_lo = (int)(lo_abs - base);
+        const int piece_hi = (int)(hi_abs - base);
+        // bytes at or beyond safe_hi may not be read: the group holding the piece's last byte is read whole
+        // unless it runs past the end of the stream
+        const int64_t room = end_q - base;
+        const int safe_hi = (int)(room < ((piece_hi + 15) & ~15) ? room : ((piece_hi + 15) & ~15));
         const bool head_ok = base > 0; // bytes before the piece may be read (halo)
 
         for (int64_t c = first_contig[kc]; c < n; c++) {
@@ -629,6 +660,18 @@ static int tnf_mode() {
     return mode;
 }
 
+// MP2_TNF_SNAP=0 keeps the nominal piece boundaries (development / A-B switch).
+static int tnf_snap() {
+    static int snap = -1;
+    if (snap < 0) {
+        const char *e = getenv("MP2_TNF_SNAP");
+        snap = (e && e[0] == '0') ? 0 : 1;
+    }
+    return snap;
+}
+
+int64_t tnf_num_chunks(const void *d_bases, int64_t n_bases);
+
 // Enqueue the counting kernels for chunks [chunk_begin, chunk_end) of the stream.
 // d_counts / d_gc_counts must have been zeroed (once) before the first range.
 int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n, int64_t n_bases,
@@ -639,14 +682,16 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
     const int64_t n_chunks = chunk_end - chunk_begin;
     if (n_chunks <= 0) return MP2_OK;
     const int ps = tnf_piece_shift(n_bases);
-    Temp map, ctr;
-    MP2_TRY(map.alloc(sizeof(int32_t) * n_chunks, stream));
+    Temp map, adj, ctr;
+    MP2_TRY(map.alloc(sizeof(int32_t) * (n_chunks + 1), stream));
+    MP2_TRY(adj.alloc(sizeof(int32_t) * (n_chunks + 1), stream));
     MP2_TRY(ctr.alloc(sizeof(int), stream));
     MP2_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int), stream));
+    const int64_t total_pieces = tnf_num_chunks(d_bases, n_bases);
     {
         Launch L("tnf_chunk_map_kernel", stream);
-        tnf_chunk_map_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, stream>>>(
-            d_offsets, n, mis, ps, chunk_begin, n_chunks, map.as<int32_t>());
+        tnf_chunk_map_kernel<<<(unsigned)((n_chunks + 1 + 255) / 256), 256, 0, stream>>>(
+            d_offsets, n, mis, ps, tnf_snap(), chunk_begin, n_chunks, map.as<int32_t>(), adj.as<int32_t>());
     }
     MP2_CUDA(cudaGetLastError());
     const int mode = tnf_mode();
@@ -659,8 +704,8 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
         if (grid > n_chunks) grid = n_chunks;                                                               \
         Launch L("tnf_kernel", stream);                                                                     \
         tnf_kernel<M, PS><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(                                      \
-            d_bases - mis, mis, n_bases + mis, d_offsets, n, map.as<int32_t>(), chunk_begin, n_chunks,     \
-            d_counts, d_gc_counts, ctr.as<int>());                                                          \
+            d_bases - mis, mis, n_bases + mis, d_offsets, n, map.as<int32_t>(), adj.as<int32_t>(),         \
+            chunk_begin, n_chunks, total_pieces, d_counts, d_gc_counts, ctr.as<int>());                     \
     } while (0)
     if (mode == 5 && ps == 15) MP2_TNF_LAUNCH(5, 15);
     else if (mode == 5) MP2_TNF_LAUNCH(5, 14);
@@ -673,8 +718,12 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
 
 // Pieces wholly inside the first `done` bytes of the stream (host staging pipelines on this).
 int64_t tnf_chunks_ready(const void *d_bases, int64_t done, int64_t n_bases) {
+    // a piece may reach half a piece beyond its nominal end (boundaries snap to contig starts) and its last
+    // 16-byte group is read whole
     const int mis = (int)(reinterpret_cast<uintptr_t>(d_bases) & 15);
-    return (done + mis) >> tnf_piece_shift(n_bases);
+    const int ps = tnf_piece_shift(n_bases);
+    const int64_t usable = done + mis - ((int64_t)1 << (ps - 1)) - 16;
+    return usable > 0 ? usable >> ps : 0;
 }
 
 int64_t tnf_num_chunks(const void *d_bases, int64_t n_bases) {
@@ -770,13 +819,15 @@ extern "C" int mp2_tnf_packed_device(const void *d_codes, const void *d_valid, c
     const int ps = tnf_piece_shift(n_bases);
     const int64_t n_chunks = (n_bases + ((int64_t)1 << ps) - 1) >> ps;
     if (n_chunks > 0) {
-        MP2_TRY(map.alloc(sizeof(int32_t) * n_chunks, stream));
+        Temp adj;  // the packed kernel keeps the nominal boundaries (snap = 0)
+        MP2_TRY(map.alloc(sizeof(int32_t) * (n_chunks + 1), stream));
+        MP2_TRY(adj.alloc(sizeof(int32_t) * (n_chunks + 1), stream));
         MP2_TRY(ctr.alloc(sizeof(int), stream));
         MP2_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int), stream));
         {
             Launch L("tnf_chunk_map_kernel", stream);
-            tnf_chunk_map_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, stream>>>(
-                (const int64_t *)d_offsets, n, 0, ps, 0, n_chunks, map.as<int32_t>());
+            tnf_chunk_map_kernel<<<(unsigned)((n_chunks + 1 + 255) / 256), 256, 0, stream>>>(
+                (const int64_t *)d_offsets, n, 0, ps, 0, 0, n_chunks, map.as<int32_t>(), adj.as<int32_t>());
         }
         MP2_CUDA(cudaGetLastError());
         const int mode = tnf_mode();

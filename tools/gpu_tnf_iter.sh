@@ -8,14 +8,14 @@ for ms in "5 14" "5 15" "4 14"; do
 done
 MP2_TNF_PIECE_SHIFT=14 python bench.py --steps 5 --warmup 3 --no-cpu --samples 0 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('C3 16KiB pieces kernel_ms', round(d['roofline']['kernel_ms'],3), 'frac', round(d['roofline']['frac'],3))"
-python bench.py --steps 5 --warmup 3 --no-cpu --samples 0 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
+python bench.py --steps 5 --warmup 3 --samples 0 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 python bench.py --steps 5 --warmup 3 --no-cpu --samples 0 --long-contigs --mags 400 > gpurun_out/bench_${tag}_c5.json 2>> gpurun_out/bench_$tag.err
 python - <<PY
 import json
 for f,n in (('gpurun_out/bench_$tag.json','C3'),('gpurun_out/bench_${tag}_c5.json','C5')):
     try:
         d=json.load(open(f))
-        print(n, round(d['value'],1),'Gbp/s kernel_ms',round(d['roofline']['kernel_ms'],3),'frac',round(d['roofline']['frac'],3),'e2e',round(d['e2e']['value'],1), 'packed', d.get('packed_2bit_path',{}).get('count_ms'))
+        print(n, d.get('cpu_baseline',{}).get('parity_with_gpu'), round(d['value'],1),'Gbp/s kernel_ms',round(d['roofline']['kernel_ms'],3),'frac',round(d['roofline']['frac'],3),'e2e',round(d['e2e']['value'],1), 'packed', d.get('packed_2bit_path',{}).get('count_ms'))
     except Exception as e: print('fail',n,e); print(open('gpurun_out/bench_$tag.err').read()[-1500:])
 PY
 if [ -z "$NO_NCU" ]; then
