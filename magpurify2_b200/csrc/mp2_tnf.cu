@@ -92,9 +92,9 @@ __device__ __forceinline__ void smem_inc(uint32_t saddr) {
 
 // ---- piece map ---------------------------------------------------------------------------------
 // Piece k nominally starts at aligned-stream position k << piece_shift.  With `snap`, a boundary moves
-// forward to the first contig start within half a piece of it: the piece before it then ends with a whole
+// forward to the first contig start within one piece of it: the piece before it then ends with a whole
 // contig and the segment that would have straddled the boundary (one more table flush) does not exist.
-// adj[k] = boundary - (k << piece_shift) in [0, piece/2); first_contig[k] = contig holding the boundary.
+// adj[k] = boundary - (k << piece_shift) in [0, piece); first_contig[k] = contig holding the boundary.
 // Entries 0..n_chunks are written (the kernel needs the boundary after its last piece).
 __global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_t n, int mis, int piece_shift,
                                      int snap, int64_t chunk_begin, int64_t n_chunks,
@@ -113,7 +113,7 @@ __global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_
         }
         if (lo < n) {
             const int64_t gap = offsets[lo] - pos;
-            if (gap > 0 && gap < ((int64_t)1 << (piece_shift - 1))) d = (int32_t)gap;
+            if (gap > 0 && gap < ((int64_t)1 << piece_shift)) d = (int32_t)gap;
         }
     }
     pos += d;
@@ -343,7 +343,7 @@ __device__ __noinline__ uint32_t tnf_edge_row(uint4 v, uint32_t cw, uint32_t hal
 }
 
 template <int MODE, int PS>
-__global__ void __launch_bounds__(TNF_THREADS)
+__global__ void __launch_bounds__(TNF_THREADS, 32)  // 32 warps per SM: at most 64 registers
 tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
            const int64_t *__restrict__ offsets, int64_t n,
            const int32_t *__restrict__ first_contig, const int32_t *__restrict__ adj, int64_t chunk_begin,
@@ -718,11 +718,11 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
 
 // Pieces wholly inside the first `done` bytes of the stream (host staging pipelines on this).
 int64_t tnf_chunks_ready(const void *d_bases, int64_t done, int64_t n_bases) {
-    // a piece may reach half a piece beyond its nominal end (boundaries snap to contig starts) and its last
+    // a piece may reach one piece beyond its nominal end (boundaries snap to contig starts) and its last
     // 16-byte group is read whole
     const int mis = (int)(reinterpret_cast<uintptr_t>(d_bases) & 15);
     const int ps = tnf_piece_shift(n_bases);
-    const int64_t usable = done + mis - ((int64_t)1 << (ps - 1)) - 16;
+    const int64_t usable = done + mis - ((int64_t)1 << ps) - 16;
     return usable > 0 ? usable >> ps : 0;
 }
 
