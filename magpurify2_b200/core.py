@@ -19,6 +19,20 @@ from ._fasta import Fasta
 TNF_SCORE_BASE = 4.0
 
 
+def read_mags(genomes, threads=1, store_sequences=True):
+    """[Mag(g) for g in genomes] on a thread pool: the FASTA reader is native code that releases the GIL, so
+    the genomes of a run are parsed `threads` at a time (the reference parses them one by one,
+    modules/composition.py:48)."""
+    genomes = list(genomes)
+    threads = max(1, min(int(threads or 1), len(genomes)))
+    if threads == 1:
+        return [Mag(g, store_sequences=store_sequences) for g in genomes]
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        return list(pool.map(lambda g: Mag(g, store_sequences=store_sequences), genomes))
+
+
 class Mag:
     def __init__(self, filepath, store_sequences=True):
         self.genome = filepath.stem

@@ -3,6 +3,7 @@
 // (/root/reference/magpurify2/tools.py:210-240, magpurify2/core.py:35-50): record id = first
 // word of the header with '~' -> '_', description = the whole header, sequence = the lines joined
 // with white space removed.
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include <cstring>
@@ -22,30 +23,13 @@ struct mp2_fasta {
 namespace mp2 {
 
 static int parse_fasta(const uint8_t *p, int64_t size, mp2_fasta *f) {
-    // pass 1: size of the sequence payload
-    int64_t payload = 0;
-    {
-        bool in_header = false, seen = false;
-        for (int64_t i = 0; i < size; i++) {
-            const uint8_t c = p[i];
-            const bool bol = i == 0 || p[i - 1] == '\n';
-            if (bol && c == '>') { in_header = true; seen = true; }
-            if (c == '\n') { in_header = false; continue; }
-            if (!in_header && seen && c > 0x20) payload++;
-        }
-    }
-    bool pin = false;
-    void *mem = nullptr;
-    const size_t bytes = (size_t)payload + 64;
-    if (cudaHostAlloc(&mem, bytes, cudaHostAllocPortable) == cudaSuccess) pin = true;
-    else {
-        (void)cudaGetLastError();
-        mem = malloc(bytes);
-    }
-    if (!mem) return fail(MP2_ENOMEM, "out of host memory for %lld bases", (long long)payload);
+    // The payload is never larger than the file: one allocation, one pass.  Plain host memory: the
+    // drivers concatenate the MAGs of a run into one stream, which is what gets staged to the device.
+    const size_t bytes = (size_t)size + 64;
+    void *mem = malloc(bytes);
+    if (!mem) return fail(MP2_ENOMEM, "out of host memory for %lld bytes of FASTA", (long long)size);
     f->bases = (uint8_t *)mem;
-    f->pinned = pin;
-    // pass 2: headers + payload
+    f->pinned = false;
     int64_t w = 0, i = 0;
     bool seen = false;
     while (i < size) {
@@ -66,8 +50,19 @@ static int parse_fasta(const uint8_t *p, int64_t size, mp2_fasta *f) {
             f->descs.push_back(desc);
             seen = true;
         } else if (seen) {
-            for (int64_t k = i; k < e; k++)
-                if (p[k] > 0x20) f->bases[w++] = p[k];
+            // sequence line: white space removed.  Lines are almost always clean (at most a trailing CR), so
+            // look for a byte <= 0x20 with a branch-free (vectorisable) scan and copy the line in one go.
+            int64_t le = e;
+            if (le > i && p[le - 1] == '\r') le--;
+            unsigned dirty = 0;
+            for (int64_t k = i; k < le; k++) dirty |= (unsigned)(p[k] <= 0x20);
+            if (!dirty) {
+                memcpy(f->bases + w, p + i, (size_t)(le - i));
+                w += le - i;
+            } else {
+                for (int64_t k = i; k < le; k++)
+                    if (p[k] > 0x20) f->bases[w++] = p[k];
+            }
         }
         i = e + 1;
     }
@@ -110,11 +105,27 @@ extern "C" int mp2_fasta_open(const char *path, mp2_fasta **out) {
     gzFile g = gzopen(path, "rb");  // transparent for files that are not gzip
     if (!g) return fail(MP2_EIO, "cannot open %s", path);
     gzbuffer(g, 1 << 20);
-    std::vector<uint8_t> buf;
-    size_t have = 0;
+    // realloc'ed window (never zero-filled); a plain file is read in one go, a gzip one grows by doubling
+    struct Raw {
+        uint8_t *p = nullptr;
+        ~Raw() { free(p); }
+    } buf;
+    size_t cap = 0, have = 0;
+    {
+        struct stat sb;
+        if (stat(path, &sb) == 0 && sb.st_size > 0) cap = (size_t)sb.st_size + (1u << 16);
+    }
+    if (cap < (1u << 20)) cap = 1u << 20;
+    buf.p = (uint8_t *)malloc(cap);
+    if (!buf.p) { gzclose(g); return fail(MP2_ENOMEM, "%s: out of host memory", path); }
     for (;;) {
-        if (buf.size() - have < (4u << 20)) buf.resize(buf.size() ? buf.size() * 2 : (16u << 20));
-        const int got = gzread(g, buf.data() + have, (unsigned)std::min<size_t>(buf.size() - have, 1u << 30));
+        if (cap - have < (1u << 16)) {
+            uint8_t *q = (uint8_t *)realloc(buf.p, cap * 2);
+            if (!q) { gzclose(g); return fail(MP2_ENOMEM, "%s: out of host memory", path); }
+            buf.p = q;
+            cap *= 2;
+        }
+        const int got = gzread(g, buf.p + have, (unsigned)std::min<size_t>(cap - have, 1u << 30));
         if (got < 0) {
             int e = 0;
             const char *msg = gzerror(g, &e);
@@ -126,7 +137,7 @@ extern "C" int mp2_fasta_open(const char *path, mp2_fasta **out) {
         have += (size_t)got;
     }
     gzclose(g);
-    return mp2_fasta_open_mem(buf.data(), (int64_t)have, out);
+    return mp2_fasta_open_mem(buf.p, (int64_t)have, out);
 }
 
 extern "C" {

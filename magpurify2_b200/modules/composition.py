@@ -11,7 +11,7 @@ import pickle
 import numpy as np
 
 from .. import _composition, tools
-from ..core import Composition, Mag, score_composition_batch
+from ..core import Composition, Mag, read_mags, score_composition_batch  # noqa: F401
 
 
 def main(args):
@@ -27,7 +27,7 @@ def main(args):
     composition_score_file = scores_directory.joinpath("composition_scores.tsv")
 
     logger.info(f"Reading {len(args.genomes)} genomes.")
-    mag_list = [Mag(genome) for genome in args.genomes]
+    mag_list = read_mags(args.genomes, threads=getattr(args, "threads", 1))
     composition_data_file = args.output_directory.joinpath("tnfs.pickle.gz")
 
     # one byte stream for the whole run

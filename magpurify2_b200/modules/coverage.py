@@ -11,7 +11,7 @@ from functools import reduce
 import numpy as np
 
 from .. import tools
-from ..core import Coverage, Mag, score_coverage_batch
+from ..core import Coverage, Mag, read_mags, score_coverage_batch  # noqa: F401
 
 
 def main(args):
@@ -39,7 +39,7 @@ def main(args):
         input_coverage = [args.coverage_file]
 
     logger.info(f"Reading {len(args.genomes)} genomes.")
-    mag_list = [Mag(genome, store_sequences=False) for genome in args.genomes]
+    mag_list = read_mags(args.genomes, threads=getattr(args, "threads", 1), store_sequences=False)
     coverage_data_file = args.output_directory.joinpath("coverages.pickle.gz")
     signatures = [tools.get_file_signature(filepath) for filepath in input_coverage]
 
