@@ -1015,18 +1015,24 @@ cov_tile_kernel(const TileArgs a) {
 // The contig histogram stays in the warp's shared memory across windows until the contig ends; only
 // contigs crossing a RUN boundary go through the global rows.  Needs max_span <= 512.
 // =====================================================================================================
-constexpr int C3_W = 2048;                   // slots per window (64 per lane)
+#ifndef MP2_C3_SPL
+#define MP2_C3_SPL 64
+#endif
+constexpr int C3_SPL = MP2_C3_SPL;           // consecutive slots per lane (a multiple of 16)
+constexpr int C3_SPL_LOG = C3_SPL == 64 ? 6 : 5;
+static_assert(C3_SPL == 64 || C3_SPL == 32, "slots per lane");
+constexpr int C3_W = 32 * C3_SPL;            // slots per window
 constexpr int C3_S = 512;                    // overflow region = largest block span of the fast path
 constexpr int C3_RUN = 65536;                // slots per run
-constexpr int C3_TPR = C3_RUN / C3_W;        // 32 windows per run
-constexpr int C3_WORDS = (C3_W + C3_S) + 4 * ((C3_W + C3_S) / 64);  // 4 pad words per 64 slots
-constexpr int C3_HEAD = C3_S + 4 * (C3_S / 64);                     // words of the overflow region
+constexpr int C3_TPR = C3_RUN / C3_W;        // windows per run
+constexpr int C3_WORDS = (C3_W + C3_S) + 4 * ((C3_W + C3_S) / C3_SPL);  // 4 pad words per lane's worth of slots
+constexpr int C3_HEAD = C3_S + 4 * (C3_S / C3_SPL);                     // words of the overflow region
 #ifndef MP2_C3_PF
 #define MP2_C3_PF 384
 #endif
 constexpr int C3_PF = MP2_C3_PF;             // events ahead of e_cur that are prefetched into L2
 
-__device__ __forceinline__ int c3_phys(int i) { return i + 4 * (i >> 6); }
+__device__ __forceinline__ int c3_phys(int i) { return i + 4 * (i >> C3_SPL_LOG); }
 
 __global__ void cov_bounds_run_kernel(const uint32_t *__restrict__ starts, const int64_t *__restrict__ ev_off,
                                       const int64_t *__restrict__ off, int64_t n, int64_t n_runs, uint32_t max_span,
@@ -1227,12 +1233,12 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
             __syncwarp();
 
             // ---- this lane's 64 slots: total, exclusive warp scan ----
-            const int myb = 68 * lane;
+            const int myb = (C3_SPL + 4) * lane;
             int tot = 0;
             {
                 const int4 *p = reinterpret_cast<const int4 *>(s_T + myb);
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
+                for (int j = 0; j < C3_SPL / 4; j++) {
                     const int4 v = p[j];
                     tot += v.x + v.y + v.z + v.w;
                 }
@@ -1247,7 +1253,7 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
             carry += __shfl_sync(0xffffffffu, incl, 31);
 
             // ---- contig windows intersecting [t_lo, t_hi) ----
-            const int q0 = t_lo + 64 * lane;
+            const int q0 = t_lo + C3_SPL * lane;
             for (;;) {
                 if (!have) {
                     if (c > c_last) break;
@@ -1266,10 +1272,10 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
                 const int lo = wlo > t_lo ? wlo : t_lo, hi = whi + 1 < t_hi ? whi + 1 : t_hi;
                 if (hi > lo) {
                     int mxl = 0;
-                    if (lo < q0 + 64 && hi > q0) {  // this lane's slots intersect the window
+                    if (lo < q0 + C3_SPL && hi > q0) {  // this lane's slots intersect the window
                         int run_d = dstart;
 #pragma unroll 1
-                        for (int ch = 0; ch < 4; ch++) {
+                        for (int ch = 0; ch < C3_SPL / 16; ch++) {
                             const int q = q0 + 16 * ch;
                             const int d_before = run_d;
                             int d[16];
