@@ -1,8 +1,8 @@
 // Host-side FASTA ingest: plain or gzip (zlib), records concatenated into ONE byte stream plus
 // offsets -- the layout mp2_tnf takes.  Replaces tools.read_fasta under core.Mag
 // (/root/reference/magpurify2/tools.py:210-240, magpurify2/core.py:35-50): record id = first
-// word of the header with '~' -> '_', description = the whole header, sequence = the lines joined
-// with white space removed.
+// word of the header with '~' -> '_', description = the whole header, sequence = the lines joined as
+// Biopython's SimpleFastaParser joins them (trailing white space stripped, ' ' and CR removed).
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -50,18 +50,20 @@ static int parse_fasta(const uint8_t *p, int64_t size, mp2_fasta *f) {
             f->descs.push_back(desc);
             seen = true;
         } else if (seen) {
-            // sequence line: white space removed.  Lines are almost always clean (at most a trailing CR), so
-            // look for a byte <= 0x20 with a branch-free (vectorisable) scan and copy the line in one go.
+            // sequence line, as Biopython's SimpleFastaParser builds it (Bio/SeqIO/FastaIO.py, under
+            // tools.read_fasta): trailing white space stripped, then every ' ' and '\r' removed; any other
+            // byte is kept.  Lines are almost always clean, so look for the two bytes with a branch-free
+            // (vectorisable) scan and copy the line in one go.
             int64_t le = e;
-            if (le > i && p[le - 1] == '\r') le--;
+            while (le > i && (p[le - 1] == ' ' || (p[le - 1] >= 0x09 && p[le - 1] <= 0x0D))) le--;
             unsigned dirty = 0;
-            for (int64_t k = i; k < le; k++) dirty |= (unsigned)(p[k] <= 0x20);
+            for (int64_t k = i; k < le; k++) dirty |= (unsigned)(p[k] == ' ') | (unsigned)(p[k] == '\r');
             if (!dirty) {
                 memcpy(f->bases + w, p + i, (size_t)(le - i));
                 w += le - i;
             } else {
                 for (int64_t k = i; k < le; k++)
-                    if (p[k] > 0x20) f->bases[w++] = p[k];
+                    if (p[k] != ' ' && p[k] != '\r') f->bases[w++] = p[k];
             }
         }
         i = e + 1;

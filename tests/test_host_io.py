@@ -139,6 +139,39 @@ def test_fasta_reader(tmp_path, opener, ext):
     assert Mag(Path(p), store_sequences=False).sequences == []
 
 
+def test_fasta_reader_odd_lines(tmp_path):
+    """Lines that need the byte-wise path (inner blanks, CRLF), an inner tab (kept: Biopython's parser under
+    tools.read_fasta only strips trailing white space and removes ' ' and CR), text before the first header, no
+    final newline, '>' inside a sequence line, and a file bigger than the reader's first window."""
+    rng = np.random.default_rng(3)
+    big = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), 3_000_000)).decode()
+    wrapped = "\n".join(big[i:i + 61] for i in range(0, len(big), 61))
+    text = "junk before\n>a d1\r\nAC\tGT \r\n A>C \n>b\n" + wrapped + "\n>c\nTTTT"
+    p = tmp_path / "odd.fa"
+    p.write_text(text)
+    recs = list(tools.read_fasta(p))
+    assert [r[0] for r in recs] == ["a", "b", "c"] and recs[0][1] == "a d1"
+    assert recs[0][2] == "AC\tGTA>C" and recs[1][2] == big and recs[2][2] == "TTTT"
+
+
+def test_read_mags_thread_pool(tmp_path):
+    from magpurify2_b200.core import read_mags
+
+    rng = np.random.default_rng(4)
+    paths = []
+    for m in range(7):
+        p = tmp_path / f"g{m}.fna"
+        with open(p, "w") as f:
+            for c in range(int(rng.integers(1, 6))):
+                f.write(f">g{m}_c{c}\n" + bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), int(rng.integers(0, 5000)))).decode() + "\n")
+        paths.append(p)
+    one, many = read_mags(paths, threads=1), read_mags(paths, threads=4)
+    assert [m.genome for m in many] == [f"g{m}" for m in range(7)]  # input order is kept
+    for a, b in zip(one, many):
+        assert a.contigs == b.contigs and np.array_equal(a.bases, b.bases) and np.array_equal(a.offsets, b.offsets)
+    assert read_mags([], threads=8) == []
+
+
 def test_validade_input_and_signature(tmp_path):
     assert tools.validade_input(5, "x", [1, 3]) == 3 and tools.validade_input(0.5, "x", [0.0, 1.0]) == 0.5
     p = tmp_path / "f.bin"

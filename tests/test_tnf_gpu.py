@@ -132,3 +132,26 @@ def test_device_pointer_entry(comp, oracle):
         torch.cuda.synchronize()
         assert np.array_equal(counts.cpu().numpy().view(np.uint32), want), shift
         assert _same_f32(gc.cpu().numpy(), want_gc)
+
+
+@pytest.mark.parametrize("env", [{"MP2_TNF_MODE": "4"}, {"MP2_TNF_PIECE_SHIFT": "15"}, {"MP2_TNF_SNAP": "0"},
+                                 {"MP2_TNF_PIECE_SHIFT": "15", "MP2_TNF_SNAP": "0"}])
+def test_development_switches_keep_parity(env, oracle, tmp_path):
+    """The A/B switches of the counting kernel (one increment per base, 32 KiB pieces on a small input,
+    nominal piece boundaries) are read once per process: run each in a child and compare with the oracle."""
+    import subprocess
+    import sys
+
+    from magpurify2_b200 import synth
+
+    d = synth.make_mags(3, seed=5, mean_bp=6e5, n_contigs=90)
+    want = oracle.get_tnf_concat(d["bases"], d["offsets"], relative=False, threads=4)
+    np.save(tmp_path / "bases.npy", d["bases"])
+    np.save(tmp_path / "offsets.npy", d["offsets"])
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from magpurify2_b200 import _composition as c; "
+            "b = np.load(%r); o = np.load(%r); "
+            "k, _r, g = c.tnf_from_concat(b, o, relative=False, want_gc=True); np.save(%r, k)"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "bases.npy"),
+               str(tmp_path / "offsets.npy"), str(tmp_path / "counts.npy")))
+    subprocess.run([sys.executable, "-c", code], check=True, env={**os.environ, **env}, timeout=300)
+    assert np.array_equal(np.load(tmp_path / "counts.npy"), want), env
