@@ -29,7 +29,7 @@ static size_t slice_bytes() {
     if (!v) {
         const char *e = getenv("MP2_SLICE_MB");
         long mb = e ? atol(e) : 0;
-        v = (size_t)(mb > 0 ? mb : 16) << 20;
+        v = (size_t)(mb > 0 ? mb : 32) << 20;
     }
     return v;
 }
