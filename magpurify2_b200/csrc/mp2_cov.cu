@@ -1509,10 +1509,10 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     MP2_TRY(meta.alloc(sizeof(RowMeta) * n_tiles, stream));
     MP2_TRY(deep_list.alloc(sizeof(int32_t) * n_contigs, stream));
     MP2_CUDA(cudaMemsetAsync(tile_sum.p, 0, sizeof(int32_t) * n_tiles, stream));
-    MP2_CUDA(cudaMemsetAsync(rows.p, 0, sizeof(uint32_t) * COV_BINS * (size_t)n_tiles, stream));
     MP2_CUDA(cudaMemsetAsync(meta.p, 0, sizeof(RowMeta) * n_tiles, stream));
-    {
+    {   // the histogram rows (186 MB at C3) and the difference array are only cleared when the path will run
         Launch L("cov_zero_kernel", stream);
+        cov_zero_kernel<<<(unsigned)(num_sms() * 8), 256, 0, stream>>>(rows.as<int4>(), (int64_t)COV_BINS / 4 * n_tiles, g);
         cov_zero_kernel<<<(unsigned)(num_sms() * 8), 256, 0, stream>>>(D.as<int4>(), (n_pos + 3) / 4, g);
     }
     MP2_CUDA(cudaGetLastError());
