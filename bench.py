@@ -85,8 +85,15 @@ class ClockSampler:
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v == "Active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": reasons, "samples": len(sm)}
+        gpus = sorted({r[0] for r in self.rows if len(r) >= 9})
+        if len(gpus) > 1:  # one sampler watching several GPUs: median SM clock and power of each
+            out["sm_mhz_by_gpu"] = {g: float(np.median([float(r[1]) for r in self.rows if len(r) >= 9 and r[0] == g]))
+                                    for g in gpus}
+            out["power_w_by_gpu"] = {g: float(np.median([float(r[3]) for r in self.rows if len(r) >= 9 and r[0] == g
+                                                         and r[3].replace(".", "").isdigit()] or [0.0])) for g in gpus}
+        return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -159,6 +166,9 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     barrier()
     l0 = lib.mp2_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cov_sampler = ClockSampler(",".join(str(i) for i in range(world))) if rank == 0 else None
+    if cov_sampler:
+        cov_sampler.start()
     barrier()
     e0.record()
     for _ in range(args.steps):
@@ -166,6 +176,7 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    cov_clocks = cov_sampler.stop() if cov_sampler else None
     launches = lib.mp2_launch_count() - l0
     # per-kernel durations for the roofline: the same steps on ONE stream (two samples in flight overlap on
     # the SMs, so a launch's event-to-event time would include the other sample's work)
@@ -185,15 +196,18 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
         lib.mp2_profile_read(name.encode(), C.byref(k_ms), C.byref(k_n))
         kern[name] = (k_ms.value, k_n.value)
     lib.mp2_profile_enable(0)
+    ms_ranks = [ms]
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        tot = torch.tensor([float(R_total)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tot)
-        R_all = float(tot.item())
+        g = torch.zeros(world, 3, dtype=torch.float64, device=dev)
+        mine = torch.tensor([ms, ms_one_stream, float(R_total)], dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(g, mine)
+        ms_ranks = [round(float(x), 3) for x in g[:, 0]]
+        ms_ranks_one = [round(float(x), 3) for x in g[:, 1]]
+        ms = float(g[:, 0].max().item())
+        R_all = float(g[:, 2].sum().item())
     else:
         R_all = float(R_total)
+        ms_ranks_one = [ms_one_stream]
     value = R_all * args.steps / (ms * 1e-3)
 
     # end to end: one sample through the host-buffer API (pinned events in, coverage column out)
@@ -256,6 +270,9 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
                    "streams": len(lanes),
                    "note": "kernel_ms / roofline are from a second pass of the same steps on one stream"},
         "ms_per_step_one_stream": ms_one_stream / args.steps,
+        "clocks": cov_clocks,
+        "ms_per_step_by_rank": [round(x / args.steps, 3) for x in ms_ranks],
+        "ms_per_step_by_rank_second_pass": [round(x / args.steps, 3) for x in ms_ranks_one],
         "roofline": dict(dom, peak_source=peak_src), "kernels": rl,
         "sample_bytes_algorithmic": sample_bytes,
         "sample_gbs": sample_bytes / (sample_ms * 1e-3) / 1e9,

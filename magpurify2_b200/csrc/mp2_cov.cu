@@ -635,8 +635,13 @@ __global__ void cov_check_kernel(const uint32_t *__restrict__ starts, const uint
 }
 
 constexpr int CT_CTAB = 96;  // contigs of a tile whose offsets are staged in shared memory
-constexpr int CT_DEEP_ROWS = 256;     // contigs per sample that may exceed the shared histogram's depth range
-constexpr int CT_DEEP_BINS = 32768;   // depths COV_BINS-1 .. COV_BINS-2+32768 are counted in the deep pool
+// Deep pool: contigs whose depth leaves the shared histogram claim a row of it.  A dominant organism sequenced
+// beyond 1000x brings ALL its contigs here at once (hundreds), so the pool is wide rather than tall: 2048 rows of
+// 4096 bins (32 MB, cleared per sample).  Beyond that -- more deep contigs, or depth >= 5118 -- the sample is
+// redone by the general path (2.5x slower, same results).  (256 rows x 32768 bins sent 2 of 80 C3-shaped
+// samples of an 8-GPU run down the general path: one rank at 87 ms per step, the others at 58.)
+constexpr int CT_DEEP_ROWS = 2048;    // contigs per sample that may exceed the shared histogram's depth range
+constexpr int CT_DEEP_BINS = 4096;    // depths COV_BINS-1 .. COV_BINS-2+4096 are counted in the deep pool
 
 struct TileArgs {
     const uint32_t *starts, *ends;
