@@ -23,17 +23,20 @@ namespace mp2 {
 constexpr int TNF_THREADS = 32;   // one warp per CTA: the warp's table sits at a fixed shared address
 // Bytes of the stream owned by one work item (one warp) = 1 << shift.  Every segment costs a table flush
 // and two edge rows, so large inputs use 32 KiB pieces (fewer piece-boundary segments); small inputs
-// keep 16 KiB so that there are enough pieces for all warps.  MP2_TNF_PIECE_SHIFT=14|15 overrides.
+// keep 16 KiB so that there are enough pieces for all warps.  MP2_TNF_PIECE_SHIFT=14|15|16 overrides.
 static int tnf_piece_shift(int64_t n_bases) {
     static int forced = -1;
     if (forced < 0) {
         const char *e = getenv("MP2_TNF_PIECE_SHIFT");
-        forced = (e && atoi(e) >= 14 && atoi(e) <= 15) ? atoi(e) : 0;
+        forced = (e && atoi(e) >= 14 && atoi(e) <= 16) ? atoi(e) : 0;
     }
     if (forced) return forced;
     return n_bases >= ((int64_t)1 << 28) ? 15 : 14;
 }
-constexpr int TNF_UNROLL = 4;     // 16-byte groups in flight per lane
+#ifndef MP2_TNF_UNROLL
+#define MP2_TNF_UNROLL 4
+#endif
+constexpr int TNF_UNROLL = MP2_TNF_UNROLL;  // 16-byte groups in flight per lane
 
 // Table words per warp: MODE 4 counts one 4-mer per base into T4[256]; MODE 5 counts one 5-mer
 // per TWO bases into T5[1024] (a 5-mer b0..b4 stands for the 4-mers b0..b3 and b1..b4) and
@@ -707,7 +710,8 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
             d_bases - mis, mis, n_bases + mis, d_offsets, n, map.as<int32_t>(), adj.as<int32_t>(),         \
             chunk_begin, n_chunks, total_pieces, d_counts, d_gc_counts, ctr.as<int>());                     \
     } while (0)
-    if (mode == 5 && ps == 15) MP2_TNF_LAUNCH(5, 15);
+    if (mode == 5 && ps == 16) MP2_TNF_LAUNCH(5, 16);
+    else if (mode == 5 && ps == 15) MP2_TNF_LAUNCH(5, 15);
     else if (mode == 5) MP2_TNF_LAUNCH(5, 14);
     else if (ps == 15) MP2_TNF_LAUNCH(4, 15);
     else MP2_TNF_LAUNCH(4, 14);
@@ -843,7 +847,8 @@ extern "C" int mp2_tnf_packed_device(const void *d_codes, const void *d_valid, c
             (const uint32_t *)d_codes, (const uint32_t *)d_valid, n_bases, (const int64_t *)d_offsets, n,       \
             map.as<int32_t>(), n_chunks, (uint32_t *)d_counts, gcc.as<unsigned long long>(), ctr.as<int>());    \
     } while (0)
-        if (mode == 5 && ps == 15) MP2_TNFP_LAUNCH(5, 15);
+        if (mode == 5 && ps == 16) MP2_TNFP_LAUNCH(5, 16);
+        else if (mode == 5 && ps == 15) MP2_TNFP_LAUNCH(5, 15);
         else if (mode == 5) MP2_TNFP_LAUNCH(5, 14);
         else if (ps == 15) MP2_TNFP_LAUNCH(4, 15);
         else MP2_TNFP_LAUNCH(4, 14);
