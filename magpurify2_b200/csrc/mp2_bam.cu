@@ -11,6 +11,7 @@
 #include <zlib.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -243,7 +244,11 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
     } buf;
     std::vector<uint32_t> ev_s, ev_e;  // accepted blocks in BAM order
     std::vector<int64_t> per_tid;
-    const int64_t BATCH = 64ll << 20;
+    int64_t BATCH = 64ll << 20;  // uncompressed bytes inflated per round (MP2_BAM_BATCH_KB: test switch)
+    if (const char *e = getenv("MP2_BAM_BATCH_KB")) {
+        const long kb = atol(e);
+        if (kb > 0) BATCH = (int64_t)kb << 10;
+    }
     size_t bi = 0;
     int64_t have = 0;   // valid bytes in buf
     bool header_done = false;

@@ -88,6 +88,28 @@ def test_bam_reader_many_blocks_and_threads(tmp_path):
         assert b1.ev_off.tolist() == [0, int((keep & (tid == 0)).sum()), int(keep.sum())]
 
 
+def test_bam_reader_small_batches(tmp_path, monkeypatch):
+    """Inflate rounds far smaller than the file: records (and the header) straddle the rounds, the leftover
+    bytes of one round are the head of the next.  Same events as one big round."""
+    rng = np.random.default_rng(43)
+    n = 20000
+    names = [f"contig_{i}" for i in range(40)]
+    lengths = [50000] * 40
+    tid = np.sort(rng.integers(0, 40, n))
+    pos = np.concatenate([np.sort(rng.integers(0, 50000 - 150, int((tid == t).sum()))) for t in range(40)])
+    nm = rng.binomial(150, 0.01, n)
+    path = tmp_path / "rounds.bam"
+    bamio.write_bam_fixed(str(path), names, lengths, tid, pos, nm)
+    with _bam.BamEvents(path, 0.97, threads=3) as ref:
+        want = (ref.starts.copy(), ref.ends.copy(), ref.ev_off.copy(), ref.n_records, ref.n_kept, ref.max_span)
+    for kb in ("1", "65", "300"):  # 1 KiB rounds are smaller than a BGZF block: one block per round
+        monkeypatch.setenv("MP2_BAM_BATCH_KB", kb)
+        with _bam.BamEvents(path, 0.97, threads=3) as b:
+            assert (b.n_records, b.n_kept, b.max_span) == want[3:], kb
+            assert np.array_equal(b.starts, want[0]) and np.array_equal(b.ends, want[1]), kb
+            assert np.array_equal(b.ev_off, want[2]) and b.names == names, kb
+
+
 def test_bam_reader_errors(tmp_path):
     p = tmp_path / "nm.bam"
     bamio.write_bam(str(p), ["c"], [1000], [dict(tid=0, pos=1, cigar=[("M", 50)], nm=None)])
