@@ -116,7 +116,8 @@ typedef struct {
  *           array is then built tile by tile in shared memory and never touches HBM.
  *           0 = unknown: the library checks both on the device first and falls back to the
  *           general path (difference array in HBM, any order) when the starts are not sorted.
- * Contigs that reach depth >= 1023 also go through the general path (exact for any depth).
+ * Contigs that reach depth >= 511 are counted in a pool of global histograms (2048 contigs per call, depth
+ * < 4607); a sample that needs more goes through the general path (exact for any depth).
  * trim_lower + trim_upper must be < 1 (the CLI clamps both, magpurify2/modules/coverage.py:39-49). */
 int mp2_cov_events_device(const void *d_starts, const void *d_ends, const void *d_ev_off,
                           const void *d_contig_off, int64_t n_contigs, int64_t n_events,

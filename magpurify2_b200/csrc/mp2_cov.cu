@@ -32,7 +32,9 @@ constexpr int COV_ITEMS = 16;                         // positions per thread pe
 constexpr int COV_SUB = COV_THREADS * COV_ITEMS;      // 4096 positions
 constexpr int COV_TILE = 65536;                       // positions per tile
 constexpr int COV_NSUB = COV_TILE / COV_SUB;          // 16
-constexpr int COV_BINS = 1024;                        // depth bins 0..1022 exact, 1023 = overflow
+constexpr int COV_BINS = 512;                         // depth bins 0..510 exact, 511 = overflow (2 KB of shared
+                                                      // memory per warp: 16 warps per SM in cov_stream_kernel; 1024
+                                                      // bins: 14 warps, 4.5 % slower on C3)
 constexpr int COV_EV_TILE = 2048;                     // events per scatter CTA
 constexpr int COV_DEEP_BINS = 8192;
 
@@ -636,8 +638,8 @@ __global__ void cov_check_kernel(const uint32_t *__restrict__ starts, const uint
 
 constexpr int CT_CTAB = 96;  // contigs of a tile whose offsets are staged in shared memory
 // Deep pool: contigs whose depth leaves the shared histogram claim a row of it.  A dominant organism sequenced
-// beyond 1000x brings ALL its contigs here at once (hundreds), so the pool is wide rather than tall: 2048 rows of
-// 4096 bins (32 MB, cleared per sample).  Beyond that -- more deep contigs, or depth >= 5118 -- the sample is
+// beyond 500x brings ALL its contigs here at once (hundreds), so the pool is wide rather than tall: 2048 rows of
+// 4096 bins (32 MB, cleared per sample).  Beyond that -- more deep contigs, or depth >= 4606 -- the sample is
 // redone by the general path (2.5x slower, same results).  (256 rows x 32768 bins sent 2 of 80 C3-shaped
 // samples of an 8-GPU run down the general path: one rank at 87 ms per step, the others at 58.)
 constexpr int CT_DEEP_ROWS = 2048;    // contigs per sample that may exceed the shared histogram's depth range
