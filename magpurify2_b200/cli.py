@@ -1,5 +1,6 @@
 """`magpurify2 composition` / `magpurify2 coverage` command line (the two sub-commands of
-magpurify2/cli.py:244-412 that run on the GPU paths; same flags and defaults, cli.py:30-62).
+magpurify2/cli.py:244-412 that run on the GPU paths; same flags and defaults, cli.py:30-62) and
+`magpurify2 filter` (cli.py:544-600), which consumes their score tables.
 
     python -m magpurify2_b200.cli composition genomes/*.fna out
     python -m magpurify2_b200.cli coverage genomes/*.fna out --bam_files a.bam b.bam
@@ -18,6 +19,7 @@ default_values = {
     "coverage": {"min_identity": 0.97, "trim_lower": 0.05, "trim_upper": 0.05, "min_average_coverage": 1.0,
                  "n_iterations": 4, "n_components": 3, "min_dist": 0.15, "n_neighbors": 15,
                  "set_op_mix_ratio": 0.6},
+    "filter": {"probability_threshold": 0.5, "suffix": "filtered"},  # cli.py:61
 }
 
 
@@ -63,6 +65,20 @@ def build_parser():
     o.add_argument("--min_average_coverage", default=d["min_average_coverage"], type=float)
     _embedding_options(o, "coverage")
     _other(c.add_argument_group("Other options"))
+    f = sub.add_parser("filter", help="Remove putative contaminants using the scores of the modules.")
+    f.set_defaults(func=modules.filter.main)
+    f.add_argument("genomes", nargs="+", type=Path)
+    f.add_argument("output_directory", type=Path, help="The directory the modules wrote their scores to.")
+    f.add_argument("filtered_output_directory", type=Path, help="Directory for the filtered MAGs.")
+    o = f.add_argument_group("Data processing options")
+    o.add_argument("--checkm_file", type=Path, help="CheckM tabular file: thresholds as a function of MAG quality.")
+    o.add_argument("--probability_threshold", default=default_values["filter"]["probability_threshold"], type=float)
+    o.add_argument("--fast_mode", action="store_true",
+                   help="Use only the outputs of the composition and coverage modules.")
+    o.add_argument("--suffix", default=default_values["filter"]["suffix"], type=str)
+    o.add_argument("--model_file", type=Path,
+                   help="XGBoost JSON model (default: models/ of an installed magpurify2 package).")
+    _other(f.add_argument_group("Other options"))
     return parser
 
 

@@ -169,3 +169,52 @@ class Coverage:
             np.round(self.cluster_scores, 5),
             np.repeat(self.n_samples, len(self)),
         )
+
+
+class ContigClassifier:
+    """Mirror of magpurify2/core.py:527-583: contamination probability of every contig from the scores of
+    the modules (gradient-boosted trees), fixed or CheckM-driven probability threshold, and the
+    genome -> contig -> flagged dictionary the genome writer takes.  The model is evaluated by
+    `_xgb.XgbJsonModel` (the xgboost package is not needed)."""
+
+    def __init__(self, genome_contig_matrix, feature_matrix, model_file, fast_mode, probability_threshold,
+                 checkm_file=None, threads=1):
+        from collections import defaultdict
+
+        from . import tools
+        from ._xgb import XgbJsonModel
+
+        self.attributes = ["genome", "contig", "contaminant_probability"]
+        self.fast_mode = fast_mode
+        self.base_probability_threshold = probability_threshold
+        genome_contig_matrix = np.asarray(genome_contig_matrix).reshape(-1, 2)
+        self.genomes = genome_contig_matrix[:, 0]
+        self.contigs = genome_contig_matrix[:, 1]
+        self.probabilities = XgbJsonModel(model_file).predict(np.asarray(feature_matrix).reshape(len(self.genomes), -1))
+        self.probability_threshold = probability_threshold
+        if checkm_file:
+            checkm_scores = tools.get_checkm_contamination(checkm_file)
+            if checkm_scores:
+                tools.logger.info("Using completeness and contamination estimates to set dynamic thresholds.")
+                if len(set(self.genomes)) > len(checkm_scores):
+                    tools.logger.warning(
+                        "The input CheckM tabular file does not contain all the genomes being filtered. The default "
+                        f"probability threshold ({self.base_probability_threshold}) will be used for the genomes not "
+                        "found in it.")
+                self.probability_threshold = self.get_dynamic_thresholds(checkm_scores)
+        self.flagged_contaminants = self.probabilities > self.probability_threshold
+        self.mags_contaminants_dict = defaultdict(dict)
+        for genome, contig, flagged in zip(self.genomes, self.contigs, self.flagged_contaminants):
+            self.mags_contaminants_dict[genome][contig] = bool(flagged)
+
+    def get_dynamic_thresholds(self, checkm_scores):  # core.py:585-596
+        thresholds = np.array([
+            0.85 + 0.72 * (np.exp(-0.141 * checkm_scores[g]) - 1) if g in checkm_scores
+            else self.base_probability_threshold for g in self.genomes])
+        return np.clip(thresholds, 0.1, 0.85)
+
+    def __len__(self):
+        return len(self.probabilities)
+
+    def __iter__(self):
+        return zip(self.genomes, self.contigs, np.round(self.probabilities, 5))

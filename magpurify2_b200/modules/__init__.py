@@ -1,1 +1,1 @@
-from . import composition, coverage  # noqa: F401
+from . import composition, coverage, filter  # noqa: F401

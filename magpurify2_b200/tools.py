@@ -159,3 +159,48 @@ def write_module_output(score_list, score_output_file):  # tools.py:607-626
             for attributes in mag_score:
                 line = "\t".join(map(str, attributes))
                 fout.write(f"{line}\n")
+
+
+def get_checkm_contamination(filepath):
+    """{genome: contamination} from a CheckM tabular file (`checkm qa --tab_table`), None when the file is
+    missing or lacks the 'Bin Id' / 'Completeness' / 'Contamination' columns (tools.py:629-670)."""
+    import csv
+    from pathlib import Path
+
+    filepath = Path(filepath)
+    if not filepath.exists():
+        logger.warning("The supplied CheckM tabular file was not found. The default probability threshold value "
+                       "will be used instead.")
+        return None
+    with open(filepath) as fin:
+        reader = csv.reader(fin, delimiter="\t")
+        fields = next(reader, [])
+        if not {"Bin Id", "Completeness", "Contamination"}.issubset(fields):
+            logger.warning("The supplied CheckM tabular file is not correctly formatted. The default probability "
+                           "threshold value will be used instead.")
+            return None
+        bin_col, cont_col = fields.index("Bin Id"), fields.index("Contamination")
+        return {row[bin_col]: float(row[cont_col]) for row in reader if row}
+
+
+def write_filtered_genome(mag, mags_contaminants_dict, filtered_output_directory, suffix):
+    """FASTA of the contigs of `mag` that were not flagged (tools.py:673-699): '>description', sequence wrapped
+    at 70 columns; genomes absent from the dictionary are skipped."""
+    import textwrap
+    from pathlib import Path
+
+    if mag.genome not in mags_contaminants_dict:
+        return None
+    name = f"{mag.genome}.{suffix}.fna" if suffix else f"{mag.genome}.fna"
+    output_fna = Path(filtered_output_directory).joinpath(name)
+    flagged = mags_contaminants_dict[mag.genome]
+    with open(output_fna, "w") as fout:
+        for contig, description, sequence in mag:
+            if flagged[contig]:
+                continue
+            fout.write(f">{description}\n")
+            if any(c in sequence for c in "- \t"):  # textwrap may break at hyphens / blanks: keep its behaviour
+                fout.write(f"{textwrap.fill(sequence, 70)}\n")
+            else:
+                fout.write("\n".join(sequence[o:o + 70] for o in range(0, len(sequence), 70)) + "\n")
+    return output_fna
