@@ -178,3 +178,39 @@ def test_filter_cli_end_to_end(tmp_path):
     if filter_module.find_model_file(True) is None:
         with pytest.raises(SystemExit):
             cli.cli(["filter", str(genomes / "g2.fna"), str(out), str(tmp_path / "f2"), "--fast_mode", "-q"])
+
+
+def test_glue_matches_reference_golden(tmp_path, golden_dir):
+    """Feature transformations, dynamic thresholds and the CheckM reader against vectors produced by the
+    reference's own code (tests/golden/make_filter_golden.py lifts it with `ast`)."""
+    import logging
+
+    gold = json.load(open(os.path.join(golden_dir, "filter_golden.json")))
+    for case in gold["transforms"]:
+        x = np.array(case["input"])
+        modules = ["composition", "coverage"] if case["fast_mode"] else ["composition", "coverage", "codon_usage", "taxonomy"]
+        ncols = {"composition": 3, "coverage": 3, "codon_usage": 5, "taxonomy": 4}
+        header = {"composition": "genome\tcontig\ttnf_score\tgc_content_score\tcontig_length",
+                  "coverage": "genome\tcontig\tcoverage_score\tcoverage_cluster_score\tn_samples",
+                  "codon_usage": "genome\tcontig\ta\tb\tc\td\te", "taxonomy": "genome\tcontig\ta\tb\tc\td"}
+        d = tmp_path / ("fast" if case["fast_mode"] else "full") / "scores"
+        d.mkdir(parents=True)
+        col = 0
+        for m in modules:
+            with open(d / f"{m}_scores.tsv", "w") as f:
+                f.write(header[m] + "\n")
+                for i, row in enumerate(x[:, col:col + ncols[m]]):
+                    f.write(f"g\tc{i}\t" + "\t".join(repr(float(v)) for v in row) + "\n")
+            col += ncols[m]
+        _names, got = filter_module.load_features(d, modules, logging.getLogger("t"))
+        assert np.array_equal(got, np.array(case["output"])), case["fast_mode"]
+    stump = make_model(tmp_path / "stump.json", [tree([1, -1, -1], [2, -1, -1], [0, 0, 0], [0.5, 2.0, -2.0], [True, False, False])], 6)
+    for case in gold["thresholds"]:
+        names = np.array([[g, f"c{i}"] for i, g in enumerate(case["genomes"])])
+        c = ContigClassifier(names, np.zeros((len(names), 6)), stump, True, case["base"])
+        assert np.array_equal(c.get_dynamic_thresholds(case["checkm"]), np.array(case["output"])), case["base"]
+    for case in gold["checkm"]:
+        p = tmp_path / f"{case['name']}.tsv"
+        if case["text"] is not None:
+            p.write_text(case["text"])
+        assert tools.get_checkm_contamination(p) == case["output"], case["name"]
