@@ -1119,16 +1119,24 @@ __device__ __noinline__ int4 c3_seek(const int64_t *__restrict__ ev_off, const i
     return make_int4((int)c, clamp_rel(ev_off[c + 1] - e_base), clamp_rel(o0 - run_lo), (int)(off[c + 1] - o0));
 }
 
-__global__ void __launch_bounds__(32)
+#ifndef MP2_C3_WPC
+#define MP2_C3_WPC 1
+#endif
+constexpr int C3_WPC = MP2_C3_WPC;  // warps per CTA: each works alone on its own slice of the shared memory; more
+                                    // than one only spreads the 1 KB the system reserves per CTA over more warps
+
+__global__ void __launch_bounds__(32 * C3_WPC)
 cov_stream_kernel(const __grid_constant__ TileArgs a) {
-    __shared__ __align__(16) int32_t s_T[C3_WORDS];
-    __shared__ uint32_t s_hist[COV_BINS];
+    __shared__ __align__(16) int32_t s_T_all[C3_WPC][C3_WORDS];
+    __shared__ uint32_t s_hist_all[C3_WPC][COV_BINS];
+    int32_t *s_T = s_T_all[threadIdx.x >> 5];
+    uint32_t *s_hist = s_hist_all[threadIdx.x >> 5];
     if (a.check && a.check[0] != 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) *a.gate_out = 1;
         return;
     }
     if (*((volatile int *)a.gate_out)) return;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const uint32_t h0 = smem_base_opaque(s_hist), sT0 = smem_base_opaque(s_T);
     const int excl = (int)a.tp.excl;
     const uint32_t span = a.span_dev ? *a.span_dev : a.span_host;  // <= C3_S (cov_bounds_run_kernel gates otherwise)
@@ -1494,12 +1502,12 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
             Launch L("cov_tile_kernel", stream);
             cov_tile_kernel<<<(unsigned)grid, COV_THREADS, CT_SMEM, stream>>>(t);
         } else {
-            MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_stream_kernel, 32, 0));
+            MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_stream_kernel, 32 * C3_WPC, 0));
             if (occ < 1) occ = 1;
             int64_t grid = (int64_t)num_sms() * occ;
-            if (grid > n_units) grid = n_units;
+            if (grid * C3_WPC > n_units) grid = (n_units + C3_WPC - 1) / C3_WPC;
             Launch L("cov_stream_kernel", stream);
-            cov_stream_kernel<<<(unsigned)grid, 32, 0, stream>>>(t);
+            cov_stream_kernel<<<(unsigned)grid, 32 * C3_WPC, 0, stream>>>(t);
         }
         MP2_CUDA(cudaGetLastError());
     }
