@@ -11,7 +11,10 @@
 
 namespace mp2 {
 
-constexpr int WM_THREADS = 256;
+#ifndef MP2_WM_THREADS
+#define MP2_WM_THREADS 256
+#endif
+constexpr int WM_THREADS = MP2_WM_THREADS;  // threads of a weighted-median CTA (sweep: tools/gpu_wm_sweep.sh)
 constexpr int WM_SMEM_CAP = 1024;  // (value, weight) pairs sorted in shared memory (16 KB: 8 CTAs per SM); larger MAGs use scratch
 
 struct VW {
