@@ -165,21 +165,48 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     main_stream = torch.cuda.current_stream()
     lanes = (main_stream,) + tuple(torch.cuda.Stream(device=dev) for _ in range(max(1, args.cov_streams) - 1))
 
-    def step(lanes=lanes):
+    def step(lanes=lanes, which=None, span=None, disorder=0, score=True):
+        which = samples if which is None else which
+        span = args.max_span if span is None else span
         for ls in lanes[1:]:
             ls.wait_stream(main_stream)
-        for s, (st, en, eo, R) in enumerate(samples):
+        for s, (st, en, eo, R) in enumerate(which):
             _lib.check(lib.mp2_cov_events_device(st.data_ptr(), en.data_ptr(), eo.data_ptr(), d_off.data_ptr(),
-                                                 n, R, L, args.max_span, 75, args.trim, args.trim,
+                                                 n, R, L, span, disorder, 75, args.trim, args.trim,
                                                  cov.data_ptr() + 4 * s, S, None, lanes[s % len(lanes)].cuda_stream))
         for ls in lanes[1:]:
             main_stream.wait_stream(ls)
+        if not score:
+            return
         # core.Coverage: samples with length-weighted mean coverage >= 1, then base-25 log-ratio score
         _lib.check(lib.mp2_select_samples_device(cov.data_ptr(), d_len.data_ptr(), d_mag_off.data_ptr(), n_mags, n, S,
                                                  1.0, d_sel.data_ptr(), None, stream))
         _lib.check(lib.mp2_logratio_device(cov.data_ptr(), d_len.data_ptr(), d_mag_off.data_ptr(), n_mags, n, S,
                                            d_sel.data_ptr(), 25.0, 1e-5, 0.0, 1.0, 3, 0, d_score.data_ptr(), None,
                                            stream))
+
+    def timed(**kw):
+        """ms per step of `steps` steps (device events on the launching stream), after one untimed step."""
+        step(**kw)
+        torch.cuda.synchronize()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for _ in range(args.steps):
+            step(**kw)
+        b_.record()
+        torch.cuda.synchronize()
+        return a_.elapsed_time(b_) / args.steps
+
+    def path_of(sample, span, disorder):
+        """Which path computed one sample: share of the contigs (with a window) the general path wrote."""
+        st, en, eo, R = sample
+        d_stats = torch.zeros(n * 56, dtype=torch.uint8, device=dev)
+        _lib.check(lib.mp2_cov_events_device(st.data_ptr(), en.data_ptr(), eo.data_ptr(), d_off.data_ptr(), n, R, L,
+                                             span, disorder, 75, args.trim, args.trim, cov.data_ptr(), S,
+                                             d_stats.data_ptr(), stream))
+        torch.cuda.synchronize()
+        fl = d_stats.cpu().numpy().view(_lib.COV_STATS_DTYPE)["flags"]
+        return "general (difference array in HBM)" if (fl & 1).any() else "shared-memory streaming kernel"
 
     for _ in range(args.warmup):
         step()
@@ -210,12 +237,37 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     barrier()
     ms_one_stream = e2.elapsed_time(e3)
     kern = {}
-    for name in ("cov_stream_kernel", "cov_tile_kernel", "cov_scatter_kernel", "cov_depth_kernel", "cov_deep_kernel",
-                 "cov_check_kernel", "cov_bounds_kernel", "cov_zero_kernel"):
+    for name in ("cov_stream2_kernel", "cov_stream_kernel", "cov_tile_kernel", "cov_scatter_kernel", "cov_depth_kernel",
+                 "cov_deep_kernel", "cov_keymax_kernel", "cov_keyscan_kernel", "cov_check_kernel", "cov_bounds_kernel",
+                 "cov_zero_kernel"):
         k_ms, k_n = C.c_double(0), C.c_int64(0)
         lib.mp2_profile_read(name.encode(), C.byref(k_ms), C.byref(k_n))
         kern[name] = (k_ms.value, k_n.value)
     lib.mp2_profile_enable(0)
+    # ---- secondary legs (N = 1 only): the same samples with the order vouched for instead of measured, and
+    # SURVEY 8(d)'s variant (read length N(150,15), 2 % of the reads with one I / D = two blocks, out of order)
+    legs = {}
+    if world == 1 and args.cov_legs:
+        legs["headline_path"] = path_of(samples[0], args.max_span, 0)
+        legs["order_vouched_ms_per_sample"] = timed(span=150, disorder=0, score=False) / S
+        legs["order_measured_ms_per_sample"] = timed(span=0, disorder=0, score=False) / S
+        nv = max(1, min(S, args.variant_samples))
+        var = [synth.make_events_device(lengths, mag_off, s, dev, seed=args.seed + 1000 * rank,
+                                        depth_scale=args.depth_scale, variant=True) for s in range(nv)]
+        Rv = sum(v[3] for v in var)
+        t_meas = timed(which=var, span=0, disorder=0, score=False) / nv
+        t_vouch = timed(which=var, span=250, disorder=250, score=False) / nv
+        legs["variant"] = {
+            "workload": "read length N(150,15) clipped to [50,250], 2 % of the reads with one 1-3 bp I or D (two "
+                        "blocks; the second one starts after the next reads' first blocks)",
+            "samples": nv, "blocks_per_sample": Rv / nv,
+            "ms_per_sample_order_measured": t_meas, "ms_per_sample_order_vouched": t_vouch,
+            "reads_per_s_order_measured": Rv / nv / (t_meas * 1e-3),
+            "path": path_of(var[0], 0, 0),
+        }
+        del var
+        step()  # leave `cov` holding the headline samples for the checks below
+        torch.cuda.synchronize()
     ms_ranks = [ms]
     if world > 1:
         g = torch.zeros(world, 3, dtype=torch.float64, device=dev)
@@ -263,13 +315,14 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     moved = {"cov_stream_kernel": 8.0 * R_avg + 24.0 * (L / 65536.0) + 4.0 * n,
              "cov_tile_kernel": 8.0 * R_avg + 24.0 * (L / 16384.0) + 4.0 * n,
              "cov_depth_kernel": 4.0 * (L + 1), "cov_scatter_kernel": 8.0 * R_avg + 8.0 * R_avg}
+    moved["cov_stream2_kernel"] = moved["cov_stream_kernel"]
     sample_ms = ms_one_stream / args.steps / S  # per sample when the samples run one after the other
     rl = []
-    for name in ("cov_stream_kernel", "cov_tile_kernel", "cov_depth_kernel", "cov_scatter_kernel"):
+    for name in ("cov_stream2_kernel", "cov_stream_kernel", "cov_tile_kernel", "cov_depth_kernel", "cov_scatter_kernel"):
         t_ms = per_launch(name)
         if t_ms < 0.02 * sample_ms:  # not launched, or gated off (exits at once): not on the path of this run
             continue
-        fused = name in ("cov_stream_kernel", "cov_tile_kernel")  # one kernel does the whole sample
+        fused = name in ("cov_stream2_kernel", "cov_stream_kernel", "cov_tile_kernel")  # one kernel does the whole sample
         bytes_ = sample_bytes if fused else moved[name]
         ach = bytes_ / (t_ms * 1e-3) / 1e9
         r = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -287,6 +340,8 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
         "config": {"workload": f"C3: coverage of {args.mags} MAGs x {S} samples per GPU, {R_total / S / 1e6:.0f} M aligned blocks/sample",
                    "samples": S, "reads_per_step": R_total, "positions": L, "trim": args.trim, "end_exclusion": 75,
                    "input": "(start,end) uint32 pairs grouped by contig, resident in HBM",
+                   "order": ("block span and start disorder measured on the device inside the timed region"
+                             if args.max_span == 0 else f"vouched by the caller: span <= {args.max_span}, sorted"),
                    "streams": len(lanes),
                    "note": "kernel_ms / roofline are from a second pass of the same steps on one stream"},
         "ms_per_step_one_stream": ms_one_stream / args.steps,
@@ -301,6 +356,9 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
                 "api": "magpurify2_b200._coverage.cov_from_events (mp2_cov_events, pinned host buffers, 1 sample)"},
         "gpu_launches": int(launches),
         "deep_fallback_ms": kern["cov_deep_kernel"][0] / max(1, kern["cov_deep_kernel"][1]),
+        "order_check_ms_per_sample": sum(kern[k][0] for k in ("cov_keymax_kernel", "cov_keyscan_kernel", "cov_check_kernel"))
+                                     / max(1, args.steps * S),
+        "legs": legs,
     }
     if not args.no_cpu:
         import oracle
@@ -416,7 +474,12 @@ def main():
     ap.add_argument("--long-contigs", action="store_true", help="C5 shape instead of C3")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--trim", type=float, default=0.05)
-    ap.add_argument("--max-span", type=int, default=150, help="0 = let the library check BAM order on the device")
+    ap.add_argument("--max-span", type=int, default=0,
+                    help="0 (default) = the library measures block span and start disorder on the device, inside the "
+                         "timed region; > 0 = vouched by the caller, as the BAM decoder does for its own output")
+    ap.add_argument("--no-cov-legs", dest="cov_legs", action="store_false",
+                    help="skip the secondary coverage legs (vouched order, indel variant)")
+    ap.add_argument("--variant-samples", type=int, default=2)
     ap.add_argument("--depth-scale", type=float, default=1.0)
     ap.add_argument("--cov-streams", type=int, default=1,
                     help="streams the coverage samples alternate between (2: 51..91 ms per C3 step, unstable; 1: 59.9 ms)")

@@ -100,8 +100,10 @@ typedef struct {
     uint64_t total;        /* integer numerator of the trimmed mean             */
     uint64_t max_depth;    /* highest occupied depth                            */
     float coverage;        /* (f32)total / (f32)(max_index - min_index)         */
-    uint32_t flags;        /* reserved (0)                                      */
+    uint32_t flags;        /* MP2_COV_GENERAL_PATH when the general path computed it */
 } mp2_cov_stats;
+
+#define MP2_COV_GENERAL_PATH 1u /* mp2_cov_stats.flags: difference array went through HBM (fallback) */
 
 /* Alignment blocks (the M/=/X runs of the reads that passed the filters), grouped by contig
  * in BAM order: block e of contig c is [starts[e], ends[e]) for ev_off[c] <= e < ev_off[c+1],
@@ -111,25 +113,34 @@ typedef struct {
  *   d_cov   : float32, element c at d_cov[c*cov_stride] -- cov_stride = n_bams writes column s of
  *             the reference's float32[n_contigs, n_bams] matrix in place        (REQUIRED)
  *   d_stats : mp2_cov_stats[n_contigs]    or NULL
- * max_span: > 0 = the caller guarantees that starts are non-decreasing inside every contig (BAM
- *           coordinate order) and that end - start <= max_span for every block: the difference
- *           array is then built tile by tile in shared memory and never touches HBM.
- *           0 = unknown: the library checks both on the device first and falls back to the
- *           general path (difference array in HBM, any order) when the starts are not sorted.
+ * max_span, max_disorder: what the caller knows about the order of the blocks inside a contig.
+ *           max_span > 0 = the caller guarantees that end - start <= max_span for every block and that
+ *           no start lies more than max_disorder below the largest start before it in the same contig
+ *           (0 = starts non-decreasing).  A coordinate-sorted BAM is ordered by READ position, so the
+ *           second block of a read with a D / N operation starts after the first blocks of the next
+ *           reads: its disorder is bounded by the reference footprint of a read, not zero (mp2_bam_open
+ *           reports both numbers).  With max_span + max_disorder <= 512 the difference array is built
+ *           window by window in shared memory and never touches HBM; anything else takes the general
+ *           path (difference array in HBM, any order, any span).
+ *           max_span = 0 = nothing is known: both numbers are measured on the device first (three small
+ *           kernels, one extra pass over the events) and the path is chosen from them.
+ * The call returns after the sample's kernels were enqueued AND the 4-byte "fall back" flag of the fast
+ * path was read (one stream synchronisation): the general path's scratch (4 bytes per position) is only
+ * allocated when it is needed.
  * Contigs that reach depth >= 511 are counted in a pool of global histograms (2048 contigs per call, depth
  * < 4607); a sample that needs more goes through the general path (exact for any depth).
  * trim_lower + trim_upper must be < 1 (the CLI clamps both, magpurify2/modules/coverage.py:39-49). */
 int mp2_cov_events_device(const void *d_starts, const void *d_ends, const void *d_ev_off,
                           const void *d_contig_off, int64_t n_contigs, int64_t n_events,
-                          int64_t n_positions, uint32_t max_span, uint32_t end_excl,
-                          float trim_lower, float trim_upper, void *d_cov, int64_t cov_stride,
-                          void *d_stats, void *stream);
+                          int64_t n_positions, uint32_t max_span, uint32_t max_disorder,
+                          uint32_t end_excl, float trim_lower, float trim_upper, void *d_cov,
+                          int64_t cov_stride, void *d_stats, void *stream);
 
 /* Host-buffer form of the same call (stages H2D/D2H itself). */
 int mp2_cov_events(const uint32_t *starts, const uint32_t *ends, const int64_t *ev_off,
                    const int64_t *contig_off, int64_t n_contigs, int64_t n_events,
-                   uint32_t max_span, uint32_t end_excl, float trim_lower, float trim_upper,
-                   int device, float *cov, int64_t cov_stride, mp2_cov_stats *stats);
+                   uint32_t max_span, uint32_t max_disorder, uint32_t end_excl, float trim_lower,
+                   float trim_upper, int device, float *cov, int64_t cov_stride, mp2_cov_stats *stats);
 
 /* ---- scoring: replaces tools.get_log_ratio_scores / get_weighted_median ----------------- */
 /* (magpurify2/tools.py:283-351; callers magpurify2/core.py:261-263 base 2, :310-312 base 25) */
@@ -183,7 +194,10 @@ int64_t mp2_bam_n_contigs(const mp2_bam *b);
 int64_t mp2_bam_n_events(const mp2_bam *b);
 int64_t mp2_bam_n_records(const mp2_bam *b);      /* records seen                      */
 int64_t mp2_bam_n_kept(const mp2_bam *b);         /* records that passed the filters   */
-uint32_t mp2_bam_max_span(const mp2_bam *b);
+uint32_t mp2_bam_max_span(const mp2_bam *b);      /* longest reference footprint of a kept read      */
+uint32_t mp2_bam_max_block(const mp2_bam *b);     /* longest M/=/X block (mp2_cov_events' max_span)  */
+uint32_t mp2_bam_max_disorder(const mp2_bam *b);  /* largest (block start - read position): bounds how far a
+                                                     start can lie below the largest start before it       */
 const char *mp2_bam_contig_name(const mp2_bam *b, int64_t i);
 const int64_t *mp2_bam_contig_len(const mp2_bam *b);
 const int64_t *mp2_bam_ev_off(const mp2_bam *b);

@@ -23,7 +23,9 @@ class BamEvents:
         self.n_events = ne
         self.n_records = lib.mp2_bam_n_records(h)
         self.n_kept = lib.mp2_bam_n_kept(h)
-        self.max_span = lib.mp2_bam_max_span(h)
+        self.max_span = lib.mp2_bam_max_span(h)          # longest reference footprint of a kept read
+        self.max_block = lib.mp2_bam_max_block(h)        # longest M/=/X block
+        self.max_disorder = lib.mp2_bam_max_disorder(h)  # largest (block start - read position)
         if ne:
             self.starts = np.ctypeslib.as_array(C.cast(lib.mp2_bam_starts(h), C.POINTER(C.c_uint32)), (ne,))
             self.ends = np.ctypeslib.as_array(C.cast(lib.mp2_bam_ends(h), C.POINTER(C.c_uint32)), (ne,))

@@ -17,13 +17,15 @@ COV_STATS_DTYPE = _lib.COV_STATS_DTYPE
 
 
 def cov_from_events(starts, ends, ev_off, contig_off, contig_end_exclusion=75, trim_lower=0.0,
-                    trim_upper=0.0, want_stats=False, device=-1, max_span=0):
+                    trim_upper=0.0, want_stats=False, device=-1, max_span=0, max_disorder=0):
     """One sample on host arrays: alignment blocks grouped by contig -> trimmed-mean coverage.
 
     starts/ends: uint32[n_events] (0-based start, exclusive end, relative to the contig);
     ev_off: int64[n_contigs+1]; contig_off: int64[n_contigs+1] cumulative contig lengths.
-    max_span > 0 vouches for BAM order (starts sorted inside a contig, end - start <= max_span);
-    0 lets the library check on the device.
+    max_span > 0 vouches for the order of the blocks: end - start <= max_span, and no start more than
+    max_disorder below the largest start before it in its contig (0 = sorted; a BAM with D / N
+    operations is not: BamEvents reports both numbers).  max_span = 0 lets the library measure both
+    on the device.
     Returns float32[n_contigs] (and the per-contig integer statistics when want_stats)."""
     starts = np.ascontiguousarray(starts, dtype=np.uint32)
     ends = np.ascontiguousarray(ends, dtype=np.uint32)
@@ -36,13 +38,13 @@ def cov_from_events(starts, ends, ev_off, contig_off, contig_end_exclusion=75, t
     stats = np.zeros(n, dtype=COV_STATS_DTYPE) if want_stats else None
     lib = _lib.load()
     _lib.check(lib.mp2_cov_events(_lib.ptr(starts), _lib.ptr(ends), _lib.ptr(ev_off), _lib.ptr(contig_off),
-                                  n, len(starts), int(max_span), int(contig_end_exclusion), float(trim_lower),
+                                  n, len(starts), int(max_span), int(max_disorder), int(contig_end_exclusion), float(trim_lower),
                                   float(trim_upper), device, _lib.ptr(cov), 1, _lib.ptr(stats)))
     return (cov, stats) if want_stats else cov
 
 
 def get_bam_coverages(bam_list, contig_end_exclusion=75, min_identity=0.97, trim_lower=0.0, trim_upper=0.0,
-                      contig_set=None, threads=1):
+                      contig_set=None, threads=1, *, device=-1, stats_out=None):
     """Trimmed-mean coverage of every contig in every BAM (src/coverage.rs:81-206).
 
     Returns (names, float32[n_contigs, n_bams]); columns follow bam_list.  Rows follow the @SQ
@@ -65,10 +67,15 @@ def get_bam_coverages(bam_list, contig_end_exclusion=75, min_identity=0.97, trim
                 np.cumsum(lengths, out=contig_off[1:])
             elif b.names != names:
                 raise ValueError(f"{path}: @SQ lines differ from {bam_list[0]} (the reference assumes identical headers)")
-            # the reader emits blocks in BAM order; blocks of a spliced read can start before the
-            # next read's first block, so sortedness is left to the device check (max_span=0)
-            cols.append(cov_from_events(b.starts, b.ends, b.ev_off, contig_off, contig_end_exclusion,
-                                        trim_lower, trim_upper))
+            # the reader emits blocks in BAM order and measures, while it decodes, the longest block and how
+            # far a block of a read with D / N operations can start behind the next reads' first blocks
+            res = cov_from_events(b.starts, b.ends, b.ev_off, contig_off, contig_end_exclusion,
+                                  trim_lower, trim_upper, device=device, max_span=b.max_block,
+                                  max_disorder=b.max_disorder, want_stats=stats_out is not None)
+            if stats_out is not None:  # per-contig integers of every BAM (tests: which path computed them)
+                stats_out.append(res[1])
+                res = res[0]
+            cols.append(res)
     if not names:
         raise ValueError("no reference sequences in the BAM header")  # the reference panics (coverage.rs:200)
     mat = np.stack(cols, axis=1).astype(np.float32, copy=False)

@@ -65,8 +65,8 @@ SIGNATURES = {
     "mp2_tnf_device": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "mp2_tnf_packed_device": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "mp2_pack_device": (_i32, [_vp, _i64, _vp, _vp, _vp]),
-    "mp2_cov_events_device": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _u32, _u32, _f32, _f32, _vp, _i64, _vp, _vp]),
-    "mp2_cov_events": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _u32, _u32, _f32, _f32, _i32, _vp, _i64, _vp]),
+    "mp2_cov_events_device": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _u32, _u32, _u32, _f32, _f32, _vp, _i64, _vp, _vp]),
+    "mp2_cov_events": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _u32, _u32, _u32, _f32, _f32, _i32, _vp, _i64, _vp]),
     "mp2_logratio_device": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _f64, _f32, _f64, _f64, _i64, _i32, _vp, _vp, _vp]),
     "mp2_logratio": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _f64, _f32, _f64, _f64, _i64, _i32, _i32, _vp, _vp]),
     "mp2_select_samples_device": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _f64, _vp, _vp, _vp]),
@@ -77,6 +77,8 @@ SIGNATURES = {
     "mp2_bam_n_records": (_i64, [_vp]),
     "mp2_bam_n_kept": (_i64, [_vp]),
     "mp2_bam_max_span": (_u32, [_vp]),
+    "mp2_bam_max_block": (_u32, [_vp]),
+    "mp2_bam_max_disorder": (_u32, [_vp]),
     "mp2_bam_contig_name": (C.c_char_p, [_vp, _i64]),
     "mp2_bam_contig_len": (_vp, [_vp]),
     "mp2_bam_ev_off": (_vp, [_vp]),

@@ -10,9 +10,11 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -23,9 +25,10 @@ struct mp2_bam {
     std::vector<int64_t> lens;
     std::vector<int64_t> ev_off;
     uint32_t *starts = nullptr, *ends = nullptr;
-    bool pinned = false;
+    size_t cap_s = 0, cap_e = 0;  // bytes of the two blocks (they go back to the pinned pool)
+    bool pinned = false, pin_s = false, pin_e = false;
     int64_t n_events = 0, n_records = 0, n_kept = 0;
-    uint32_t max_span = 0;
+    uint32_t max_span = 0, max_block = 0, max_disorder = 0;
     std::string header_text;
 };
 
@@ -89,16 +92,53 @@ static bool inflate_block(const uint8_t *f, const Block &b, uint8_t *dst) {
     return ok;
 }
 
+// Aux field `t0 t1` of a record: pointer to its value and its type, or NULL.  *bad is set when the aux
+// area is malformed.
+static const uint8_t *find_aux(const uint8_t *a, const uint8_t *end, char t0, char t1, uint8_t &type, bool &bad) {
+    while (a + 3 <= end) {
+        const uint8_t k0 = a[0], k1 = a[1], ty = a[2];
+        a += 3;
+        size_t sz = 0;
+        switch (ty) {
+        case 'A': case 'c': case 'C': sz = 1; break;
+        case 's': case 'S': sz = 2; break;
+        case 'i': case 'I': case 'f': sz = 4; break;
+        case 'Z': case 'H': {
+            const uint8_t *z = (const uint8_t *)memchr(a, 0, end - a);
+            if (!z) { bad = true; return nullptr; }
+            sz = (z - a) + 1;
+            break;
+        }
+        case 'B': {
+            if (a + 5 > end) { bad = true; return nullptr; }
+            const uint8_t st = a[0];
+            const uint32_t cnt = rd32(a + 1);
+            const size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+            sz = 5 + es * (size_t)cnt;
+            break;
+        }
+        default: bad = true; return nullptr;
+        }
+        if (a + sz > end) { bad = true; return nullptr; }
+        if (k0 == (uint8_t)t0 && k1 == (uint8_t)t1) { type = ty; return a; }
+        a += sz;
+    }
+    return nullptr;
+}
+
 // One record -> alignment blocks, straight from the BAM wire format.
-// Returns the number of M/=/X blocks (0 = dropped),
-// -1 = NM tag missing, -2 = malformed.  The first block goes to (s0, e0).
-static int record_blocks(const uint8_t *r, uint32_t block_size, float min_identity, int32_t &tid, uint32_t &s0,
-                         uint32_t &e0, uint32_t *more_s, uint32_t *more_e, int max_more) {
+// Returns the number of M/=/X blocks (0 = dropped), -1 = NM tag missing, -2 = malformed.  The first block
+// goes to (s0, e0), the others to more_s / more_e (when given); `pos` is the record's position.
+// A read with more than 65535 CIGAR operations keeps its real CIGAR in the CG:B,I tag behind a
+// placeholder "<l_seq>S<ref_len>N" (SAM spec 4.2.2); htslib, which the reference reads BAMs with, swaps it in
+// when the record is read, and so does this function.
+static int record_blocks(const uint8_t *r, uint32_t block_size, float min_identity, int32_t &tid, int32_t &pos,
+                         uint32_t &s0, uint32_t &e0, uint32_t *more_s, uint32_t *more_e, int max_more) {
     if (block_size < 32) return -2;
     tid = rds32(r);
-    const int32_t pos = rds32(r + 4);
+    pos = rds32(r + 4);
     const uint32_t l_read_name = r[8];
-    const uint32_t n_cigar = rd16(r + 12);
+    uint32_t n_cigar = rd16(r + 12);
     const uint32_t flag = rd16(r + 14);
     const uint32_t l_seq = rd32(r + 16);
     const uint64_t fixed = 32ull + l_read_name + 4ull * n_cigar + (l_seq + 1) / 2 + l_seq;
@@ -107,50 +147,36 @@ static int record_blocks(const uint8_t *r, uint32_t block_size, float min_identi
     if (flag & 0x800) return 0;  // supplementary  (src/coverage.rs:105)
     if ((flag & 0x4) || tid < 0 || pos < 0) return 0;  // unmapped: contributes nothing
     const uint8_t *cig = r + 32 + l_read_name;
+    const uint8_t *aux = r + fixed, *end = r + block_size;
+    if (n_cigar == 2) {
+        const uint32_t c0 = rd32(cig), c1 = rd32(cig + 4);
+        if ((c0 & 0xF) == 4 && (c0 >> 4) == l_seq && (c1 & 0xF) == 3) {  // placeholder: real CIGAR in CG:B,I
+            uint8_t ty = 0;
+            bool bad = false;
+            const uint8_t *v = find_aux(aux, end, 'C', 'G', ty, bad);
+            if (bad) return -2;
+            if (v && ty == 'B' && (v[0] == 'I' || v[0] == 'i')) {
+                n_cigar = rd32(v + 1);
+                cig = v + 5;
+            }
+        }
+    }
     if (min_identity > 0.0f) {
         // NM aux tag (required, as in coverm: the reference panics without it)
-        const uint8_t *a = r + fixed, *end = r + block_size;
-        int64_t nm = -1;
-        while (a + 3 <= end) {
-            const uint8_t t0 = a[0], t1 = a[1], ty = a[2];
-            a += 3;
-            int64_t val = 0;
-            size_t sz = 0;
-            switch (ty) {
-            case 'A': case 'c': case 'C': sz = 1; break;
-            case 's': case 'S': sz = 2; break;
-            case 'i': case 'I': case 'f': sz = 4; break;
-            case 'Z': case 'H': {
-                const uint8_t *z = (const uint8_t *)memchr(a, 0, end - a);
-                if (!z) return -2;
-                sz = (z - a) + 1;
-                break;
-            }
-            case 'B': {
-                if (a + 5 > end) return -2;
-                const uint8_t st = a[0];
-                const uint32_t cnt = rd32(a + 1);
-                const size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
-                sz = 5 + es * (size_t)cnt;
-                break;
-            }
-            default: return -2;
-            }
-            if (a + sz > end) return -2;
-            if (t0 == 'N' && t1 == 'M') {
-                switch (ty) {
-                case 'c': val = (int8_t)a[0]; break;
-                case 'C': val = a[0]; break;
-                case 's': val = (int16_t)rd16(a); break;
-                case 'S': val = rd16(a); break;
-                case 'i': val = rds32(a); break;
-                case 'I': val = rd32(a); break;
-                default: return -2;
-                }
-                nm = val;
-                break;
-            }
-            a += sz;
+        uint8_t ty = 0;
+        bool bad = false;
+        const uint8_t *v = find_aux(aux, end, 'N', 'M', ty, bad);
+        if (bad) return -2;
+        if (!v) return -1;
+        int64_t nm;
+        switch (ty) {
+        case 'c': nm = (int8_t)v[0]; break;
+        case 'C': nm = v[0]; break;
+        case 's': nm = (int16_t)rd16(v); break;
+        case 'S': nm = rd16(v); break;
+        case 'i': nm = rds32(v); break;
+        case 'I': nm = rd32(v); break;
+        default: return -2;
         }
         if (nm < 0) return -1;
         uint32_t aligned = 0;
@@ -178,17 +204,74 @@ static int record_blocks(const uint8_t *r, uint32_t block_size, float min_identi
     return nb;
 }
 
-static void *host_alloc(size_t bytes, bool &pinned) {
-    void *p = nullptr;
-    if (bytes == 0) bytes = 16;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) {
-        pinned = true;
-        return p;
+// ---- pinned host memory, pooled ------------------------------------------------------------------------
+// Page-locking is slow (tens of ms for a sample's events), so the blocks of a closed sample go back to a
+// small process-wide pool and the next sample decodes straight into them: in a run over many BAMs the
+// events are written once, into pinned memory, and copied to the device from there.
+struct PinBlock { void *p; size_t bytes; bool pinned; };
+static std::mutex g_pin_mu;
+static std::vector<PinBlock> g_pin_pool;
+constexpr size_t PIN_POOL_MAX = 8;
+
+static PinBlock pin_get(size_t bytes) {
+    if (bytes < 4096) bytes = 4096;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_pin_pool.size(); i++)
+            if (g_pin_pool[i].bytes >= bytes && (best < 0 || g_pin_pool[i].bytes < g_pin_pool[best].bytes)) best = (int)i;
+        if (best >= 0) {
+            PinBlock b = g_pin_pool[best];
+            g_pin_pool.erase(g_pin_pool.begin() + best);
+            return b;
+        }
     }
-    (void)cudaGetLastError();
-    pinned = false;
-    return malloc(bytes);
+    PinBlock b{nullptr, bytes, false};
+    if (cudaHostAlloc(&b.p, bytes, cudaHostAllocPortable) == cudaSuccess) {
+        b.pinned = true;
+    } else {
+        (void)cudaGetLastError();
+        b.p = malloc(bytes);
+    }
+    return b;
 }
+
+static void pin_put(PinBlock b) {
+    if (!b.p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (b.pinned && g_pin_pool.size() < PIN_POOL_MAX) {
+            g_pin_pool.push_back(b);
+            return;
+        }
+    }
+    if (b.pinned) cudaFreeHost(b.p);
+    else free(b.p);
+}
+
+// growable uint32 array in pooled pinned memory
+struct PinVec {
+    PinBlock blk{nullptr, 0, false};
+    size_t n = 0;
+    uint32_t *data() { return (uint32_t *)blk.p; }
+    bool reserve(size_t want, int threads) {
+        if (want * 4 <= blk.bytes) return true;
+        size_t cap = std::max(want * 4, blk.bytes + blk.bytes / 2);
+        PinBlock nb = pin_get(cap);
+        if (!nb.p) return false;
+        if (n) {
+            const size_t bytes = n * 4, grain = 1u << 20;
+            const int64_t parts = (int64_t)((bytes + grain - 1) / grain);
+#pragma omp parallel for schedule(static) num_threads(threads)
+            for (int64_t i = 0; i < parts; i++)
+                memcpy((char *)nb.p + i * grain, (const char *)blk.p + i * grain, std::min(grain, bytes - (size_t)i * grain));
+        }
+        pin_put(blk);
+        blk = nb;
+        return true;
+    }
+    ~PinVec() { pin_put(blk); }
+};
 
 }  // namespace mp2
 
@@ -242,7 +325,7 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
         }
         uint8_t *data() { return p; }
     } buf;
-    std::vector<uint32_t> ev_s, ev_e;  // accepted blocks in BAM order
+    PinVec ev_s, ev_e;  // accepted blocks in BAM order, decoded straight into (pooled) pinned memory
     std::vector<int64_t> per_tid;
     int64_t BATCH = 64ll << 20;  // uncompressed bytes inflated per round (MP2_BAM_BATCH_KB: test switch)
     if (const char *e = getenv("MP2_BAM_BATCH_KB")) {
@@ -252,11 +335,13 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
     size_t bi = 0;
     int64_t have = 0;   // valid bytes in buf
     bool header_done = false;
-    int64_t last_tid = -1;
+    int64_t last_tid = -1, last_pos = -1;
+    bool unsorted_pos = false;
     std::vector<int64_t> rec_off;
     std::vector<int32_t> rec_tid;
     std::vector<int32_t> rec_n;
     std::vector<uint32_t> rec_s, rec_e;
+    std::vector<int32_t> rec_pos;
 
     while (bi < blocks.size() || have > 0) {
         // ---- inflate the next batch of blocks behind the leftover bytes ----
@@ -342,15 +427,17 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
         rec_n.resize(nr);
         rec_s.resize(nr);
         rec_e.resize(nr);
+        rec_pos.resize(nr);
         std::atomic<int> err{0};
 #pragma omp parallel for schedule(static) num_threads(threads)
         for (int64_t i = 0; i < nr; i++) {
             const uint8_t *r = p + rec_off[i];
-            int32_t tid = -1;
+            int32_t tid = -1, rpos = 0;
             uint32_t s0 = 0, e0 = 0;
-            const int k = record_blocks(r + 4, rd32(r), min_identity, tid, s0, e0, nullptr, nullptr, 0);
+            const int k = record_blocks(r + 4, rd32(r), min_identity, tid, rpos, s0, e0, nullptr, nullptr, 0);
             if (k < 0) err = k == -1 ? 1 : 2;
             rec_tid[i] = tid;
+            rec_pos[i] = rpos;
             rec_n[i] = k;
             rec_s[i] = s0;
             rec_e[i] = e0;
@@ -364,7 +451,7 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
         // ---- merge: serial scan of the per-record block counts (order, totals), parallel fill ----
         std::vector<int64_t> ev_pos((size_t)nr + 1);
         {
-            int64_t pos = (int64_t)ev_s.size();
+            int64_t pos = (int64_t)ev_s.n;
             for (int64_t i = 0; i < nr; i++) {
                 ev_pos[i] = pos;
                 const int k = rec_n[i];
@@ -374,6 +461,9 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
                     return fail(MP2_EIO, "%s: record refers to an unknown reference", path);
                 if (tid < last_tid)
                     return fail(MP2_EFORMAT, "%s: records are not sorted by reference (SO:coordinate required)", path);
+                if (tid != last_tid) last_pos = -1;
+                if (rec_pos[i] < last_pos) unsorted_pos = true;
+                last_pos = rec_pos[i];
                 last_tid = tid;
                 b->n_kept++;
                 per_tid[tid] += k;
@@ -381,29 +471,37 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
             }
             ev_pos[nr] = pos;
             b->n_records += nr;
-            ev_s.resize((size_t)pos);
-            ev_e.resize((size_t)pos);
+            if (!ev_s.reserve((size_t)pos, threads) || !ev_e.reserve((size_t)pos, threads))
+                return fail(MP2_ENOMEM, "%s: out of host memory for %lld alignment blocks", path, (long long)pos);
+            ev_s.n = ev_e.n = (size_t)pos;
         }
-        uint32_t span_max = b->max_span;
-#pragma omp parallel for schedule(static) num_threads(threads) reduction(max : span_max)
+        uint32_t span_max = b->max_span, block_max = b->max_block, dis_max = b->max_disorder;
+        uint32_t *const out_s = ev_s.data(), *const out_e = ev_e.data();
+#pragma omp parallel for schedule(static) num_threads(threads) reduction(max : span_max, block_max, dis_max)
         for (int64_t i = 0; i < nr; i++) {
             const int k = rec_n[i];
             if (k <= 0) continue;
             const int64_t at = ev_pos[i];
+            const uint32_t rpos = (uint32_t)rec_pos[i];
             if (k == 1) {
-                ev_s[at] = rec_s[i];
-                ev_e[at] = rec_e[i];
-                const uint32_t span = rec_e[i] - rec_s[i];
-                span_max = span > span_max ? span : span_max;
+                out_s[at] = rec_s[i];
+                out_e[at] = rec_e[i];
             } else {
-                int32_t t2 = 0; uint32_t s0 = 0, e0 = 0;
+                int32_t t2 = 0, p2 = 0; uint32_t s0 = 0, e0 = 0;
                 const uint8_t *r = p + rec_off[i];
-                record_blocks(r + 4, rd32(r), min_identity, t2, s0, e0, &ev_s[at + 1], &ev_e[at + 1], k - 1);
-                ev_s[at] = s0; ev_e[at] = e0;
-                const uint32_t span = ev_e[at + k - 1] - s0;  // the whole read footprint bounds every block
-                span_max = span > span_max ? span : span_max;
+                record_blocks(r + 4, rd32(r), min_identity, t2, p2, s0, e0, out_s + at + 1, out_e + at + 1, k - 1);
+                out_s[at] = s0; out_e[at] = e0;
             }
+            for (int j = 0; j < k; j++) {
+                const uint32_t blk = out_e[at + j] - out_s[at + j], dis = out_s[at + j] - rpos;
+                block_max = blk > block_max ? blk : block_max;
+                dis_max = dis > dis_max ? dis : dis_max;   // how far this start can lie below a later read's
+            }
+            const uint32_t span = out_e[at + k - 1] - rpos;  // the whole read footprint
+            span_max = span > span_max ? span : span_max;
         }
+        b->max_block = block_max;
+        b->max_disorder = dis_max;
         b->max_span = span_max;
         t_mrg += omp_get_wtime() - t_x;
         // ---- keep the partial record for the next batch ----
@@ -420,21 +518,16 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
     const int64_t n = (int64_t)b->names.size();
     b->ev_off.assign(n + 1, 0);
     for (int64_t i = 0; i < n; i++) b->ev_off[i + 1] = b->ev_off[i] + per_tid[i];
-    b->n_events = (int64_t)ev_s.size();
-    bool pin1 = false, pin2 = false;
-    b->starts = (uint32_t *)host_alloc(sizeof(uint32_t) * ev_s.size(), pin1);
-    b->ends = (uint32_t *)host_alloc(sizeof(uint32_t) * ev_e.size(), pin2);
-    if (!b->starts || !b->ends) return fail(MP2_ENOMEM, "out of host memory for %lld events", (long long)b->n_events);
-    b->pinned = pin1 && pin2;
-    if (pin1 != pin2) {  // keep the free path simple: both pinned or both malloc'ed
-        if (pin1) { cudaFreeHost(b->starts); b->starts = (uint32_t *)malloc(sizeof(uint32_t) * ev_s.size() + 16); }
-        if (pin2) { cudaFreeHost(b->ends); b->ends = (uint32_t *)malloc(sizeof(uint32_t) * ev_e.size() + 16); }
-        b->pinned = false;
-    }
-    if (!ev_s.empty()) {
-        memcpy(b->starts, ev_s.data(), sizeof(uint32_t) * ev_s.size());
-        memcpy(b->ends, ev_e.data(), sizeof(uint32_t) * ev_e.size());
-    }
+    b->n_events = (int64_t)ev_s.n;
+    if (!ev_s.reserve(4, threads) || !ev_e.reserve(4, threads)) return fail(MP2_ENOMEM, "out of host memory");
+    // the sample keeps the two blocks (mp2_bam_close gives them back to the pool)
+    b->starts = ev_s.data(); b->cap_s = ev_s.blk.bytes;
+    b->ends = ev_e.data(); b->cap_e = ev_e.blk.bytes;
+    b->pinned = ev_s.blk.pinned && ev_e.blk.pinned;
+    b->pin_s = ev_s.blk.pinned; b->pin_e = ev_e.blk.pinned;
+    ev_s.blk = PinBlock{nullptr, 0, false};
+    ev_e.blk = PinBlock{nullptr, 0, false};
+    if (unsorted_pos) b->max_disorder = 0xFFFFFFFFu;  // positions go back inside a reference: general path
     if (trace)
         fprintf(stderr, "[mp2_bam] index %.3f resize %.3f inflate %.3f hop %.3f filter %.3f merge %.3f s (%d threads)\n",
                 t_idx, t_res, t_inf, t_hop, t_flt, t_mrg, threads);
@@ -450,6 +543,8 @@ int64_t mp2_bam_n_events(const mp2_bam *b) { return b ? b->n_events : 0; }
 int64_t mp2_bam_n_records(const mp2_bam *b) { return b ? b->n_records : 0; }
 int64_t mp2_bam_n_kept(const mp2_bam *b) { return b ? b->n_kept : 0; }
 uint32_t mp2_bam_max_span(const mp2_bam *b) { return b ? b->max_span : 0; }
+uint32_t mp2_bam_max_block(const mp2_bam *b) { return b ? b->max_block : 0; }
+uint32_t mp2_bam_max_disorder(const mp2_bam *b) { return b ? b->max_disorder : 0; }
 const char *mp2_bam_contig_name(const mp2_bam *b, int64_t i) {
     return (b && i >= 0 && i < (int64_t)b->names.size()) ? b->names[i].c_str() : nullptr;
 }
@@ -464,13 +559,8 @@ const char *mp2_bam_header_text(const mp2_bam *b, int64_t *len) {
 }
 void mp2_bam_close(mp2_bam *b) {
     if (!b) return;
-    if (b->pinned) {
-        if (b->starts) cudaFreeHost(b->starts);
-        if (b->ends) cudaFreeHost(b->ends);
-    } else {
-        free(b->starts);
-        free(b->ends);
-    }
+    mp2::pin_put(mp2::PinBlock{b->starts, b->cap_s, b->pin_s});
+    mp2::pin_put(mp2::PinBlock{b->ends, b->cap_e, b->pin_e});
     delete b;
 }
 

@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
+#include <mutex>
 
 #include "mp2_common.h"
 
@@ -290,7 +291,7 @@ __device__ __forceinline__ void finish_contig(const DepthArgs &a, int64_t c, uin
     const uint64_t covered = N - (uint64_t)load(0);
     unsigned long long acc = 0, total = 0;
     if (covered) trim_walk_warp(load, 0, maxd + 1, mn, mx, acc, total);
-    if (lane == 0) write_result(c, N, covered, mn, mx, total, maxd, 0, a.cov, a.cov_stride, a.stats);
+    if (lane == 0) write_result(c, N, covered, mn, mx, total, maxd, MP2_COV_GENERAL_PATH, a.cov, a.cov_stride, a.stats);
 }
 
 __global__ void __launch_bounds__(COV_THREADS)
@@ -552,7 +553,7 @@ cov_deep_kernel(const DepthArgs a, int *__restrict__ deep_next) {
             __syncthreads();
             if ((uint64_t)base + COV_DEEP_BINS > maxd) break;
         }
-        if (tid == 0) write_result(c, N, covered, mn, mx, s_total, maxd, 0, a.cov, a.cov_stride, a.stats);
+        if (tid == 0) write_result(c, N, covered, mn, mx, s_total, maxd, MP2_COV_GENERAL_PATH, a.cov, a.cov_stride, a.stats);
         __syncthreads();
     }
 }
@@ -601,7 +602,7 @@ __global__ void cov_bounds_kernel(const uint32_t *__restrict__ starts, const int
                                   int32_t *__restrict__ c_hi) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n_tiles) return;
-    if (d_span) max_span = *d_span;  // measured by cov_check_kernel
+    if (d_span) max_span = d_span[1];  // measured by cov_check_kernel
     const int64_t A = k * CT_TILE - (int64_t)max_span, B = (k + 1) * CT_TILE;
     e_lo[k] = first_event_ge(starts, ev_off, off, n, A);
     e_hi[k] = first_event_ge(starts, ev_off, off, n, B);
@@ -610,28 +611,142 @@ __global__ void cov_bounds_kernel(const uint32_t *__restrict__ starts, const int
     c_hi[k] = (int32_t)last_le(off, 0, n, B - 1 < off[n] ? B - 1 : off[n]);
 }
 
-// sortedness + span check: flag[0] = 1 when some contig's starts decrease, flag[1] = max(end - start)
-__global__ void cov_check_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends,
-                                 const int64_t *__restrict__ ev_off, int64_t n, int64_t n_events,
-                                 const int32_t *__restrict__ ev_first, unsigned int *__restrict__ flag) {
+// ---- order / span measurement (max_span == 0: nothing is vouched for) ---------------------------------
+// The fast paths need two numbers: the longest block (end - start) and the DISORDER of the starts,
+//   disorder = max_j ( max_{i<j} g_i - g_j ),   g = contig offset + start  (monotone across contigs),
+// i.e. how far a start may fall behind the running maximum.  A BAM is sorted by read position, so the first
+// blocks of the reads are in order, but the second block of a read with a D / N operation starts after the
+// next reads' first blocks: the disorder is bounded by the reference footprint of a read (a few hundred bp),
+// not zero.  Three small kernels: per-tile maxima of g, their exclusive prefix maximum, then the exact
+// in-tile prefix maximum.  flag[0] = 1: starts go back (old kernels need disorder == 0), flag[1] = longest
+// block, flag[2] = disorder.  Events that are dropped anyway (start beyond the contig, empty) do not count.
+__device__ __forceinline__ long long cov_event_key(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends,
+                                                   const int64_t *__restrict__ ev_off, const int64_t *__restrict__ off,
+                                                   int64_t c_first, int64_t c_last, int64_t e, uint32_t &span) {
+    const int64_t c = c_first == c_last ? c_first : last_le(ev_off, c_first, c_last + 1, e);
+    const int64_t base = off[c], len = off[c + 1] - base;
+    const int64_t s = starts[e];
+    int64_t en = ends[e];
+    if (en > len) en = len;
+    span = 0;
+    if (!(s < len && en > s)) return -1;  // dropped by every path
+    span = (uint32_t)(en - s);
+    return (long long)(base + s);
+}
+
+__global__ void __launch_bounds__(256)
+cov_keymax_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends,
+                  const int64_t *__restrict__ ev_off, const int64_t *__restrict__ off, int64_t n, int64_t n_events,
+                  const int32_t *__restrict__ ev_first, long long *__restrict__ tile_max) {
+    __shared__ long long s_w[8];
     const int64_t t0 = (int64_t)blockIdx.x * COV_EV_TILE;
-    unsigned int bad = 0, span = 0;
+    const int64_t t_last = t0 + COV_EV_TILE - 1 < n_events - 1 ? t0 + COV_EV_TILE - 1 : n_events - 1;
+    const int64_t c_first = ev_first[blockIdx.x];
+    const int64_t c_last = last_le(ev_off, c_first, n, t_last);
+    long long m = -1;
     for (int k = 0; k < COV_EV_TILE / 256; k++) {
         const int64_t e = t0 + k * 256 + threadIdx.x;
         if (e < n_events) {
-            const uint32_t s = starts[e], en = ends[e];
-            if (en > s && en - s > span) span = en - s;
-            if (e > 0 && starts[e - 1] > s) {
-                // a decrease is fine only at a contig boundary: e must be the first event of its contig
-                const int64_t c = last_le(ev_off, ev_first[blockIdx.x], n, e);
-                if (ev_off[c] != e) bad = 1;
-            }
+            uint32_t sp;
+            const long long g = cov_event_key(starts, ends, ev_off, off, c_first, c_last, e, sp);
+            m = g > m ? g : m;
         }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) m = s_w[w] > m ? s_w[w] : m;
+        tile_max[blockIdx.x] = m;
+    }
+}
+
+// exclusive prefix maximum of the tile maxima (one CTA; n_tiles = n_events / 2048)
+__global__ void __launch_bounds__(1024)
+cov_keyscan_kernel(const long long *__restrict__ tile_max, int64_t n_tiles, long long *__restrict__ tile_pre) {
+    __shared__ long long s_w[32];
+    __shared__ long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = -1;
+    __syncthreads();
+    for (int64_t b = 0; b < n_tiles; b += 1024) {
+        const int64_t i = b + tid;
+        const long long v = i < n_tiles ? tile_max[i] : -1;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o && t > incl) incl = t;
+        }
+        long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = -1;
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        long long wpre = s_carry;
+        for (int w = 0; w < warp; w++) wpre = s_w[w] > wpre ? s_w[w] : wpre;
+        if (i < n_tiles) tile_pre[i] = excl > wpre ? excl : wpre;
+        __syncthreads();
+        if (tid == 1023) s_carry = incl > wpre ? incl : wpre;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+cov_check_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends,
+                 const int64_t *__restrict__ ev_off, const int64_t *__restrict__ off, int64_t n, int64_t n_events,
+                 const int32_t *__restrict__ ev_first, const long long *__restrict__ tile_pre,
+                 unsigned int *__restrict__ flag) {
+    constexpr int PER = COV_EV_TILE / 256;  // consecutive events per thread
+    __shared__ long long s_w[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * COV_EV_TILE;
+    const int64_t t_last = t0 + COV_EV_TILE - 1 < n_events - 1 ? t0 + COV_EV_TILE - 1 : n_events - 1;
+    const int64_t c_first = ev_first[blockIdx.x];
+    const int64_t c_last = last_le(ev_off, c_first, n, t_last);
+    long long g[PER];
+    long long tmax = -1;
+    unsigned int span = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int64_t e = t0 + (int64_t)tid * PER + k;
+        g[k] = -1;
+        if (e < n_events) {
+            uint32_t sp;
+            g[k] = cov_event_key(starts, ends, ev_off, off, c_first, c_last, e, sp);
+            span = sp > span ? sp : span;
+        }
+        tmax = g[k] > tmax ? g[k] : tmax;
+    }
+    long long incl = tmax;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o && t > incl) incl = t;
+    }
+    long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = -1;
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    long long pm = tile_pre[blockIdx.x];
+    for (int w = 0; w < warp; w++) pm = s_w[w] > pm ? s_w[w] : pm;
+    pm = excl > pm ? excl : pm;  // maximum of every key before this thread's first event
+    unsigned long long dis = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        if (g[k] >= 0) {
+            if (pm > g[k] && (unsigned long long)(pm - g[k]) > dis) dis = (unsigned long long)(pm - g[k]);
+            pm = g[k] > pm ? g[k] : pm;
+        }
+    }
+    unsigned int d32 = dis > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned int)dis;
     span = __reduce_max_sync(0xffffffffu, span);
-    bad = __reduce_or_sync(0xffffffffu, bad);
-    if ((threadIdx.x & 31) == 0) {
-        if (bad) atomicOr(&flag[0], 1u);
+    d32 = __reduce_max_sync(0xffffffffu, d32);
+    if (lane == 0) {
+        if (d32) { atomicOr(&flag[0], 1u); atomicMax(&flag[2], d32); }
         if (span) atomicMax(&flag[1], span);
     }
 }
@@ -651,6 +766,8 @@ struct TileArgs {
     int64_t n, n_pos, n_tiles;
     const int64_t *e_lo, *e_hi;
     const int32_t *c_lo, *c_hi;  // contigs the tile's events can belong to
+    const int32_t *c_ev;         // cov_stream2_kernel: a contig at or before the one owning the run's first event
+    int64_t n_events;            // all events of the sample (bulk copies never read beyond their 16-byte granule)
     uint32_t *rows;              // [n_tiles][COV_BINS]
     RowMeta *meta;
     int32_t *deep_list;
@@ -1041,23 +1158,32 @@ constexpr int C3_PF = MP2_C3_PF;             // events ahead of e_cur that are p
 
 __device__ __forceinline__ int c3_phys(int i) { return i + 4 * (i >> C3_SPL_LOG); }
 
+// Event range and contigs of every run.  `meas` = {unsorted, longest block, disorder} measured by
+// cov_check_kernel, or NULL when the caller vouched for (max_span, max_disorder).  The ranges are computed with
+// the LARGEST margins the kernels support (span + disorder <= C3_S), so they do not depend on the measured
+// values: with starts that fall at most `disorder` behind their running maximum, a binary search for X ends
+// between the first event whose running maximum reaches X and the first one whose running maximum reaches
+// X + disorder.  Hence every event before search(A - C3_S) ends at or before slot A, and every event from
+// search(B + C3_S) on starts at or after slot B.
 __global__ void cov_bounds_run_kernel(const uint32_t *__restrict__ starts, const int64_t *__restrict__ ev_off,
                                       const int64_t *__restrict__ off, int64_t n, int64_t n_runs, uint32_t max_span,
-                                      const unsigned int *__restrict__ d_span, int64_t *__restrict__ e_lo,
-                                      int64_t *__restrict__ e_hi, int32_t *__restrict__ c_lo,
-                                      int32_t *__restrict__ c_hi, int *__restrict__ gate) {
+                                      uint32_t max_disorder, int need_sorted, const unsigned int *__restrict__ meas,
+                                      int64_t *__restrict__ e_lo, int64_t *__restrict__ e_hi,
+                                      int32_t *__restrict__ c_lo, int32_t *__restrict__ c_hi,
+                                      int32_t *__restrict__ c_ev, int *__restrict__ gate) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n_runs) return;
-    if (d_span) max_span = *d_span;
-    if (max_span > (uint32_t)C3_S) {  // blocks longer than the overflow region: general path
-        if (k == 0) *gate = 1;
+    if (meas) { max_span = meas[1]; max_disorder = meas[2]; }
+    if ((uint64_t)max_span + max_disorder > (uint64_t)C3_S || (need_sorted && max_disorder)) {
+        if (k == 0) *gate = 1;  // blocks too long / starts too far out of order for the overflow region: general path
         return;
     }
-    const int64_t A = k * C3_RUN - (int64_t)max_span, B = (k + 1) * C3_RUN;
+    const int64_t A = k * C3_RUN - (int64_t)C3_S, B = (k + 1) * C3_RUN;
     e_lo[k] = first_event_ge(starts, ev_off, off, n, A);
-    e_hi[k] = first_event_ge(starts, ev_off, off, n, B);
+    e_hi[k] = first_event_ge(starts, ev_off, off, n, need_sorted ? B : B + C3_S);
     c_lo[k] = (int32_t)last_le(off, 0, n, k * C3_RUN);  // contig holding the run's first slot
     c_hi[k] = (int32_t)last_le(off, 0, n, B - 1 < off[n] ? B - 1 : off[n]);
+    c_ev[k] = (int32_t)last_le(ev_off, 0, n, e_lo[k]);  // contig owning the run's first event (any, if there is none)
 }
 
 // Out-of-line pieces of cov_stream_kernel: they run once per contig (or never), keeping them out of the
@@ -1368,9 +1494,389 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
     }
 }
 
+
+// =====================================================================================================
+// cov_stream2_kernel: the streaming algorithm again, leaner and order-tolerant.
+//
+//   * Events reach the warp through a ring in its shared memory filled by the bulk-copy engine
+//     (cp.async.bulk + mbarrier, 4 stages of 64 events per array): no registers, no scoreboard and no
+//     re-alignment when a window ends in the middle of a batch -- the next batch simply starts at e_cur.
+//   * Bounded disorder: the blocks of a BAM are ordered by READ position, so the second block of a read with
+//     a D / N operation starts after the first blocks of the following reads.  Events are consumed by the
+//     running maximum of their starts: a batch is taken whole while max(pm, batch max) < t_hi + delta
+//     (one REDUX per batch); only the batch that crosses the limit is split by an exact prefix maximum.
+//     Since a start is never more than `disorder` (<= delta) behind the running maximum, every event that
+//     starts inside the window has been applied when the window is histogrammed; events taken early land
+//     in the overflow region (delta + span <= 512 slots) that becomes the head of the next window.
+//   * The difference array holds 4 * (+-1), so the running value of the lane-serial walk IS the byte offset
+//     of the depth's histogram bin: one IADD and one ATOMS per position.  The overflow test of 16 positions
+//     is one OR chain; the highest occupied bin is looked up when the contig closes instead of being
+//     tracked per position.
+// =====================================================================================================
+constexpr int C4_STAGE = 64;                 // events per bulk copy and array (256 bytes)
+constexpr int C4_NST = 4;                    // stages = mbarriers
+constexpr int C4_RING = C4_STAGE * C4_NST;   // events per array in the ring
+constexpr int C4_LIMIT4 = 4 * (COV_BINS - 1);
+
+struct __align__(16) C4Smem {
+    int32_t T[C3_WORDS];         // 4 * difference array: window + overflow region, 4 pad words per 64 slots
+    uint32_t hist[COV_BINS];
+    uint32_t ring_s[C4_RING];
+    uint32_t ring_e[C4_RING];
+    unsigned long long bar[C4_NST];
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "MP2_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MP2_DONE;\n\t"
+        "bra MP2_WAIT;\n\t"
+        "MP2_DONE:\n\t}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void smem_add_if(uint32_t saddr, int v, bool cond) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.s32 [%0], %1;\n\t}" ::"r"(saddr), "r"(v),
+                 "r"((uint32_t)cond)
+                 : "memory");
+}
+
+// contig cursor (see c3_seek) found by galloping from contig c0, which is at or before the event's contig
+__device__ __noinline__ int4 c4_seek(const int64_t *__restrict__ ev_off, const int64_t *__restrict__ off, int c0, int64_t n,
+                                     int64_t e_abs, int64_t e_base, int64_t run_lo) {
+    int64_t lo = c0, step = 1;
+    while (lo + step < n && ev_off[lo + step] <= e_abs) { lo += step; step <<= 1; }
+    const int64_t hi = lo + step < n ? lo + step : n;
+    const int64_t c = last_le(ev_off, lo, hi, e_abs);
+    const int64_t o0 = off[c];
+    return make_int4((int)c, clamp_rel(ev_off[c + 1] - e_base), clamp_rel(o0 - run_lo), (int)(off[c + 1] - o0));
+}
+
+// 16 positions that are not all inside the contig window, or that reach the last bin: exact, one by one.
+// chunk = 4 * differences, d4_before = 4 * depth just before the chunk, m = positions inside the window.
+// Returns the largest depth among them.
+__device__ __noinline__ int c4_slow_chunk(const TileArgs &a, int64_t c, const int32_t *chunk, int d4_before, uint32_t m,
+                                          uint32_t *hist) {
+    int dd[COV_ITEMS];
+    int run = d4_before, mx = 0;
+    bool deep = false;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        run += chunk[i];
+        int d = run >> 2;
+        d = d < 0 ? 0 : d;
+        dd[i] = d;
+        if (m & (1u << i)) {
+            mx = d > mx ? d : mx;
+            if (d < COV_BINS - 1) atomicAdd(&hist[d], 1u);
+            else deep = true;
+        }
+    }
+    if (deep) ct_deep_positions(a, c, dd, m);
+    return mx;
+}
+
+// The window of contig c is complete (or the run ends): the highest occupied bin is read off the histogram.
+__device__ __noinline__ void c4_close_window(const TileArgs &a, int64_t c, bool local, int deep_max, int in_run,
+                                             uint32_t *s_hist) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    int top = 0;
+    for (int j = COV_BINS / 32 - 1; j >= 0; j--)
+        if (s_hist[(COV_BINS / 32) * lane + j]) { top = (COV_BINS / 32) * lane + j; break; }
+    top = __reduce_max_sync(0xffffffffu, top);
+    deep_max = __reduce_max_sync(0xffffffffu, deep_max);
+    c3_close_window(a, c, local, deep_max > top ? deep_max : top, in_run, s_hist);
+}
+
+__global__ void __launch_bounds__(32)
+cov_stream2_kernel(const __grid_constant__ TileArgs a) {
+    __shared__ C4Smem sm;
+    if (*((volatile int *)a.gate_out)) return;
+    const int lane = threadIdx.x;
+    const uint32_t sT0 = smem_base_opaque(sm.T);
+    const uint32_t rS0 = smem_base_opaque(sm.ring_s), rE0 = smem_base_opaque(sm.ring_e);
+    const uint32_t bar0 = smem_base_opaque(sm.bar);
+    const int excl = (int)a.tp.excl;
+    const uint32_t span = a.span_dev ? *a.span_dev : a.span_host;
+    // events are consumed up to `delta` slots ahead of the window; delta >= disorder and delta + span <= C3_S
+    // (cov_bounds_run_kernel sends anything else to the general path)
+    const int delta = C3_S - (int)(span < (uint32_t)C3_S ? span : (uint32_t)C3_S);
+    for (int i = lane; i < COV_BINS; i += 32) sm.hist[i] = 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < C4_NST; i++) mbar_init(bar0 + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    // bulk copies need 16-byte aligned global addresses: copy from the aligned address at or before the array
+    // (the extra bytes are inside the first / last 16-byte granule of the allocation)
+    const uint32_t ms = ((uint32_t)reinterpret_cast<uintptr_t>(a.starts) >> 2) & 3u;
+    const uint32_t me = ((uint32_t)reinterpret_cast<uintptr_t>(a.ends) >> 2) & 3u;
+    const uint32_t *__restrict__ s_al = a.starts - ms;
+    const uint32_t *__restrict__ e_al = a.ends - me;
+    const int64_t lim_s = ((int64_t)ms + a.n_events + 3) & ~3ll, lim_e = ((int64_t)me + a.n_events + 3) & ~3ll;
+    uint32_t sq = 0;  // stages issued so far by this warp: slot = sq & 3, phase parity of the slot = (sq >> 2) & 1
+
+    for (;;) {
+        int64_t run = 0;
+        if (lane == 0) run = atomicAdd(a.work_counter, 1);
+        run = __shfl_sync(0xffffffffu, run, 0);
+        if (run >= a.n_tiles) break;
+        const int64_t run_lo = run * C3_RUN;
+        const int rlen = (int)(run_lo + C3_RUN < a.n_pos ? C3_RUN : a.n_pos - run_lo);
+        const int64_t e_base = a.e_lo[run];
+        const int64_t n_ev64 = a.e_hi[run] - e_base;
+        const int n_ev = n_ev64 > 0 ? (int)n_ev64 : 0;
+        // ---- staging geometry: stage s holds s_al[gs0 + 64 s ..) and e_al[ge0 + 64 s ..) ----
+        const int64_t gs0 = (e_base + ms) & ~3ll, ge0 = (e_base + me) & ~3ll;
+        const int r_s = (int)((e_base + ms) & 3), r_e = (int)((e_base + me) & 3);
+        const int rmax = r_s > r_e ? r_s : r_e, rmin = r_s < r_e ? r_s : r_e;
+        const int n_st = n_ev > 0 ? ((rmax + n_ev - 1) >> 6) + 1 : 0;
+        const uint32_t sq0 = sq;
+        int issued = 0, waited = 0;
+        const int bs = r_s + C4_STAGE * (int)(sq0 & 3u) + lane, be = r_e + C4_STAGE * (int)(sq0 & 3u) + lane;
+        auto issue = [&](int s) {
+            if (lane == 0) {
+                const uint32_t slot = (sq0 + (uint32_t)s) & 3u, bar = bar0 + 8u * slot;
+                int64_t cs = lim_s - (gs0 + (int64_t)C4_STAGE * s), ce = lim_e - (ge0 + (int64_t)C4_STAGE * s);
+                cs = cs > C4_STAGE ? C4_STAGE : (cs < 0 ? 0 : cs);
+                ce = ce > C4_STAGE ? C4_STAGE : (ce < 0 ? 0 : ce);
+                mbar_expect_tx(bar, (uint32_t)(4 * (cs + ce)));
+                if (cs > 0) bulk_g2s(rS0 + 4u * C4_STAGE * slot, s_al + gs0 + (int64_t)C4_STAGE * s, (uint32_t)(4 * cs), bar);
+                if (ce > 0) bulk_g2s(rE0 + 4u * C4_STAGE * slot, e_al + ge0 + (int64_t)C4_STAGE * s, (uint32_t)(4 * ce), bar);
+            }
+        };
+        auto wait_stage = [&](int s) {
+            const uint32_t q = sq0 + (uint32_t)s;
+            mbar_wait(bar0 + 8u * (q & 3u), (q >> 2) & 1u);
+        };
+        __syncwarp();  // the previous run's reads of the ring are done
+        while (issued < n_st && issued < C4_NST) { issue(issued); issued++; }
+
+        int e_cur = 0;  // next event to consume, relative to e_base
+        int4 cur = make_int4(0, 0, 0, 0);
+        if (n_ev > 0) cur = c4_seek(a.ev_off, a.off, a.c_ev[run], a.n, e_base, e_base, run_lo);
+        for (int i = lane; i < C3_WORDS / 4; i += 32) reinterpret_cast<int4 *>(sm.T)[i] = make_int4(0, 0, 0, 0);
+        __syncwarp();
+
+        int64_t c = a.c_lo[run];
+        const int64_t c_last = a.c_hi[run];
+        bool have = false;
+        int wlo = 0, whi = -1;      // run-relative window of contig c
+        int in_run = 0;             // window slots of c accumulated in this run
+        int deep_max = 0;           // largest depth seen by the exact chunk path for c in this run (per lane)
+        int carry4 = 0;             // 4 * depth just before the current window
+        int pm = INT_MIN;           // running maximum of the starts consumed so far (run-relative)
+        bool viol = false;          // the vouched bounds do not hold
+
+        for (int k = 0; k < C3_TPR; k++) {
+            const int t_lo = k * C3_W;
+            if (t_lo >= rlen) break;
+            const int t_hi = t_lo + C3_W < rlen ? t_lo + C3_W : rlen;
+            const int lim = t_hi + delta;
+            int open = 0;
+            while (e_cur < n_ev) {
+                {   // staging: refill the slots behind e_cur, wait for the stages this batch reads
+                    const int can = ((rmin + e_cur) >> 6) + C4_NST;
+                    if (issued < n_st && issued < can) {
+                        __syncwarp();
+                        do { issue(issued); issued++; } while (issued < n_st && issued < can);
+                    }
+                    const int e_end = e_cur + 32 < n_ev ? e_cur + 32 : n_ev;
+                    const int need = (rmax + e_end - 1) >> 6;
+                    while (waited <= need) { wait_stage(waited); waited++; }
+                }
+                const int e = e_cur + lane;
+                const bool live = e < n_ev;
+                const uint32_t sv = sm.ring_s[(bs + e_cur) & (C4_RING - 1)];
+                const uint32_t ev = sm.ring_e[(be + e_cur) & (C4_RING - 1)];
+                int crel = cur.z;
+                uint32_t len = (uint32_t)cur.w;
+                if (live && e >= cur.y) {  // this lane's event belongs to a later contig (rare)
+                    const int4 mine = c4_seek(a.ev_off, a.off, cur.x, a.n, e_base + e, e_base, run_lo);
+                    crel = mine.z;
+                    len = (uint32_t)mine.w;
+                }
+                const uint32_t en = ev < len ? ev : len;
+                const bool ok = live && sv < len && en > sv;
+                const int gs = (int)((uint32_t)crel + sv);  // run-relative start
+                const int key = ok ? gs : INT_MIN;
+                int bm = __reduce_max_sync(0xffffffffu, key);
+                bm = bm > pm ? bm : pm;
+                int cnt = 32, pm_new = bm;
+                if (bm >= lim || e_cur + 32 > n_ev) {  // the batch crosses the limit: exact prefix maximum
+                    int p = key;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, p, o);
+                        if (lane >= o && t > p) p = t;
+                    }
+                    p = p > pm ? p : pm;
+                    const unsigned nb = ~__ballot_sync(0xffffffffu, live && p < lim);
+                    cnt = nb ? __ffs(nb) - 1 : 32;
+                    pm_new = __shfl_sync(0xffffffffu, p, cnt ? cnt - 1 : 0);
+                    if (!cnt) pm_new = pm;
+                }
+                const bool act = ok && lane < cnt;
+                const int rs = gs - t_lo, re = rs + (int)(en - sv);
+                const bool in = act && rs >= 0 && re < C3_W + C3_S;
+                viol |= act && (en - sv > span);  // a vouched max_span that does not hold
+                if (k == 0) {  // first window of the run: blocks that are open across run_lo
+                    const bool tail = act && rs < 0 && re >= 0;
+                    open += tail;
+                    smem_add_if(sT0 + 4u * (uint32_t)c3_phys(re), -4, tail && re < C3_W + C3_S);
+                    viol |= (tail && re >= C3_W + C3_S) || (act && rs >= 0 && !in);
+                } else {
+                    viol |= act && !in;  // a start before the window was missed earlier; an end beyond the overflow region
+                }
+                smem_add_if(sT0 + 4u * (uint32_t)c3_phys(rs), 4, in);
+                smem_add_if(sT0 + 4u * (uint32_t)c3_phys(re), -4, in);
+                e_cur += cnt;
+                pm = pm_new;
+                if (cnt && e_cur < n_ev && e_cur >= cur.y)  // advance the warp's contig cursor
+                    cur = c4_seek(a.ev_off, a.off, cur.x, a.n, e_base + e_cur, e_base, run_lo);
+                if (cnt < 32) break;
+            }
+            open = __reduce_add_sync(0xffffffffu, open);
+            carry4 += 4 * open;
+            __syncwarp();
+
+            // ---- this lane's 64 slots: total, exclusive warp scan ----
+            const int myb = (C3_SPL + 4) * lane;
+            int tot = 0;
+            {
+                const int4 *p = reinterpret_cast<const int4 *>(sm.T + myb);
+#pragma unroll
+                for (int j = 0; j < C3_SPL / 4; j++) {
+                    const int4 v = p[j];
+                    tot += v.x + v.y + v.z + v.w;
+                }
+            }
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int dstart4 = carry4 + incl - tot;
+            carry4 += __shfl_sync(0xffffffffu, incl, 31);
+
+            // ---- contig windows intersecting [t_lo, t_hi) ----
+            const int q0 = t_lo + C3_SPL * lane;
+            for (;;) {
+                if (!have) {
+                    if (c > c_last) break;
+                    const int64_t o0 = a.off[c], o1 = a.off[c + 1];
+                    const int r0 = clamp_rel(o0 - run_lo);
+                    if (r0 >= t_hi) break;
+                    const int r1 = clamp_rel(o1 - run_lo);
+                    if (o1 - o0 > 2 * (int64_t)excl) { wlo = r0 + excl; whi = r1 - excl - 1; }
+                    else { wlo = 0; whi = -1; }
+                    have = true;
+                    in_run = 0;
+                    deep_max = 0;
+                }
+                if (whi < wlo || whi < 0) { c++; have = false; continue; }  // no window / ended before this run
+                if (wlo >= t_hi) break;
+                const int lo = wlo > t_lo ? wlo : t_lo, hi = whi + 1 < t_hi ? whi + 1 : t_hi;
+                if (hi > lo) {
+                    if (lo < q0 + C3_SPL && hi > q0) {  // this lane's slots intersect the window
+                        int d4 = dstart4;
+#pragma unroll 1
+                        for (int ch = 0; ch < C3_SPL / 16; ch++) {
+                            const int q = q0 + 16 * ch;
+                            const int d4_before = d4;
+                            int d[16];
+                            const int4 *p = reinterpret_cast<const int4 *>(sm.T + myb + 16 * ch);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const int4 v = p[j];
+                                d4 += v.x; d[4 * j] = d4;
+                                d4 += v.y; d[4 * j + 1] = d4;
+                                d4 += v.z; d[4 * j + 2] = d4;
+                                d4 += v.w; d[4 * j + 3] = d4;
+                            }
+                            int orr = 0;
+#pragma unroll
+                            for (int i = 0; i < 16; i++) orr |= d[i];
+                            const int l2 = lo > q ? lo : q, h2 = hi < q + 16 ? hi : q + 16;
+                            if (h2 - l2 == 16 && (unsigned)orr < (unsigned)C4_LIMIT4) {
+#pragma unroll
+                                for (int i = 0; i < 16; i++)
+                                    atomicAdd(reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(sm.hist) + d[i]), 1u);
+                            } else if (h2 > l2) {
+                                const uint32_t m = ((1u << (h2 - q)) - 1u) & ~((1u << (l2 - q)) - 1u);
+                                const int mx = c4_slow_chunk(a, c, sm.T + myb + 16 * ch, d4_before, m, sm.hist);
+                                deep_max = mx > deep_max ? mx : deep_max;
+                            }
+                        }
+                    }
+                    in_run += hi - lo;
+                }
+                if (whi >= t_hi) break;  // the window continues in the next 2048 slots
+                c4_close_window(a, c, wlo >= 0, deep_max, in_run, sm.hist);
+                c++;
+                have = false;
+            }
+            // ---- slide: the overflow region becomes the head of the next window ----
+            __syncwarp();
+            if (k + 1 < C3_TPR && t_hi < rlen) {
+                const int src = c3_phys(C3_W);
+                int4 keep[(C3_HEAD / 4 + 31) / 32];
+#pragma unroll
+                for (int j = 0; j < (C3_HEAD / 4 + 31) / 32; j++) {
+                    const int i = lane + 32 * j;
+                    keep[j] = i < C3_HEAD / 4 ? reinterpret_cast<const int4 *>(sm.T + src)[i] : make_int4(0, 0, 0, 0);
+                }
+                __syncwarp();
+                for (int i = lane; i < C3_WORDS / 4; i += 32) reinterpret_cast<int4 *>(sm.T)[i] = make_int4(0, 0, 0, 0);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < (C3_HEAD / 4 + 31) / 32; j++) {
+                    const int i = lane + 32 * j;
+                    if (i < C3_HEAD / 4) reinterpret_cast<int4 *>(sm.T)[i] = keep[j];
+                }
+                __syncwarp();
+            }
+        }
+        // ---- run end ----
+        if (have && whi >= wlo && in_run > 0) c4_close_window(a, c, false, deep_max, in_run, sm.hist);
+        if (__any_sync(0xffffffffu, viol) && lane == 0) *a.gate_out = 1;  // unreliable ranges: the general path redoes the sample
+        while (waited < issued) { wait_stage(waited); waited++; }  // no copy may be in flight when the ring is reused
+        sq = sq0 + (uint32_t)issued;
+    }
+}
+
 }  // namespace mp2
 
 using namespace mp2;
+
+// cudaFuncSetAttribute is per device: done once for every device this process uses
+static int cov_tile_attr_once() {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    MP2_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return MP2_OK;
+    MP2_CUDA(cudaFuncSetAttribute(cov_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return MP2_OK;
+}
 
 // MP2_COV_PATH=general forces the difference array through HBM (development / A-B switch).
 static bool cov_force_general() {
@@ -1382,15 +1888,33 @@ static bool cov_force_general() {
     return v == 1;
 }
 
+// Which fast-path kernel runs: cov_stream2_kernel unless MP2_COV_STREAM=1 (the first streaming kernel) or
+// MP2_COV_TILE=1 (block per tile) asks for an older one (development / A-B switches; both need sorted starts).
+static int cov_fast_version() {
+    static int v = 0;
+    if (!v) {
+        const char *t = getenv("MP2_COV_TILE"), *o = getenv("MP2_COV_STREAM");
+        v = (t && t[0] == '1') ? 1 : (o && o[0] == '1') ? 3 : 4;
+    }
+    return v;
+}
+
+static int cov_general_path(const uint32_t *starts, const uint32_t *ends, const int64_t *ev_off, const int64_t *off,
+                            int64_t n_contigs, int64_t n_events, int64_t n_pos, const int32_t *ev_first,
+                            const TrimParams &tp, int *ctrs, float *d_cov, int64_t cov_stride, mp2_cov_stats *d_stats,
+                            cudaStream_t stream);
+
 extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, const void *d_ev_off,
                                      const void *d_contig_off, int64_t n_contigs, int64_t n_events,
-                                     int64_t n_positions, uint32_t max_span, uint32_t end_excl,
+                                     int64_t n_positions, uint32_t max_span, uint32_t max_disorder, uint32_t end_excl,
                                      float trim_lower, float trim_upper, void *d_cov, int64_t cov_stride,
                                      void *d_stats, void *stream_) {
     if (n_contigs < 0 || n_events < 0 || n_positions < 0) return fail(MP2_EINVAL, "negative size");
     if (n_contigs > INT32_MAX) return fail(MP2_EINVAL, "too many contigs in one call");
     if (!d_contig_off || !d_ev_off || !d_cov || (n_events > 0 && (!d_starts || !d_ends)))
         return fail(MP2_EINVAL, "NULL argument");
+    if ((reinterpret_cast<uintptr_t>(d_starts) & 3) || (reinterpret_cast<uintptr_t>(d_ends) & 3))
+        return fail(MP2_EINVAL, "d_starts and d_ends must be 4-byte aligned");
     if (!(trim_lower >= 0.0f) || !(trim_upper >= 0.0f) || !(trim_lower + trim_upper < 1.0f))
         return fail(MP2_EINVAL, "trim_lower and trim_upper must be >= 0 and sum to < 1");
     if (cov_stride < 1) return fail(MP2_EINVAL, "cov_stride must be >= 1");
@@ -1409,13 +1933,13 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     tp.excl = end_excl;
 
     // ctrs: [0] deep count (tile path) [1] tile work counter [2] gate [3] deep count (general) [4] general
-    // work counter [5] deep next; flags: [0] starts not sorted [1] measured max span
+    // work counter [5] deep next [6] deep rows used; flags: [0] starts go back [1] longest block [2] disorder
     Temp ctrs, flags, ev_first;
     MP2_TRY(ctrs.alloc(sizeof(int) * 8, stream));
-    MP2_TRY(flags.alloc(sizeof(unsigned int) * 2, stream));
+    MP2_TRY(flags.alloc(sizeof(unsigned int) * 4, stream));
     MP2_TRY(ev_first.alloc(sizeof(int32_t) * (n_ev_tiles + 1), stream));
     MP2_CUDA(cudaMemsetAsync(ctrs.p, 0, sizeof(int) * 8, stream));
-    MP2_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(unsigned int) * 2, stream));
+    MP2_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(unsigned int) * 4, stream));
     int *gate = ctrs.as<int>() + 2;
     {
         Launch L("cov_init_kernel", stream);
@@ -1430,15 +1954,15 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     }
     MP2_CUDA(cudaGetLastError());
 
-    const bool general_only = cov_force_general();
+    const int fast_ver = cov_fast_version();
+    const bool need_sorted = fast_ver != 4;
+    const bool measure = max_span == 0;
+    // a vouched sample the chosen kernel cannot take goes straight to the general path
+    bool general_only = cov_force_general() ||
+                        (!measure && ((uint64_t)max_span + max_disorder > (uint64_t)C3_S || (need_sorted && max_disorder)));
     // ---------------- fast path: difference array in shared memory ----------------
-    static int fast_ver = 0;  // MP2_COV_TILE=1 selects the block-per-tile kernel (A/B), default = streaming warps
-    if (!fast_ver) {
-        const char *e = getenv("MP2_COV_TILE");
-        fast_ver = (e && e[0] == '1') ? 1 : 3;
-    }
-    Temp e_lo, e_hi, c_lo, c_hi, t_rows, t_meta, t_deep, t_drow, t_dpool;
     if (!general_only) {
+        Temp e_lo, e_hi, c_lo, c_hi, c_ev, t_rows, t_meta, t_deep, t_drow, t_dpool, k_max, k_pre;
         const int64_t unit = fast_ver == 1 ? CT_TILE : C3_RUN;
         const int64_t n_units = (n_pos + unit - 1) / unit;
         if (n_units > INT32_MAX / 2) return fail(MP2_EINVAL, "too many positions in one call");
@@ -1446,6 +1970,7 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
         MP2_TRY(e_hi.alloc(sizeof(int64_t) * n_units, stream));
         MP2_TRY(c_lo.alloc(sizeof(int32_t) * n_units, stream));
         MP2_TRY(c_hi.alloc(sizeof(int32_t) * n_units, stream));
+        MP2_TRY(c_ev.alloc(sizeof(int32_t) * n_units, stream));
         MP2_TRY(t_rows.alloc(sizeof(uint32_t) * COV_BINS * (size_t)n_units, stream));
         MP2_TRY(t_meta.alloc(sizeof(RowMeta) * n_units, stream));
         MP2_TRY(t_deep.alloc(sizeof(int32_t) * n_contigs, stream));
@@ -1455,66 +1980,99 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
         MP2_CUDA(cudaMemsetAsync(t_meta.p, 0, sizeof(RowMeta) * n_units, stream));
         MP2_CUDA(cudaMemsetAsync(t_drow.p, 0xFF, sizeof(int32_t) * n_contigs, stream));
         MP2_CUDA(cudaMemsetAsync(t_dpool.p, 0, sizeof(uint32_t) * (size_t)CT_DEEP_ROWS * CT_DEEP_BINS, stream));
-        if (n_events > 0 && max_span == 0) {
-            Launch L("cov_check_kernel", stream);
-            cov_check_kernel<<<(unsigned)n_ev_tiles, 256, 0, stream>>>(starts, ends, ev_off, n_contigs, n_events,
-                                                                     ev_first.as<int32_t>(), flags.as<unsigned int>());
+        if (n_events > 0 && measure) {  // longest block and disorder of the starts, exactly
+            MP2_TRY(k_max.alloc(sizeof(long long) * n_ev_tiles, stream));
+            MP2_TRY(k_pre.alloc(sizeof(long long) * n_ev_tiles, stream));
+            {
+                Launch L("cov_keymax_kernel", stream);
+                cov_keymax_kernel<<<(unsigned)n_ev_tiles, 256, 0, stream>>>(starts, ends, ev_off, off, n_contigs, n_events,
+                                                                         ev_first.as<int32_t>(), k_max.as<long long>());
+            }
+            {
+                Launch L("cov_keyscan_kernel", stream);
+                cov_keyscan_kernel<<<1, 1024, 0, stream>>>(k_max.as<long long>(), n_ev_tiles, k_pre.as<long long>());
+            }
+            {
+                Launch L("cov_check_kernel", stream);
+                cov_check_kernel<<<(unsigned)n_ev_tiles, 256, 0, stream>>>(starts, ends, ev_off, off, n_contigs, n_events,
+                                                                        ev_first.as<int32_t>(), k_pre.as<long long>(),
+                                                                        flags.as<unsigned int>());
+            }
         }
         MP2_CUDA(cudaGetLastError());
-        const unsigned int *d_span = max_span == 0 ? flags.as<unsigned int>() + 1 : nullptr;
+        const unsigned int *meas = measure ? flags.as<unsigned int>() : nullptr;
         {
             Launch L("cov_bounds_kernel", stream);
             if (fast_ver == 1)
                 cov_bounds_kernel<<<(unsigned)((n_units + 127) / 128), 128, 0, stream>>>(
-                    starts, ev_off, off, n_contigs, n_units, max_span, d_span, e_lo.as<int64_t>(), e_hi.as<int64_t>(),
+                    starts, ev_off, off, n_contigs, n_units, max_span, meas, e_lo.as<int64_t>(), e_hi.as<int64_t>(),
                     c_lo.as<int32_t>(), c_hi.as<int32_t>());
             else
                 cov_bounds_run_kernel<<<(unsigned)((n_units + 127) / 128), 128, 0, stream>>>(
-                    starts, ev_off, off, n_contigs, n_units, max_span, d_span, e_lo.as<int64_t>(), e_hi.as<int64_t>(),
-                    c_lo.as<int32_t>(), c_hi.as<int32_t>(), gate);
+                    starts, ev_off, off, n_contigs, n_units, max_span, max_disorder, need_sorted ? 1 : 0, meas,
+                    e_lo.as<int64_t>(), e_hi.as<int64_t>(), c_lo.as<int32_t>(), c_hi.as<int32_t>(), c_ev.as<int32_t>(),
+                    gate);
         }
         MP2_CUDA(cudaGetLastError());
         TileArgs t;
         t.starts = starts; t.ends = ends; t.ev_off = ev_off; t.off = off;
         t.n = n_contigs; t.n_pos = n_pos; t.n_tiles = n_units;
         t.e_lo = e_lo.as<int64_t>(); t.e_hi = e_hi.as<int64_t>();
-        t.c_lo = c_lo.as<int32_t>(); t.c_hi = c_hi.as<int32_t>();
+        t.c_lo = c_lo.as<int32_t>(); t.c_hi = c_hi.as<int32_t>(); t.c_ev = c_ev.as<int32_t>();
+        t.n_events = n_events;
         t.rows = t_rows.as<uint32_t>(); t.meta = t_meta.as<RowMeta>();
         t.deep_list = t_deep.as<int32_t>(); t.deep_count = ctrs.as<int>() + 0;
         t.work_counter = ctrs.as<int>() + 1;
         t.deep_row_of = t_drow.as<int32_t>(); t.deep_pool = t_dpool.as<uint32_t>(); t.deep_rows_used = ctrs.as<int>() + 6;
-        t.check = max_span == 0 ? flags.as<unsigned int>() : nullptr;
+        t.check = measure ? flags.as<unsigned int>() : nullptr;  // tile kernel: flag[0] != 0 => not sorted
         t.span_host = max_span;
-        t.span_dev = d_span;
+        t.span_dev = measure ? flags.as<unsigned int>() + 1 : nullptr;
         t.gate_out = gate;
         t.cov = (float *)d_cov; t.cov_stride = cov_stride; t.stats = (mp2_cov_stats *)d_stats; t.tp = tp;
         int occ = 0;
         if (fast_ver == 1) {
-            static bool attr_done = false;
-            if (!attr_done) {
-                MP2_CUDA(cudaFuncSetAttribute(cov_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
-                attr_done = true;
-            }
+            MP2_TRY(cov_tile_attr_once());
             MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_tile_kernel, COV_THREADS, CT_SMEM));
             if (occ < 1) occ = 1;
             int64_t grid = (int64_t)num_sms() * occ;
             if (grid > n_units) grid = n_units;
             Launch L("cov_tile_kernel", stream);
             cov_tile_kernel<<<(unsigned)grid, COV_THREADS, CT_SMEM, stream>>>(t);
-        } else {
+        } else if (fast_ver == 3) {
             MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_stream_kernel, 32 * C3_WPC, 0));
             if (occ < 1) occ = 1;
             int64_t grid = (int64_t)num_sms() * occ;
             if (grid * C3_WPC > n_units) grid = (n_units + C3_WPC - 1) / C3_WPC;
             Launch L("cov_stream_kernel", stream);
             cov_stream_kernel<<<(unsigned)grid, 32 * C3_WPC, 0, stream>>>(t);
+        } else {
+            MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_stream2_kernel, 32, 0));
+            if (occ < 1) occ = 1;
+            int64_t grid = (int64_t)num_sms() * occ;
+            if (grid > n_units) grid = n_units;
+            Launch L("cov_stream2_kernel", stream);
+            cov_stream2_kernel<<<(unsigned)grid, 32, 0, stream>>>(t);
         }
         MP2_CUDA(cudaGetLastError());
+        // The general path needs 4 bytes per position of scratch (12 GB at C3): it is only allocated when the
+        // gate says the sample has to be redone, which costs one 4-byte read of the gate here.
+        int h_gate = 0;
+        MP2_CUDA(cudaMemcpyAsync(&h_gate, gate, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        MP2_CUDA(cudaStreamSynchronize(stream));
+        if (!h_gate) return MP2_OK;
     }
+    return cov_general_path(starts, ends, ev_off, off, n_contigs, n_events, n_pos, ev_first.as<int32_t>(), tp,
+                            ctrs.as<int>(), (float *)d_cov, cov_stride, (mp2_cov_stats *)d_stats, stream);
+}
 
-    // ---------------- general path: difference array in HBM (gated fallback, or forced) ----------------
+// ---------------- general path: difference array in HBM (any order, any span, any depth) ----------------
+static int cov_general_path(const uint32_t *starts, const uint32_t *ends, const int64_t *ev_off, const int64_t *off,
+                            int64_t n_contigs, int64_t n_events, int64_t n_pos, const int32_t *ev_first,
+                            const TrimParams &tp, int *ctrs, float *d_cov, int64_t cov_stride, mp2_cov_stats *d_stats,
+                            cudaStream_t stream) {
+    const int64_t n_ev_tiles = (n_events + COV_EV_TILE - 1) / COV_EV_TILE;
     const int64_t n_tiles = (n_pos + COV_TILE - 1) / COV_TILE;
-    const int *g = general_only ? nullptr : gate;
+    const int *g = nullptr;  // the kernels below are not gated any more: this function only runs when needed
     Temp D, tile_sum, tile_pre, first, rows, meta, deep_list;
     MP2_TRY(D.alloc(sizeof(int32_t) * (size_t)(n_pos + 4), stream));
     MP2_TRY(tile_sum.alloc(sizeof(int32_t) * n_tiles, stream));
@@ -1525,7 +2083,7 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     MP2_TRY(deep_list.alloc(sizeof(int32_t) * n_contigs, stream));
     MP2_CUDA(cudaMemsetAsync(tile_sum.p, 0, sizeof(int32_t) * n_tiles, stream));
     MP2_CUDA(cudaMemsetAsync(meta.p, 0, sizeof(RowMeta) * n_tiles, stream));
-    {   // the histogram rows (186 MB at C3) and the difference array are only cleared when the path will run
+    {
         Launch L("cov_zero_kernel", stream);
         cov_zero_kernel<<<(unsigned)(num_sms() * 8), 256, 0, stream>>>(rows.as<int4>(), (int64_t)COV_BINS / 4 * n_tiles, g);
         cov_zero_kernel<<<(unsigned)(num_sms() * 8), 256, 0, stream>>>(D.as<int4>(), (n_pos + 3) / 4, g);
@@ -1539,9 +2097,8 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     MP2_CUDA(cudaGetLastError());
     if (n_events > 0) {
         Launch L("cov_scatter_kernel", stream);
-        cov_scatter_kernel<<<(unsigned)std::min<int64_t>(n_ev_tiles, (int64_t)num_sms() * 16), 256, 0, stream>>>(starts, ends, ev_off, off, n_contigs, n_events,
-                                                                   ev_first.as<int32_t>(), D.as<int32_t>(),
-                                                                   tile_sum.as<int32_t>(), g);
+        cov_scatter_kernel<<<(unsigned)std::min<int64_t>(n_ev_tiles, (int64_t)num_sms() * 16), 256, 0, stream>>>(
+            starts, ends, ev_off, off, n_contigs, n_events, ev_first, D.as<int32_t>(), tile_sum.as<int32_t>(), g);
     }
     MP2_CUDA(cudaGetLastError());
     {
@@ -1560,12 +2117,12 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     a.rows = rows.as<uint32_t>();
     a.meta = meta.as<RowMeta>();
     a.deep_list = deep_list.as<int32_t>();
-    a.deep_count = ctrs.as<int>() + 3;
-    a.work_counter = ctrs.as<int>() + 4;
+    a.deep_count = ctrs + 3;
+    a.work_counter = ctrs + 4;
     a.gate = g;
-    a.cov = (float *)d_cov;
+    a.cov = d_cov;
     a.cov_stride = cov_stride;
-    a.stats = (mp2_cov_stats *)d_stats;
+    a.stats = d_stats;
     a.tp = tp;
     int occ = 0;
     MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_depth_kernel, COV_THREADS, 0));
@@ -1579,7 +2136,7 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     MP2_CUDA(cudaGetLastError());
     {
         Launch L("cov_deep_kernel", stream);
-        cov_deep_kernel<<<(unsigned)(num_sms() * 2), COV_THREADS, 0, stream>>>(a, ctrs.as<int>() + 5);
+        cov_deep_kernel<<<(unsigned)(num_sms() * 2), COV_THREADS, 0, stream>>>(a, ctrs + 5);
     }
     MP2_CUDA(cudaGetLastError());
     return MP2_OK;

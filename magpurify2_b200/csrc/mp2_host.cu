@@ -203,8 +203,8 @@ extern "C" int mp2_tnf(const uint8_t *bases, const int64_t *offsets, int64_t n, 
 
 extern "C" int mp2_cov_events(const uint32_t *starts, const uint32_t *ends, const int64_t *ev_off,
                               const int64_t *contig_off, int64_t n_contigs, int64_t n_events,
-                              uint32_t max_span, uint32_t end_excl, float trim_lower, float trim_upper,
-                              int device, float *cov, int64_t cov_stride, mp2_cov_stats *stats) {
+                              uint32_t max_span, uint32_t max_disorder, uint32_t end_excl, float trim_lower,
+                              float trim_upper, int device, float *cov, int64_t cov_stride, mp2_cov_stats *stats) {
     if (n_contigs < 0 || n_events < 0) return fail(MP2_EINVAL, "negative size");
     if (!contig_off || !ev_off || !cov) return fail(MP2_EINVAL, "NULL argument");
     if (n_events > 0 && (!starts || !ends)) return fail(MP2_EINVAL, "NULL events");
@@ -230,7 +230,8 @@ extern "C" int mp2_cov_events(const uint32_t *starts, const uint32_t *ends, cons
     MP2_TRY(upload(d_s.p, starts, sizeof(uint32_t) * n_events, st.comp));
     MP2_TRY(upload(d_e.p, ends, sizeof(uint32_t) * n_events, st.comp));
     MP2_TRY(mp2_cov_events_device(d_s.p, d_e.p, d_eo.p, d_co.p, n_contigs, n_events, contig_off[n_contigs],
-                                  max_span, end_excl, trim_lower, trim_upper, d_cov.p, 1, d_stats.p, st.comp));
+                                  max_span, max_disorder, end_excl, trim_lower, trim_upper, d_cov.p, 1, d_stats.p,
+                                  st.comp));
     MP2_CUDA(cudaStreamSynchronize(st.comp));
     if (cov_stride == 1) {
         MP2_TRY(download(cov, d_cov.p, sizeof(float) * n_contigs, st.comp));

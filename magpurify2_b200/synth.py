@@ -140,9 +140,12 @@ def abundances(n_mags, n_samples, seed=0):
     return a
 
 
-def make_events(lengths, mag_off, sample, seed=0, read_len=READ_LEN, variable=False, depth_scale=1.0):
-    """Host generator of one sample's alignment blocks, grouped by contig and sorted by start
-    inside a contig (BAM order).  Returns (starts u32, ends u32, ev_off i64[n+1])."""
+def make_events(lengths, mag_off, sample, seed=0, read_len=READ_LEN, variable=False, depth_scale=1.0, indel_frac=0.0):
+    """Host generator of one sample's alignment blocks, grouped by contig, in BAM order (reads sorted by
+    position inside a contig, the blocks of a read one after the other).  Returns (starts u32, ends u32,
+    ev_off i64[n+1]).  variable: read length N(read_len, 15) clipped to [50, 250]; indel_frac: that share
+    of the reads carries one insertion or deletion of 1-3 bp (SURVEY 8(d) variant), i.e. two M blocks --
+    the second one starts AFTER the first blocks of the following reads, so the starts are not sorted."""
     n_mags = len(mag_off) - 1
     ab = abundances(n_mags, sample + 1, seed)[:, sample] * depth_scale
     rng = np.random.Generator(np.random.Philox(key=(SEED_COV ^ (sample << 20)) + (seed << 40)))
@@ -164,13 +167,34 @@ def make_events(lengths, mag_off, sample, seed=0, read_len=READ_LEN, variable=Fa
         rl = np.full(R, read_len, dtype=np.int64)
     order = np.lexsort((st, cid))
     st, rl = st[order], rl[order]
-    en = np.minimum(st + rl, lengths[cid])  # a BAM never aligns past the contig end
-    return st.astype(np.uint32), en.astype(np.uint32), ev_off
+    clen = lengths[cid]
+    if indel_frac <= 0.0:
+        en = np.minimum(st + rl, clen)  # a BAM never aligns past the contig end
+        return st.astype(np.uint32), en.astype(np.uint32), ev_off
+    two = rng.random(R) < indel_frac
+    a = np.floor(rng.random(R) * (rl - 20)).astype(np.int64) + 10       # bases before the indel
+    k = rng.integers(1, 4, R)                                            # its length
+    dele = rng.random(R) < 0.5                                           # deletion: gap on the reference
+    s2 = st + a + np.where(dele, k, 0)
+    e2 = s2 + (rl - a - np.where(dele, 0, k))                            # insertion: k read bases are not aligned
+    two &= (e2 <= clen) & (e2 > s2)
+    nb = 1 + two.astype(np.int64)
+    at = np.zeros(R + 1, dtype=np.int64)
+    np.cumsum(nb, out=at[1:])
+    S = np.empty(int(at[-1]), dtype=np.int64)
+    E = np.empty(int(at[-1]), dtype=np.int64)
+    S[at[:-1]] = st
+    E[at[:-1]] = np.where(two, st + a, np.minimum(st + rl, clen))
+    S[at[:-1][two] + 1] = s2[two]
+    E[at[:-1][two] + 1] = e2[two]
+    ev_off2 = at[ev_off]
+    return S.astype(np.uint32), E.astype(np.uint32), ev_off2
 
 
-def make_events_device(lengths, mag_off, sample, device, seed=0, read_len=READ_LEN, depth_scale=1.0):
+def make_events_device(lengths, mag_off, sample, device, seed=0, read_len=READ_LEN, depth_scale=1.0, variant=False):
     """Device generator (bench sizes).  Same model, torch RNG; returns torch tensors
-    (starts u32-as-int32 storage, ends, ev_off int64) on `device`."""
+    (starts u32-as-int32 storage, ends, ev_off int64) on `device`.  variant: read length N(150, 15)
+    clipped to [50, 250] and 2 % of the reads with one 1-3 bp insertion or deletion (two blocks)."""
     import torch
 
     n_mags = len(mag_off) - 1
@@ -197,6 +221,30 @@ def make_events_device(lengths, mag_off, sample, device, seed=0, read_len=READ_L
     key, _ = torch.sort(key)
     st = (key & 0xFFFFFFFF)
     del key
-    starts = st.to(torch.int32)  # bit pattern == uint32 (contigs are < 2^31)
-    ends = (st + read_len).to(torch.int32)
-    return starts, ends, torch.from_numpy(ev_off).to(device), R
+    if not variant:
+        starts = st.to(torch.int32)  # bit pattern == uint32 (contigs are < 2^31)
+        ends = (st + read_len).to(torch.int32)
+        return starts, ends, torch.from_numpy(ev_off).to(device), R
+    cid = torch.repeat_interleave(torch.arange(len(lengths), device=device, dtype=torch.int64), d_n, output_size=R)
+    clen = torch.from_numpy(lengths.astype(np.int64)).to(device)[cid]
+    del cid
+    rl = torch.clamp(torch.round(torch.randn(R, device=device, generator=gen) * 15.0 + read_len), 50, 250).to(torch.int64)
+    two = torch.rand(R, device=device, generator=gen) < 0.02
+    a = torch.floor(torch.rand(R, device=device, generator=gen) * (rl - 20)).to(torch.int64) + 10
+    k = torch.randint(1, 4, (R,), device=device, generator=gen)
+    dele = torch.rand(R, device=device, generator=gen) < 0.5
+    s2 = st + a + torch.where(dele, k, torch.zeros_like(k))
+    e2 = s2 + (rl - a - torch.where(dele, torch.zeros_like(k), k))
+    two &= (e2 <= clen) & (e2 > s2)
+    at = torch.zeros(R + 1, dtype=torch.int64, device=device)
+    torch.cumsum(1 + two.to(torch.int64), 0, out=at[1:])
+    n_blocks = int(at[-1].item())
+    S = torch.empty(n_blocks, dtype=torch.int32, device=device)
+    E = torch.empty(n_blocks, dtype=torch.int32, device=device)
+    first = at[:-1]
+    S[first] = st.to(torch.int32)
+    E[first] = torch.where(two, st + a, torch.minimum(st + rl, clen)).to(torch.int32)
+    S[first[two] + 1] = s2[two].to(torch.int32)
+    E[first[two] + 1] = e2[two].to(torch.int32)
+    ev_off2 = at[torch.from_numpy(ev_off).to(device)]
+    return S, E, ev_off2, n_blocks

@@ -161,7 +161,7 @@ def test_device_entry_strided_columns(covmod, oracle):
         d_en = torch.from_numpy(en.view(np.int32)).cuda()
         d_eo = torch.from_numpy(ev_off).cuda()
         _lib.check(lib.mp2_cov_events_device(d_st.data_ptr(), d_en.data_ptr(), d_eo.data_ptr(), d_off.data_ptr(),
-                                             n, len(st), int(off[-1]), 150, 75, 0.05, 0.05,
+                                             n, len(st), int(off[-1]), 150, 0, 75, 0.05, 0.05,
                                              mat.data_ptr() + 4 * s, S, None,
                                              torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
@@ -223,3 +223,97 @@ def test_wrong_vouched_span_is_caught(covmod, oracle):
     want, _ = oracle.cov_sample(s, e, [0, 2000], [ln], 75, 0.05, 0.05)
     assert np.array_equal(covmod.cov_from_events(s, e, [0, 2000], [0, ln], 75, 0.05, 0.05), want)
     assert np.array_equal(covmod.cov_from_events(s, e, [0, 2000], [0, ln], 75, 0.05, 0.05, max_span=5000), want)
+
+
+GENERAL = 1  # mp2.h MP2_COV_GENERAL_PATH
+
+
+def _disorder(st, ev_off, lengths):
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    cid = np.repeat(np.arange(len(lengths)), np.diff(ev_off))
+    g = off[cid] + st.astype(np.int64)
+    return int((np.maximum.accumulate(g) - g).max()) if len(g) else 0
+
+
+@pytest.mark.parametrize("mode", ["measured", "vouched"])
+def test_indel_variant_takes_the_fast_path(covmod, oracle, mode):
+    """SURVEY 8(d) variant: read length N(150,15), 5 % of the reads with one I / D (two blocks, the second one
+    out of order).  Bit-exact, and computed by the shared-memory path (flags == 0 everywhere)."""
+    from magpurify2_b200 import synth
+
+    lengths, mag_off, _gc = synth.mag_layout(5, seed=12, mean_bp=9e5, n_contigs=60)
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    st, en, ev_off = synth.make_events(lengths, mag_off, 2, seed=12, variable=True, indel_frac=0.05)
+    dis = _disorder(st, ev_off, lengths)
+    assert dis > 0 and (np.diff(st.astype(np.int64)) < 0).sum() > len(lengths)  # really unsorted
+    kw = {} if mode == "measured" else dict(max_span=int((en - st).max()), max_disorder=dis)
+    cov, stats = covmod.cov_from_events(st, en, ev_off, off, 75, 0.05, 0.05, want_stats=True, **kw)
+    wcov, wst = oracle.cov_sample(st, en, ev_off, lengths, 75, 0.05, 0.05, threads=8)
+    for f in INT_FIELDS:
+        assert np.array_equal(stats[f], wst[f]), f
+    assert np.array_equal(cov.view(np.uint32), wcov.view(np.uint32))
+    assert not (stats["flags"] & GENERAL).any()
+
+
+def test_large_disorder_goes_to_the_general_path(covmod, oracle):
+    from magpurify2_b200 import synth
+
+    lengths, mag_off, _gc = synth.mag_layout(2, seed=13, mean_bp=4e5, n_contigs=30)
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    st, en, ev_off = synth.make_events(lengths, mag_off, 0, seed=13)
+    rng = np.random.default_rng(13)
+    for c in range(len(lengths)):  # shuffle inside every contig: disorder = contig length
+        p = rng.permutation(ev_off[c + 1] - ev_off[c]) + ev_off[c]
+        st[ev_off[c]:ev_off[c + 1]], en[ev_off[c]:ev_off[c + 1]] = st[p], en[p]
+    cov, stats = covmod.cov_from_events(st, en, ev_off, off, 75, 0.05, 0.05, want_stats=True)
+    wcov, wst = oracle.cov_sample(st, en, ev_off, lengths, 75, 0.05, 0.05, threads=8)
+    assert np.array_equal(stats["total"], wst["total"]) and np.array_equal(cov.view(np.uint32), wcov.view(np.uint32))
+    has_window = lengths > 150
+    assert (stats["flags"][has_window] & GENERAL).all()
+    # a caller vouching for more disorder than the kernel takes: general path as well, same numbers
+    cov2 = covmod.cov_from_events(st, en, ev_off, off, 75, 0.05, 0.05, max_span=150, max_disorder=100000)
+    assert np.array_equal(cov2.view(np.uint32), wcov.view(np.uint32))
+
+
+@pytest.mark.parametrize("shift", [1, 2, 3])
+def test_event_arrays_at_any_4_byte_alignment(covmod, oracle, shift):
+    """The event ring is filled by 16-byte bulk copies; the arrays may start at any 4-byte boundary."""
+    import torch
+
+    from magpurify2_b200 import _lib, synth
+
+    lengths, mag_off, _gc = synth.mag_layout(3, seed=14, mean_bp=6e5, n_contigs=50)
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    st, en, ev_off = synth.make_events(lengths, mag_off, 1, seed=14, variable=True, indel_frac=0.03)
+    want, _ = oracle.cov_sample(st, en, ev_off, lengths, 75, 0.05, 0.05, threads=8)
+    n, R = len(lengths), len(st)
+    pad = np.zeros(shift, np.int32)
+    d_st = torch.from_numpy(np.concatenate([pad, st.view(np.int32)])).cuda()[shift:]
+    d_en = torch.from_numpy(np.concatenate([pad, pad, en.view(np.int32)])).cuda()[2 * shift:]
+    d_eo, d_off = torch.from_numpy(ev_off).cuda(), torch.from_numpy(off).cuda()
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    lib = _lib.load()
+    _lib.check(lib.mp2_cov_events_device(d_st.data_ptr(), d_en.data_ptr(), d_eo.data_ptr(), d_off.data_ptr(), n, R,
+                                         int(off[-1]), 0, 0, 75, 0.05, 0.05, out.data_ptr(), 1, None,
+                                         torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_sparse_and_empty_contigs(covmod, oracle):
+    """Runs of contigs without any event, events only at the very end, single events: the contig cursor of the
+    event stream has to gallop over empty contigs."""
+    rng = np.random.default_rng(15)
+    lengths = rng.integers(1, 4000, 3000).astype(np.int64)
+    lengths[::7] = rng.integers(60000, 200000, len(lengths[::7]))
+    n_reads = np.zeros(len(lengths), dtype=np.int64)
+    pick = rng.random(len(lengths)) < 0.03
+    n_reads[pick] = rng.integers(1, 400, int(pick.sum()))
+    n_reads[lengths < 160] = 0
+    ev_off = np.concatenate([[0], np.cumsum(n_reads)])
+    cid = np.repeat(np.arange(len(lengths)), n_reads)
+    st = np.floor(rng.random(len(cid)) * (lengths[cid] - 150)).astype(np.int64)
+    order = np.lexsort((st, cid))
+    st = st[order].astype(np.uint32)
+    en = (st + 150).astype(np.uint32)
+    check_sample(covmod, oracle, st, en, ev_off, lengths, 75, 0.05, 0.05)

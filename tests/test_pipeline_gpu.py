@@ -108,6 +108,53 @@ def test_get_bam_coverages(tmp_path, oracle):
         tools.get_bam_coverages(str(bams[0]))
 
 
+def test_get_bam_coverages_with_indel_and_spliced_cigars(tmp_path, oracle):
+    """BAMs whose reads carry D / N / I / S / H / = / X operations (two or three blocks per read, the later
+    ones out of start order) through get_bam_coverages: bit-exact against the oracle's record walk + depth
+    arithmetic, and computed by the shared-memory path -- not the HBM fallback -- for every contig."""
+    from magpurify2_b200 import bamio, tools
+
+    rng = np.random.default_rng(77)
+    names = [f"c{i}" for i in range(30)]
+    lengths = rng.integers(200, 60000, 30).astype(np.int64)
+    lengths[3], lengths[11] = 140, 100000
+    shapes = [
+        [("M", 150)],
+        [("S", 10), ("M", 70), ("I", 2), ("M", 68)],
+        [("M", 60), ("D", 3), ("M", 90)],
+        [("=", 50), ("X", 1), ("=", 99)],
+        [("H", 5), ("M", 40), ("N", 120), ("M", 110)],
+        [("M", 30), ("D", 1), ("M", 30), ("I", 1), ("M", 30), ("N", 60), ("M", 58)],
+        [("M", 100)],
+    ]
+    recs, want_ev = [], [[] for _ in names]
+    for tid, ln in enumerate(lengths.tolist()):
+        if ln < 600:
+            continue
+        pos = np.sort(rng.integers(0, ln - 420, int(ln * 20 / 150)))
+        for p in pos.tolist():
+            cig = shapes[int(rng.choice(len(shapes), p=[0.55, 0.1, 0.1, 0.05, 0.08, 0.07, 0.05]))]
+            flag = int(rng.choice([0, 1, 0x10, 0x100, 0x800, 0x400], p=[0.8, 0.08, 0.08, 0.015, 0.015, 0.01]))
+            nm = int(rng.binomial(150, 0.012))
+            recs.append(dict(tid=tid, pos=p, cigar=cig, flag=flag, nm=nm))
+            packed = [(l << 4) | bamio.CIGAR_OPS.index(op) for op, l in cig]
+            want_ev[tid] += oracle.record_events(flag, tid, p, packed, nm, 0.97)
+    path = tmp_path / "spliced.bam"
+    bamio.write_bam(str(path), names, lengths.tolist(), recs)
+    st = np.array([e[0] for ev in want_ev for e in ev], dtype=np.uint32)
+    en = np.array([e[1] for ev in want_ev for e in ev], dtype=np.uint32)
+    ev_off = np.concatenate([[0], np.cumsum([len(ev) for ev in want_ev])]).astype(np.int64)
+    assert (np.diff(st.astype(np.int64)) < 0).sum() > 100  # the later blocks really are out of order
+    want, wst = oracle.cov_sample(st, en, ev_off, lengths, 75, 0.05, 0.05, threads=4)
+    stats = []
+    got_names, mat = tools.get_bam_coverages([str(path)], min_identity=0.97, trim_lower=0.05, trim_upper=0.05,
+                                             threads=4, stats_out=stats)
+    assert got_names == names
+    assert np.array_equal(mat[:, 0].view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(stats[0]["total"], wst["total"]) and np.array_equal(stats[0]["max_depth"], wst["max_depth"])
+    assert not (stats[0]["flags"] & 1).any(), "fell back to the general path"
+
+
 def test_cli_composition_and_coverage(tmp_path, oracle):
     from magpurify2_b200 import cli
 
