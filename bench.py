@@ -238,7 +238,7 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
     ms_one_stream = e2.elapsed_time(e3)
     kern = {}
     for name in ("cov_stream2_kernel", "cov_stream_kernel", "cov_tile_kernel", "cov_scatter_kernel", "cov_depth_kernel",
-                 "cov_deep_kernel", "cov_keymax_kernel", "cov_keyscan_kernel", "cov_check_kernel", "cov_bounds_kernel",
+                 "cov_deep_kernel", "cov_order_kernel", "cov_order_scan_kernel", "cov_bounds_kernel",
                  "cov_zero_kernel"):
         k_ms, k_n = C.c_double(0), C.c_int64(0)
         lib.mp2_profile_read(name.encode(), C.byref(k_ms), C.byref(k_n))
@@ -356,8 +356,9 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
                 "api": "magpurify2_b200._coverage.cov_from_events (mp2_cov_events, pinned host buffers, 1 sample)"},
         "gpu_launches": int(launches),
         "deep_fallback_ms": kern["cov_deep_kernel"][0] / max(1, kern["cov_deep_kernel"][1]),
-        "order_check_ms_per_sample": sum(kern[k][0] for k in ("cov_keymax_kernel", "cov_keyscan_kernel", "cov_check_kernel"))
+        "order_check_ms_per_sample": sum(kern[k][0] for k in ("cov_order_kernel", "cov_order_scan_kernel"))
                                      / max(1, args.steps * S),
+        "kernel_ms_per_sample": {k: round(v[0] / max(1, args.steps * S), 4) for k, v in kern.items() if v[1]},
         "legs": legs,
     }
     if not args.no_cpu:

@@ -71,7 +71,6 @@ def tnf_from_concat(bases, offsets, relative=True, want_gc=False, want_counts=Fa
     bases = np.ascontiguousarray(bases, dtype=np.uint8)
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     n = len(offsets) - 1
-    lib = _lib.load()
     counts = rel = gc = None
     if want_counts or not relative or out_counts is not None:
         counts = _check_out(out_counts, (n, NCANON), np.uint32, "out_counts") if out_counts is not None \
@@ -81,9 +80,14 @@ def tnf_from_concat(bases, offsets, relative=True, want_gc=False, want_counts=Fa
             else _out((n, NCANON), np.float32)
     if want_gc or out_gc is not None:
         gc = _check_out(out_gc, (n,), np.float32, "out_gc") if out_gc is not None else np.empty(n, dtype=np.float32)
-    _lib.check(lib.mp2_tnf(_lib.ptr(bases), _lib.ptr(offsets), n, device,
-                           _lib.ptr(counts), _lib.ptr(rel), _lib.ptr(gc)))
+    _run(bases, offsets, counts, rel, gc, device)
     return counts, rel, gc
+
+
+def _run(bases, offsets, counts, rel, gc, device=-1):
+    """The one native call of this module: mp2_tnf on host arrays (any of counts / rel / gc may be None)."""
+    _lib.check(_lib.load().mp2_tnf(_lib.ptr(bases), _lib.ptr(offsets), len(offsets) - 1, device,
+                                   _lib.ptr(counts), _lib.ptr(rel), _lib.ptr(gc)))
 
 
 def get_tnf(seq_list, relative=True, threads=1):
@@ -101,6 +105,5 @@ def get_gc(seq_list):
     bases, offsets = _concat(seq_list)
     n = len(offsets) - 1
     gc = np.empty(n, dtype=np.float32)
-    _lib.check(_lib.load().mp2_tnf(_lib.ptr(bases), _lib.ptr(offsets), n, -1, None, None,
-                                   _lib.ptr(gc)))
+    _run(bases, offsets, None, None, gc)
     return gc

@@ -44,12 +44,21 @@ def cov_from_events(starts, ends, ev_off, contig_off, contig_end_exclusion=75, t
 
 
 def get_bam_coverages(bam_list, contig_end_exclusion=75, min_identity=0.97, trim_lower=0.0, trim_upper=0.0,
-                      contig_set=None, threads=1, *, device=-1, stats_out=None):
+                      contig_set=None, threads=1, *, device=-1, devices=None, stats_out=None):
     """Trimmed-mean coverage of every contig in every BAM (src/coverage.rs:81-206).
 
     Returns (names, float32[n_contigs, n_bams]); columns follow bam_list.  Rows follow the @SQ
     order of the first BAM (the reference returns them in Rust HashMap order, i.e. arbitrary:
-    callers index by name, magpurify2/modules/coverage.py:113-119)."""
+    callers index by name, magpurify2/modules/coverage.py:113-119).
+
+    The BAMs are decoded on the host (`threads` inflate / filter workers, one file at a time) while the
+    GPUs work on the files decoded before: file s+1 is being decoded while file s is uploaded and
+    reduced (the reference reads the BAMs strictly one after the other, src/coverage.rs:125-142).
+    `devices` (keyword only, not in the reference) spreads the files over several GPUs: samples are
+    independent columns of the result, so there is no exchange between devices."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+
     from . import _bam
 
     if isinstance(bam_list, (str, bytes)):
@@ -57,27 +66,65 @@ def get_bam_coverages(bam_list, contig_end_exclusion=75, min_identity=0.97, trim
     bam_list = [str(b) for b in bam_list]
     if not bam_list:
         raise ValueError("bam_list is empty")
-    names = None
-    cols = []
-    for path in bam_list:
-        with _bam.BamEvents(path, min_identity=min_identity, threads=threads) as b:
-            if names is None:
-                names, lengths = b.names, b.lengths
-                contig_off = np.zeros(len(lengths) + 1, dtype=np.int64)
-                np.cumsum(lengths, out=contig_off[1:])
-            elif b.names != names:
-                raise ValueError(f"{path}: @SQ lines differ from {bam_list[0]} (the reference assumes identical headers)")
-            # the reader emits blocks in BAM order and measures, while it decodes, the longest block and how
-            # far a block of a read with D / N operations can start behind the next reads' first blocks
-            res = cov_from_events(b.starts, b.ends, b.ev_off, contig_off, contig_end_exclusion,
-                                  trim_lower, trim_upper, device=device, max_span=b.max_block,
+    devices = [device] if not devices else list(devices)
+    n_bams = len(bam_list)
+    header = {}                      # names / lengths / contig_off of the first file, set by whoever decodes it
+    header_lock = threading.Lock()
+    in_flight = threading.Semaphore(len(devices) + 1)  # decoded samples waiting for, or on, a GPU
+    cols = [None] * n_bams
+    stats = [None] * n_bams
+
+    def decode(s):
+        in_flight.acquire()
+        try:
+            b = _bam.BamEvents(bam_list[s], min_identity=min_identity, threads=threads)
+        except BaseException:
+            in_flight.release()
+            raise
+        with header_lock:
+            if not header:
+                off = np.zeros(len(b.lengths) + 1, dtype=np.int64)
+                np.cumsum(b.lengths, out=off[1:])
+                header.update(names=b.names, contig_off=off, first=bam_list[s])
+            elif b.names != header["names"]:
+                b.close()
+                in_flight.release()
+                raise ValueError(f"{bam_list[s]}: @SQ lines differ from {header['first']} (the reference assumes "
+                                 "identical headers)")
+        return b
+
+    def reduce_on(dev, s, fut):
+        b = fut.result()
+        try:
+            # the reader measured, while decoding, the longest block and how far a block of a read with D / N
+            # operations can start behind the first blocks of the following reads
+            res = cov_from_events(b.starts, b.ends, b.ev_off, header["contig_off"], contig_end_exclusion,
+                                  trim_lower, trim_upper, device=dev, max_span=b.max_block,
                                   max_disorder=b.max_disorder, want_stats=stats_out is not None)
-            if stats_out is not None:  # per-contig integers of every BAM (tests: which path computed them)
-                stats_out.append(res[1])
-                res = res[0]
-            cols.append(res)
+            if stats_out is not None:
+                cols[s], stats[s] = res
+            else:
+                cols[s] = res
+        finally:
+            b.close()
+            in_flight.release()
+
+    with ThreadPoolExecutor(max_workers=1) as decoder:
+        lanes = [ThreadPoolExecutor(max_workers=1) for _ in devices]
+        try:
+            decoded = [decoder.submit(decode, s) for s in range(n_bams)]
+            done = [lanes[s % len(devices)].submit(reduce_on, devices[s % len(devices)], s, decoded[s])
+                    for s in range(n_bams)]
+            for f in done:
+                f.result()
+        finally:
+            for ln in lanes:
+                ln.shutdown(wait=True, cancel_futures=True)
+    names = header.get("names")
     if not names:
         raise ValueError("no reference sequences in the BAM header")  # the reference panics (coverage.rs:200)
+    if stats_out is not None:  # per-contig integers of every BAM (tests: which path computed them)
+        stats_out.extend(stats)
     mat = np.stack(cols, axis=1).astype(np.float32, copy=False)
     if contig_set is not None:
         keep = np.fromiter((nm in contig_set for nm in names), dtype=bool, count=len(names))

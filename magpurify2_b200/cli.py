@@ -38,6 +38,9 @@ def _other(other):
     other.add_argument("-t", "--threads", default=multiprocessing.cpu_count(), type=int,
                        help="Host threads (BGZF inflate / BAM record filter). All by default.")
     other.add_argument("--device", default=-1, type=int, help="CUDA device (default: current).")
+    other.add_argument("--devices", default=None, type=str,
+                       help="Several CUDA devices, e.g. '0,1,2,3' or 'all': MAGs (composition) and BAM files "
+                            "(coverage) are dealt out to them; overrides --device.")
     other.add_argument("-q", "--quiet", help="Suppress the logger output", action="store_true")
 
 

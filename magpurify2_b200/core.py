@@ -76,26 +76,26 @@ def _mag_offsets(mags):
     return off
 
 
-def score_composition_batch(mags, counts, gc):
+def score_composition_batch(mags, counts, gc, device=-1):
     """counts uint32[n,136], gc float32[n] for all contigs of `mags` stacked.
     Returns (tnf_scores f64[n], gc_content_scores f64[n])."""
     mag_off = _mag_offsets(mags)
     lengths = np.concatenate([m.lengths for m in mags]) if mags else np.zeros(0, np.int64)
-    dist = _scoring.clr_centroid_batch(counts, lengths, mag_off)
+    dist = _scoring.clr_centroid_batch(counts, lengths, mag_off, device=device)
     tnf = _scoring.log_ratio_scores_batch(dist.astype(np.float32), lengths, mag_off, TNF_SCORE_BASE,
-                                          min_rows=3, one_sided=True)
-    gcs = _scoring.log_ratio_scores_batch(gc, lengths, mag_off, 2, min_rows=3)  # core.py:261-263
+                                          min_rows=3, one_sided=True, device=device)
+    gcs = _scoring.log_ratio_scores_batch(gc, lengths, mag_off, 2, min_rows=3, device=device)  # core.py:261-263
     return tnf, gcs
 
 
-def score_coverage_batch(mags, coverages, min_average_coverage):
+def score_coverage_batch(mags, coverages, min_average_coverage, device=-1):
     """coverages float32[n, n_samples] stacked over `mags`.
     Returns (scores f64[n], n_samples int[n_mags], selected bool[n_mags, n_samples])."""
     mag_off = _mag_offsets(mags)
     lengths = np.concatenate([m.lengths for m in mags]) if mags else np.zeros(0, np.int64)
     cov = np.ascontiguousarray(coverages, dtype=np.float32)
-    sel, _means = _scoring.select_samples_batch(cov, lengths, mag_off, min_average_coverage)  # core.py:301-305
-    scores = _scoring.log_ratio_scores_batch(cov, lengths, mag_off, 25, col_mask=sel, min_rows=3)  # :310-312
+    sel, _means = _scoring.select_samples_batch(cov, lengths, mag_off, min_average_coverage, device=device)  # core.py:301-305
+    scores = _scoring.log_ratio_scores_batch(cov, lengths, mag_off, 25, col_mask=sel, min_rows=3, device=device)  # :310-312
     return scores, sel.sum(axis=1), sel
 
 
@@ -106,8 +106,8 @@ class Composition:
                  min_dist=None, n_neighbors=None, set_op_mix_ratio=None, *, scores=None):
         """Reference shape: Composition(mag, composition_dict, gc_content, <UMAP options>)
         (core.py:225-235).  composition_dict[mag.genome] must hold the RAW uint32 counts
-        (get_tnf(..., relative=False)) or the relative profile together with lengths (the counts are
-        then recovered as round(rel * (len - 3)) only when no base was skipped, so pass counts).
+        (get_tnf(..., relative=False)) or, as in the reference, the relative profile (the counts are then
+        counted again from mag.bases).
         `scores=(tnf, gc)` short-circuits to precomputed batch results."""
         self.attributes = list(Composition.attributes)
         self.genome = mag.genome
@@ -123,7 +123,16 @@ class Composition:
         else:
             counts = np.asarray(self.tnf)
             if counts.dtype != np.uint32:
-                raise TypeError("Composition needs the raw uint32 4-mer counts (get_tnf(..., relative=False))")
+                # the reference's callers (and tnfs.pickle.gz) hold the RELATIVE profile, which is what
+                # tools.get_tnf returns by default; the CLR score needs the raw counts, so they are counted
+                # again from the sequences (one kernel launch)
+                if getattr(mag, "bases", None) is None:
+                    raise TypeError("Composition got a relative TNF profile and a Mag without sequences: pass the raw "
+                                    "uint32 counts (get_tnf(..., relative=False)) or read the Mag with "
+                                    "store_sequences=True")
+                from . import _composition
+
+                counts, _rel, _gc = _composition.tnf_from_concat(mag.bases, mag.offsets, relative=False)
             self.tnf_scores, self.gc_content_scores = score_composition_batch([mag], counts, gc_content)
 
     def __len__(self):

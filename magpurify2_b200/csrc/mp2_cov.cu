@@ -21,6 +21,7 @@
 //                        depth ranges; rare).
 #include <algorithm>
 #include <climits>
+#include <cstddef>
 #include <cstdlib>
 #include <mutex>
 
@@ -562,7 +563,7 @@ cov_deep_kernel(const DepthArgs a, int *__restrict__ deep_next) {
 // =====================================================================================================
 // Fast path: the difference array never leaves shared memory.
 //
-// Precondition (checked by cov_check_kernel unless the caller vouches for it with max_span > 0):
+// Precondition (checked by cov_order_kernel unless the caller vouches for it with max_span > 0):
 // starts are non-decreasing inside every contig and end - start <= max_span.  Then the blocks that
 // can touch the slots [lo, hi) of the concatenated coordinate space are one contiguous range of
 // the event arrays (global start in [lo - max_span, hi)), found by two binary searches.
@@ -602,7 +603,7 @@ __global__ void cov_bounds_kernel(const uint32_t *__restrict__ starts, const int
                                   int32_t *__restrict__ c_hi) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n_tiles) return;
-    if (d_span) max_span = d_span[1];  // measured by cov_check_kernel
+    if (d_span) max_span = d_span[1];  // measured by cov_order_kernel
     const int64_t A = k * CT_TILE - (int64_t)max_span, B = (k + 1) * CT_TILE;
     e_lo[k] = first_event_ge(starts, ev_off, off, n, A);
     e_hi[k] = first_event_ge(starts, ev_off, off, n, B);
@@ -617,123 +618,87 @@ __global__ void cov_bounds_kernel(const uint32_t *__restrict__ starts, const int
 // i.e. how far a start may fall behind the running maximum.  A BAM is sorted by read position, so the first
 // blocks of the reads are in order, but the second block of a read with a D / N operation starts after the
 // next reads' first blocks: the disorder is bounded by the reference footprint of a read (a few hundred bp),
-// not zero.  Three small kernels: per-tile maxima of g, their exclusive prefix maximum, then the exact
-// in-tile prefix maximum.  flag[0] = 1: starts go back (old kernels need disorder == 0), flag[1] = longest
+// not zero.  flag[0] = 1: starts go back (old kernels need disorder == 0), flag[1] = longest
 // block, flag[2] = disorder.  Events that are dropped anyway (start beyond the contig, empty) do not count.
-__device__ __forceinline__ long long cov_event_key(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends,
-                                                   const int64_t *__restrict__ ev_off, const int64_t *__restrict__ off,
-                                                   int64_t c_first, int64_t c_last, int64_t e, uint32_t &span) {
-    const int64_t c = c_first == c_last ? c_first : last_le(ev_off, c_first, c_last + 1, e);
-    const int64_t base = off[c], len = off[c + 1] - base;
-    const int64_t s = starts[e];
-    int64_t en = ends[e];
-    if (en > len) en = len;
-    span = 0;
-    if (!(s < len && en > s)) return -1;  // dropped by every path
-    span = (uint32_t)(en - s);
-    return (long long)(base + s);
-}
+// One pass over the events: every CTA takes a tile of 2048 consecutive events, every thread 8 consecutive ones
+// (a contig cursor walks along, so the contig of an event costs a comparison, not a search).  Per tile:
+// largest and smallest key, the disorder INSIDE the tile (against the tile's own running maximum) and the
+// longest block.  The disorder against everything before the tile is (largest key before the tile) - (smallest
+// key of the tile); cov_order_scan_kernel takes that maximum over the tiles.  Together: exact.
+struct OrderTile {
+    long long kmax, kmin;
+};
 
 __global__ void __launch_bounds__(256)
-cov_keymax_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends,
-                  const int64_t *__restrict__ ev_off, const int64_t *__restrict__ off, int64_t n, int64_t n_events,
-                  const int32_t *__restrict__ ev_first, long long *__restrict__ tile_max) {
-    __shared__ long long s_w[8];
-    const int64_t t0 = (int64_t)blockIdx.x * COV_EV_TILE;
-    const int64_t t_last = t0 + COV_EV_TILE - 1 < n_events - 1 ? t0 + COV_EV_TILE - 1 : n_events - 1;
-    const int64_t c_first = ev_first[blockIdx.x];
-    const int64_t c_last = last_le(ev_off, c_first, n, t_last);
-    long long m = -1;
-    for (int k = 0; k < COV_EV_TILE / 256; k++) {
-        const int64_t e = t0 + k * 256 + threadIdx.x;
-        if (e < n_events) {
-            uint32_t sp;
-            const long long g = cov_event_key(starts, ends, ev_off, off, c_first, c_last, e, sp);
-            m = g > m ? g : m;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const long long t = __shfl_xor_sync(0xffffffffu, m, o);
-        m = t > m ? t : m;
-    }
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; w++) m = s_w[w] > m ? s_w[w] : m;
-        tile_max[blockIdx.x] = m;
-    }
-}
-
-// exclusive prefix maximum of the tile maxima (one CTA; n_tiles = n_events / 2048)
-__global__ void __launch_bounds__(1024)
-cov_keyscan_kernel(const long long *__restrict__ tile_max, int64_t n_tiles, long long *__restrict__ tile_pre) {
-    __shared__ long long s_w[32];
-    __shared__ long long s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = -1;
-    __syncthreads();
-    for (int64_t b = 0; b < n_tiles; b += 1024) {
-        const int64_t i = b + tid;
-        const long long v = i < n_tiles ? tile_max[i] : -1;
-        long long incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o && t > incl) incl = t;
-        }
-        long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) excl = -1;
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        long long wpre = s_carry;
-        for (int w = 0; w < warp; w++) wpre = s_w[w] > wpre ? s_w[w] : wpre;
-        if (i < n_tiles) tile_pre[i] = excl > wpre ? excl : wpre;
-        __syncthreads();
-        if (tid == 1023) s_carry = incl > wpre ? incl : wpre;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(256)
-cov_check_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends,
+cov_order_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends,
                  const int64_t *__restrict__ ev_off, const int64_t *__restrict__ off, int64_t n, int64_t n_events,
-                 const int32_t *__restrict__ ev_first, const long long *__restrict__ tile_pre,
-                 unsigned int *__restrict__ flag) {
+                 const int32_t *__restrict__ ev_first, OrderTile *__restrict__ tiles, unsigned int *__restrict__ flag) {
     constexpr int PER = COV_EV_TILE / 256;  // consecutive events per thread
     __shared__ long long s_w[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t t0 = (int64_t)blockIdx.x * COV_EV_TILE;
-    const int64_t t_last = t0 + COV_EV_TILE - 1 < n_events - 1 ? t0 + COV_EV_TILE - 1 : n_events - 1;
-    const int64_t c_first = ev_first[blockIdx.x];
-    const int64_t c_last = last_le(ev_off, c_first, n, t_last);
+    const int64_t e0 = t0 + (int64_t)tid * PER;
     long long g[PER];
-    long long tmax = -1;
+    long long tmax = -1, tmin = LLONG_MAX;
     unsigned int span = 0;
+    if (e0 < n_events) {
+        int64_t c = last_le(ev_off, ev_first[blockIdx.x], n, e0);
+        int64_t next = ev_off[c + 1], base = off[c], len = off[c + 1] - base;
+        uint32_t sv[PER], ev[PER];
+        if (e0 + PER <= n_events && ((reinterpret_cast<uintptr_t>(starts + e0) | reinterpret_cast<uintptr_t>(ends + e0)) & 15) == 0) {
 #pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const int64_t e = t0 + (int64_t)tid * PER + k;
-        g[k] = -1;
-        if (e < n_events) {
-            uint32_t sp;
-            g[k] = cov_event_key(starts, ends, ev_off, off, c_first, c_last, e, sp);
-            span = sp > span ? sp : span;
+            for (int k = 0; k < PER; k += 4) {
+                const uint4 a4 = __ldg(reinterpret_cast<const uint4 *>(starts + e0 + k));
+                const uint4 b4 = __ldg(reinterpret_cast<const uint4 *>(ends + e0 + k));
+                sv[k] = a4.x; sv[k + 1] = a4.y; sv[k + 2] = a4.z; sv[k + 3] = a4.w;
+                ev[k] = b4.x; ev[k + 1] = b4.y; ev[k + 2] = b4.z; ev[k + 3] = b4.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                sv[k] = e0 + k < n_events ? __ldg(starts + e0 + k) : 0u;
+                ev[k] = e0 + k < n_events ? __ldg(ends + e0 + k) : 0u;
+            }
         }
-        tmax = g[k] > tmax ? g[k] : tmax;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int64_t e = e0 + k;
+            g[k] = -1;
+            if (e < n_events) {
+                while (e >= next) {  // next contig that has events
+                    c++;
+                    next = ev_off[c + 1];
+                    base = off[c];
+                    len = off[c + 1] - base;
+                }
+                const int64_t s = sv[k];
+                int64_t en = ev[k];
+                if (en > len) en = len;
+                if (s < len && en > s) {  // anything else is dropped by every path
+                    g[k] = base + s;
+                    const unsigned int sp = (unsigned int)(en - s);
+                    span = sp > span ? sp : span;
+                    tmax = g[k] > tmax ? g[k] : tmax;
+                    tmin = g[k] < tmin ? g[k] : tmin;
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < PER; k++) g[k] = -1;
     }
+    // exclusive prefix maximum of the thread maxima inside the tile
     long long incl = tmax;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const long long t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o && t > incl) incl = t;
     }
-    long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) excl = -1;
+    long long pm = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) pm = -1;
     if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    long long pm = tile_pre[blockIdx.x];
     for (int w = 0; w < warp; w++) pm = s_w[w] > pm ? s_w[w] : pm;
-    pm = excl > pm ? excl : pm;  // maximum of every key before this thread's first event
     unsigned long long dis = 0;
 #pragma unroll
     for (int k = 0; k < PER; k++) {
@@ -745,10 +710,63 @@ cov_check_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict
     unsigned int d32 = dis > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned int)dis;
     span = __reduce_max_sync(0xffffffffu, span);
     d32 = __reduce_max_sync(0xffffffffu, d32);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long t = __shfl_xor_sync(0xffffffffu, tmin, o);
+        tmin = t < tmin ? t : tmin;
+    }
+    __shared__ long long s_min[8];
     if (lane == 0) {
+        s_min[warp] = tmin;
         if (d32) { atomicOr(&flag[0], 1u); atomicMax(&flag[2], d32); }
         if (span) atomicMax(&flag[1], span);
     }
+    __syncthreads();
+    if (tid == 0) {
+        long long mx = -1, mn = LLONG_MAX;
+        for (int w = 0; w < 8; w++) {
+            mx = s_w[w] > mx ? s_w[w] : mx;
+            mn = s_min[w] < mn ? s_min[w] : mn;
+        }
+        tiles[blockIdx.x].kmax = mx;
+        tiles[blockIdx.x].kmin = mn;
+    }
+}
+
+// disorder across tiles: max over the tiles of (largest key before the tile) - (smallest key of the tile)
+__global__ void __launch_bounds__(1024)
+cov_order_scan_kernel(const OrderTile *__restrict__ tiles, int64_t n_tiles, unsigned int *__restrict__ flag) {
+    __shared__ long long s_w[32];
+    __shared__ long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = -1;
+    __syncthreads();
+    unsigned long long dis = 0;
+    for (int64_t b = 0; b < n_tiles; b += 1024) {
+        const int64_t i = b + tid;
+        const long long v = i < n_tiles ? tiles[i].kmax : -1;
+        const long long mn = i < n_tiles ? tiles[i].kmin : LLONG_MAX;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o && t > incl) incl = t;
+        }
+        long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = -1;
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        long long pre = s_carry;
+        for (int w = 0; w < warp; w++) pre = s_w[w] > pre ? s_w[w] : pre;
+        pre = excl > pre ? excl : pre;  // largest key before tile i
+        if (mn != LLONG_MAX && pre > mn && (unsigned long long)(pre - mn) > dis) dis = (unsigned long long)(pre - mn);
+        __syncthreads();
+        if (tid == 1023) s_carry = incl > pre ? incl : pre;
+        __syncthreads();
+    }
+    unsigned int d32 = dis > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned int)dis;
+    d32 = __reduce_max_sync(0xffffffffu, d32);
+    if (lane == 0 && d32) { atomicOr(&flag[0], 1u); atomicMax(&flag[2], d32); }
 }
 
 constexpr int CT_CTAB = 96;  // contigs of a tile whose offsets are staged in shared memory
@@ -1159,7 +1177,7 @@ constexpr int C3_PF = MP2_C3_PF;             // events ahead of e_cur that are p
 __device__ __forceinline__ int c3_phys(int i) { return i + 4 * (i >> C3_SPL_LOG); }
 
 // Event range and contigs of every run.  `meas` = {unsorted, longest block, disorder} measured by
-// cov_check_kernel, or NULL when the caller vouched for (max_span, max_disorder).  The ranges are computed with
+// cov_order_kernel, or NULL when the caller vouched for (max_span, max_disorder).  The ranges are computed with
 // the LARGEST margins the kernels support (span + disorder <= C3_S), so they do not depend on the measured
 // values: with starts that fall at most `disorder` behind their running maximum, a binary search for X ends
 // between the first event whose running maximum reaches X and the first one whose running maximum reaches
@@ -1513,18 +1531,42 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
 //     is one OR chain; the highest occupied bin is looked up when the contig closes instead of being
 //     tracked per position.
 // =====================================================================================================
-constexpr int C4_STAGE = 64;                 // events per bulk copy and array (256 bytes)
-constexpr int C4_NST = 4;                    // stages = mbarriers
+#ifndef MP2_C4_STAGE
+#define MP2_C4_STAGE 64
+#endif
+#ifndef MP2_C4_NST
+#define MP2_C4_NST 4
+#endif
+constexpr int C4_STAGE = MP2_C4_STAGE;       // events per bulk copy and array (a power of two, >= 64)
+constexpr int C4_NST = MP2_C4_NST;           // stages = mbarriers (a power of two)
+static_assert((C4_STAGE & (C4_STAGE - 1)) == 0 && (C4_NST & (C4_NST - 1)) == 0 && C4_STAGE >= 64, "ring geometry");
 constexpr int C4_RING = C4_STAGE * C4_NST;   // events per array in the ring
 constexpr int C4_LIMIT4 = 4 * (COV_BINS - 1);
 
-struct __align__(16) C4Smem {
+// The histogram sits at a shared-window address that is a multiple of its own size (2 KB; the window of a CTA
+// starts with 1 KB the system reserves): base | offset == base + offset for every offset inside it, which the
+// position walk uses to test 16 bins with one OR chain.  (Checked when the kernel starts.)
+constexpr int C4_PAD = (2048 - (1024 + (int)sizeof(int32_t) * C3_WORDS + 8 * C4_NST) % 2048) % 2048;
+struct __align__(1024) C4Smem {
     int32_t T[C3_WORDS];         // 4 * difference array: window + overflow region, 4 pad words per 64 slots
+    unsigned long long bar[C4_NST];
+    uint8_t pad[C4_PAD];
     uint32_t hist[COV_BINS];
     uint32_t ring_s[C4_RING];
     uint32_t ring_e[C4_RING];
-    unsigned long long bar[C4_NST];
 };
+static_assert(sizeof(uint32_t) * COV_BINS == 2048 && (1024 + offsetof(C4Smem, hist)) % 2048 == 0, "histogram alignment");
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ int4 lds_v4(uint32_t saddr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -1594,8 +1636,9 @@ __device__ __noinline__ void c4_close_window(const TileArgs &a, int64_t c, bool 
     const int lane = threadIdx.x & 31;
     __syncwarp();
     int top = 0;
-    for (int j = COV_BINS / 32 - 1; j >= 0; j--)
-        if (s_hist[(COV_BINS / 32) * lane + j]) { top = (COV_BINS / 32) * lane + j; break; }
+#pragma unroll
+    for (int j = 0; j < COV_BINS / 32; j++)  // lane + 32 j: conflict-free
+        if (s_hist[lane + 32 * j]) top = lane + 32 * j;
     top = __reduce_max_sync(0xffffffffu, top);
     deep_max = __reduce_max_sync(0xffffffffu, deep_max);
     c3_close_window(a, c, local, deep_max > top ? deep_max : top, in_run, s_hist);
@@ -1608,7 +1651,11 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
     const int lane = threadIdx.x;
     const uint32_t sT0 = smem_base_opaque(sm.T);
     const uint32_t rS0 = smem_base_opaque(sm.ring_s), rE0 = smem_base_opaque(sm.ring_e);
-    const uint32_t bar0 = smem_base_opaque(sm.bar);
+    const uint32_t bar0 = smem_base_opaque(sm.bar), h0 = smem_base_opaque(sm.hist);
+    if (h0 & 2047u) {  // the shared window is not laid out as assumed: leave the sample to the general path
+        if (lane == 0) *a.gate_out = 1;
+        return;
+    }
     const int excl = (int)a.tp.excl;
     const uint32_t span = a.span_dev ? *a.span_dev : a.span_host;
     // events are consumed up to `delta` slots ahead of the window; delta >= disorder and delta + span <= C3_S
@@ -1641,31 +1688,51 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
         const int64_t e_base = a.e_lo[run];
         const int64_t n_ev64 = a.e_hi[run] - e_base;
         const int n_ev = n_ev64 > 0 ? (int)n_ev64 : 0;
-        // ---- staging geometry: stage s holds s_al[gs0 + 64 s ..) and e_al[ge0 + 64 s ..) ----
+        // ---- staging geometry: stage s holds s_al[gs0 + ST s ..) and e_al[ge0 + ST s ..) ----
+        constexpr int ST = C4_STAGE, RM = C4_RING - 1;
         const int64_t gs0 = (e_base + ms) & ~3ll, ge0 = (e_base + me) & ~3ll;
         const int r_s = (int)((e_base + ms) & 3), r_e = (int)((e_base + me) & 3);
         const int rmax = r_s > r_e ? r_s : r_e, rmin = r_s < r_e ? r_s : r_e;
-        const int n_st = n_ev > 0 ? ((rmax + n_ev - 1) >> 6) + 1 : 0;
+        const int n_st = n_ev > 0 ? (rmax + n_ev - 1) / ST + 1 : 0;
+        // stages below `full` are whole for both arrays (only the last stage of the whole sample can be short)
+        const int64_t fs = (lim_s - gs0) / ST, fe = (lim_e - ge0) / ST;
+        const int full = (int)((fs < fe ? fs : fe) < n_st ? (fs < fe ? fs : fe) : n_st);
         const uint32_t sq0 = sq;
         int issued = 0, waited = 0;
-        const int bs = r_s + C4_STAGE * (int)(sq0 & 3u) + lane, be = r_e + C4_STAGE * (int)(sq0 & 3u) + lane;
-        auto issue = [&](int s) {
+        int avail = -rmax;             // events [0, avail) of the run are in the ring (ST * waited - rmax)
+        int next_issue = -(1 << 30);   // the next stage may be issued once e_cur reaches this event
+        const uint32_t *src_s = s_al + gs0, *src_e = e_al + ge0;
+        const int bs = r_s + ST * (int)(sq0 & (C4_NST - 1)) + lane, be = r_e + ST * (int)(sq0 & (C4_NST - 1)) + lane;
+        auto issue = [&]() {  // stage `issued`; its slot was read for the last time before e_cur
             if (lane == 0) {
-                const uint32_t slot = (sq0 + (uint32_t)s) & 3u, bar = bar0 + 8u * slot;
-                int64_t cs = lim_s - (gs0 + (int64_t)C4_STAGE * s), ce = lim_e - (ge0 + (int64_t)C4_STAGE * s);
-                cs = cs > C4_STAGE ? C4_STAGE : (cs < 0 ? 0 : cs);
-                ce = ce > C4_STAGE ? C4_STAGE : (ce < 0 ? 0 : ce);
-                mbar_expect_tx(bar, (uint32_t)(4 * (cs + ce)));
-                if (cs > 0) bulk_g2s(rS0 + 4u * C4_STAGE * slot, s_al + gs0 + (int64_t)C4_STAGE * s, (uint32_t)(4 * cs), bar);
-                if (ce > 0) bulk_g2s(rE0 + 4u * C4_STAGE * slot, e_al + ge0 + (int64_t)C4_STAGE * s, (uint32_t)(4 * ce), bar);
+                const uint32_t slot = (sq0 + (uint32_t)issued) & (uint32_t)(C4_NST - 1), bar = bar0 + 8u * slot;
+                const uint32_t ds = rS0 + 4u * ST * slot, de = rE0 + 4u * ST * slot;
+                if (issued < full) {
+                    mbar_expect_tx(bar, 8u * ST);
+                    bulk_g2s(ds, src_s, 4u * ST, bar);
+                    bulk_g2s(de, src_e, 4u * ST, bar);
+                } else {
+                    int64_t cs = lim_s - (gs0 + (int64_t)ST * issued), ce = lim_e - (ge0 + (int64_t)ST * issued);
+                    cs = cs > ST ? ST : (cs < 0 ? 0 : cs);
+                    ce = ce > ST ? ST : (ce < 0 ? 0 : ce);
+                    mbar_expect_tx(bar, (uint32_t)(4 * (cs + ce)));
+                    if (cs > 0) bulk_g2s(ds, src_s, (uint32_t)(4 * cs), bar);
+                    if (ce > 0) bulk_g2s(de, src_e, (uint32_t)(4 * ce), bar);
+                }
             }
+            src_s += ST;
+            src_e += ST;
+            issued++;
+            next_issue = ST * (issued - C4_NST + 1) - rmin;
         };
-        auto wait_stage = [&](int s) {
-            const uint32_t q = sq0 + (uint32_t)s;
-            mbar_wait(bar0 + 8u * (q & 3u), (q >> 2) & 1u);
+        auto wait_next = [&]() {
+            const uint32_t q = sq0 + (uint32_t)waited;
+            mbar_wait(bar0 + 8u * (q & (uint32_t)(C4_NST - 1)), (q / (uint32_t)C4_NST) & 1u);
+            waited++;
+            avail += ST;
         };
         __syncwarp();  // the previous run's reads of the ring are done
-        while (issued < n_st && issued < C4_NST) { issue(issued); issued++; }
+        while (issued < n_st && issued < C4_NST) issue();
 
         int e_cur = 0;  // next event to consume, relative to e_base
         int4 cur = make_int4(0, 0, 0, 0);
@@ -1681,7 +1748,11 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
         int deep_max = 0;           // largest depth seen by the exact chunk path for c in this run (per lane)
         int carry4 = 0;             // 4 * depth just before the current window
         int pm = INT_MIN;           // running maximum of the starts consumed so far (run-relative)
-        bool viol = false;          // the vouched bounds do not hold
+        // the vouched bounds are checked on three running extremes (per lane) instead of per event:
+        int v_re = 0;               // largest window-relative end applied      (must stay < C3_W + C3_S)
+        int v_rs = 0;               // smallest window-relative start applied   (must stay >= 0 after the first window)
+        uint32_t v_blk = 0;         // longest block                             (must stay <= span)
+        bool viol = false;
 
         for (int k = 0; k < C3_TPR; k++) {
             const int t_lo = k * C3_W;
@@ -1690,20 +1761,57 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
             const int lim = t_hi + delta;
             int open = 0;
             while (e_cur < n_ev) {
-                {   // staging: refill the slots behind e_cur, wait for the stages this batch reads
-                    const int can = ((rmin + e_cur) >> 6) + C4_NST;
-                    if (issued < n_st && issued < can) {
-                        __syncwarp();
-                        do { issue(issued); issued++; } while (issued < n_st && issued < can);
-                    }
-                    const int e_end = e_cur + 32 < n_ev ? e_cur + 32 : n_ev;
-                    const int need = (rmax + e_end - 1) >> 6;
-                    while (waited <= need) { wait_stage(waited); waited++; }
+                // ---- staging: refill the slots behind e_cur, wait for the stages the next 64 events are in ----
+                if (e_cur >= next_issue && issued < n_st) {
+                    __syncwarp();
+                    do issue(); while (e_cur >= next_issue && issued < n_st);
                 }
+                {
+                    const int want = e_cur + 64 < n_ev ? e_cur + 64 : n_ev;
+                    while (want > avail) wait_next();
+                }
+                const int i0 = (bs + e_cur) & RM, j0 = (be + e_cur) & RM;
+                const int room = (n_ev < cur.y ? n_ev : cur.y) - e_cur;  // events ahead in this contig
+                if (k > 0 && room >= 64) {
+                    // ---- 64 events of one contig: both batches are taken whole if none is beyond the limit ----
+                    const uint32_t len = (uint32_t)cur.w;
+                    const uint32_t sv0 = lds_u32(rS0 + 4u * i0), sv1 = lds_u32(rS0 + 4u * ((i0 + 32) & RM));
+                    const uint32_t ev0 = lds_u32(rE0 + 4u * j0), ev1 = lds_u32(rE0 + 4u * ((j0 + 32) & RM));
+                    const uint32_t en0 = ev0 < len ? ev0 : len, en1 = ev1 < len ? ev1 : len;
+                    const bool ok0 = sv0 < en0, ok1 = sv1 < en1;  // start inside the contig, block not empty
+                    const int g0 = cur.z + (int)sv0, g1 = cur.z + (int)sv1;
+                    const int key0 = ok0 ? g0 : INT_MIN, key1 = ok1 ? g1 : INT_MIN;
+                    int bm = __reduce_max_sync(0xffffffffu, key0 > key1 ? key0 : key1);
+                    bm = bm > pm ? bm : pm;
+                    if (bm < lim) {
+                        // a dropped event becomes (+4, -4) on slot 0 of the window: no predicate for it
+                        const int rs0 = ok0 ? g0 - t_lo : 0, rs1 = ok1 ? g1 - t_lo : 0;
+                        const uint32_t b0 = ok0 ? en0 - sv0 : 0u, b1 = ok1 ? en1 - sv1 : 0u;
+                        const int re0 = rs0 + (int)b0, re1 = rs1 + (int)b1;
+                        const bool in0 = rs0 >= 0 && re0 < C3_W + C3_S, in1 = rs1 >= 0 && re1 < C3_W + C3_S;
+                        if (in0) {
+                            smem_add(sT0 + 4u * (uint32_t)c3_phys(rs0), 4);
+                            smem_add(sT0 + 4u * (uint32_t)c3_phys(re0), -4);
+                        }
+                        if (in1) {
+                            smem_add(sT0 + 4u * (uint32_t)c3_phys(rs1), 4);
+                            smem_add(sT0 + 4u * (uint32_t)c3_phys(re1), -4);
+                        }
+                        const int mre = re0 > re1 ? re0 : re1, mrs = rs0 < rs1 ? rs0 : rs1;
+                        const uint32_t mb = b0 > b1 ? b0 : b1;
+                        v_re = mre > v_re ? mre : v_re;
+                        v_rs = mrs < v_rs ? mrs : v_rs;
+                        v_blk = mb > v_blk ? mb : v_blk;
+                        e_cur += 64;
+                        pm = bm;
+                        continue;
+                    }
+                }
+                // ---- one batch, any shape: contig boundary inside, end of the range, the window's last batch ----
                 const int e = e_cur + lane;
                 const bool live = e < n_ev;
-                const uint32_t sv = sm.ring_s[(bs + e_cur) & (C4_RING - 1)];
-                const uint32_t ev = sm.ring_e[(be + e_cur) & (C4_RING - 1)];
+                const uint32_t sv = lds_u32(rS0 + 4u * i0);
+                const uint32_t ev = lds_u32(rE0 + 4u * j0);
                 int crel = cur.z;
                 uint32_t len = (uint32_t)cur.w;
                 if (live && e >= cur.y) {  // this lane's event belongs to a later contig (rare)
@@ -1712,13 +1820,13 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
                     len = (uint32_t)mine.w;
                 }
                 const uint32_t en = ev < len ? ev : len;
-                const bool ok = live && sv < len && en > sv;
+                const bool ok = live && sv < en;
                 const int gs = (int)((uint32_t)crel + sv);  // run-relative start
                 const int key = ok ? gs : INT_MIN;
                 int bm = __reduce_max_sync(0xffffffffu, key);
                 bm = bm > pm ? bm : pm;
                 int cnt = 32, pm_new = bm;
-                if (bm >= lim || e_cur + 32 > n_ev) {  // the batch crosses the limit: exact prefix maximum
+                if (bm >= lim || room < 32) {  // the batch crosses the limit: exact prefix maximum
                     int p = key;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -1757,14 +1865,12 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
 
             // ---- this lane's 64 slots: total, exclusive warp scan ----
             const int myb = (C3_SPL + 4) * lane;
+            const uint32_t my_sa = sT0 + 4u * (uint32_t)myb;  // this lane's 64 slots
             int tot = 0;
-            {
-                const int4 *p = reinterpret_cast<const int4 *>(sm.T + myb);
 #pragma unroll
-                for (int j = 0; j < C3_SPL / 4; j++) {
-                    const int4 v = p[j];
-                    tot += v.x + v.y + v.z + v.w;
-                }
+            for (int j = 0; j < C3_SPL / 4; j++) {
+                const int4 v = lds_v4(my_sa + 16u * j);
+                tot += v.x + v.y + v.z + v.w;
             }
             int incl = tot;
 #pragma unroll
@@ -1795,32 +1901,31 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
                 const int lo = wlo > t_lo ? wlo : t_lo, hi = whi + 1 < t_hi ? whi + 1 : t_hi;
                 if (hi > lo) {
                     if (lo < q0 + C3_SPL && hi > q0) {  // this lane's slots intersect the window
-                        int d4 = dstart4;
+                        uint32_t x = h0 + (uint32_t)dstart4;  // address of the current depth's bin
 #pragma unroll 1
                         for (int ch = 0; ch < C3_SPL / 16; ch++) {
                             const int q = q0 + 16 * ch;
-                            const int d4_before = d4;
-                            int d[16];
-                            const int4 *p = reinterpret_cast<const int4 *>(sm.T + myb + 16 * ch);
+                            const uint32_t x_before = x;
+                            uint32_t d[16];
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                const int4 v = p[j];
-                                d4 += v.x; d[4 * j] = d4;
-                                d4 += v.y; d[4 * j + 1] = d4;
-                                d4 += v.z; d[4 * j + 2] = d4;
-                                d4 += v.w; d[4 * j + 3] = d4;
+                                const int4 v = lds_v4(my_sa + 64u * ch + 16u * j);
+                                x += (uint32_t)v.x; d[4 * j] = x;
+                                x += (uint32_t)v.y; d[4 * j + 1] = x;
+                                x += (uint32_t)v.z; d[4 * j + 2] = x;
+                                x += (uint32_t)v.w; d[4 * j + 3] = x;
                             }
-                            int orr = 0;
+                            uint32_t orr = 0;
 #pragma unroll
                             for (int i = 0; i < 16; i++) orr |= d[i];
                             const int l2 = lo > q ? lo : q, h2 = hi < q + 16 ? hi : q + 16;
-                            if (h2 - l2 == 16 && (unsigned)orr < (unsigned)C4_LIMIT4) {
+                            // depths are never negative, so every bin below the last one <=> (OR ^ base) below it
+                            if (h2 - l2 == 16 && (orr ^ h0) < (uint32_t)C4_LIMIT4) {
 #pragma unroll
-                                for (int i = 0; i < 16; i++)
-                                    atomicAdd(reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(sm.hist) + d[i]), 1u);
+                                for (int i = 0; i < 16; i++) smem_inc(d[i]);
                             } else if (h2 > l2) {
                                 const uint32_t m = ((1u << (h2 - q)) - 1u) & ~((1u << (l2 - q)) - 1u);
-                                const int mx = c4_slow_chunk(a, c, sm.T + myb + 16 * ch, d4_before, m, sm.hist);
+                                const int mx = c4_slow_chunk(a, c, sm.T + myb + 16 * ch, (int)(x_before - h0), m, sm.hist);
                                 deep_max = mx > deep_max ? mx : deep_max;
                             }
                         }
@@ -1855,8 +1960,9 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
         }
         // ---- run end ----
         if (have && whi >= wlo && in_run > 0) c4_close_window(a, c, false, deep_max, in_run, sm.hist);
+        viol |= v_re >= C3_W + C3_S || v_rs < 0 || v_blk > span;
         if (__any_sync(0xffffffffu, viol) && lane == 0) *a.gate_out = 1;  // unreliable ranges: the general path redoes the sample
-        while (waited < issued) { wait_stage(waited); waited++; }  // no copy may be in flight when the ring is reused
+        while (waited < issued) wait_next();  // no copy may be in flight when the ring is reused
         sq = sq0 + (uint32_t)issued;
     }
 }
@@ -1962,7 +2068,7 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
                         (!measure && ((uint64_t)max_span + max_disorder > (uint64_t)C3_S || (need_sorted && max_disorder)));
     // ---------------- fast path: difference array in shared memory ----------------
     if (!general_only) {
-        Temp e_lo, e_hi, c_lo, c_hi, c_ev, t_rows, t_meta, t_deep, t_drow, t_dpool, k_max, k_pre;
+        Temp e_lo, e_hi, c_lo, c_hi, c_ev, t_rows, t_meta, t_deep, t_drow, t_dpool, k_max;
         const int64_t unit = fast_ver == 1 ? CT_TILE : C3_RUN;
         const int64_t n_units = (n_pos + unit - 1) / unit;
         if (n_units > INT32_MAX / 2) return fail(MP2_EINVAL, "too many positions in one call");
@@ -1980,23 +2086,17 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
         MP2_CUDA(cudaMemsetAsync(t_meta.p, 0, sizeof(RowMeta) * n_units, stream));
         MP2_CUDA(cudaMemsetAsync(t_drow.p, 0xFF, sizeof(int32_t) * n_contigs, stream));
         MP2_CUDA(cudaMemsetAsync(t_dpool.p, 0, sizeof(uint32_t) * (size_t)CT_DEEP_ROWS * CT_DEEP_BINS, stream));
-        if (n_events > 0 && measure) {  // longest block and disorder of the starts, exactly
-            MP2_TRY(k_max.alloc(sizeof(long long) * n_ev_tiles, stream));
-            MP2_TRY(k_pre.alloc(sizeof(long long) * n_ev_tiles, stream));
+        if (n_events > 0 && measure) {  // longest block and disorder of the starts, exactly (one pass over the events)
+            MP2_TRY(k_max.alloc(sizeof(OrderTile) * n_ev_tiles, stream));
             {
-                Launch L("cov_keymax_kernel", stream);
-                cov_keymax_kernel<<<(unsigned)n_ev_tiles, 256, 0, stream>>>(starts, ends, ev_off, off, n_contigs, n_events,
-                                                                         ev_first.as<int32_t>(), k_max.as<long long>());
-            }
-            {
-                Launch L("cov_keyscan_kernel", stream);
-                cov_keyscan_kernel<<<1, 1024, 0, stream>>>(k_max.as<long long>(), n_ev_tiles, k_pre.as<long long>());
-            }
-            {
-                Launch L("cov_check_kernel", stream);
-                cov_check_kernel<<<(unsigned)n_ev_tiles, 256, 0, stream>>>(starts, ends, ev_off, off, n_contigs, n_events,
-                                                                        ev_first.as<int32_t>(), k_pre.as<long long>(),
+                Launch L("cov_order_kernel", stream);
+                cov_order_kernel<<<(unsigned)n_ev_tiles, 256, 0, stream>>>(starts, ends, ev_off, off, n_contigs, n_events,
+                                                                        ev_first.as<int32_t>(), k_max.as<OrderTile>(),
                                                                         flags.as<unsigned int>());
+            }
+            {
+                Launch L("cov_order_scan_kernel", stream);
+                cov_order_scan_kernel<<<1, 1024, 0, stream>>>(k_max.as<OrderTile>(), n_ev_tiles, flags.as<unsigned int>());
             }
         }
         MP2_CUDA(cudaGetLastError());

@@ -37,21 +37,32 @@ static size_t slice_bytes() {
 constexpr size_t RING_SLICE = 16u << 20;
 constexpr int NRING = 4;
 
+// One ring per device: the slots are plain (portable) pinned memory, but the events that guard them belong to
+// the device they were created on, and threads driving different GPUs must not wait for each other.
 struct Ring {
     uint8_t *buf[NRING] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t freed[NRING];
     bool ready = false;
     std::mutex mu;
 };
-static Ring g_ring;
+constexpr int MAX_DEV = 64;
+static Ring g_rings[MAX_DEV];
 
-static int ring_init() {
-    if (g_ring.ready) return MP2_OK;
+static int ring_of_current_device(Ring **out) {
+    int dev = 0;
+    MP2_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEV) return fail(MP2_EINVAL, "device index %d out of range", dev);
+    *out = &g_rings[dev];
+    return MP2_OK;
+}
+
+static int ring_init(Ring &r) {  // called with r.mu held
+    if (r.ready) return MP2_OK;
     for (int i = 0; i < NRING; i++) {
-        MP2_CUDA(cudaHostAlloc((void **)&g_ring.buf[i], RING_SLICE, cudaHostAllocPortable));
-        MP2_CUDA(cudaEventCreateWithFlags(&g_ring.freed[i], cudaEventDisableTiming));
+        MP2_CUDA(cudaHostAlloc((void **)&r.buf[i], RING_SLICE, cudaHostAllocPortable));
+        MP2_CUDA(cudaEventCreateWithFlags(&r.freed[i], cudaEventDisableTiming));
     }
-    g_ring.ready = true;
+    r.ready = true;
     return MP2_OK;
 }
 
@@ -93,8 +104,11 @@ static int upload(void *d_dst, const void *h_src, size_t bytes, cudaStream_t cop
         }
         return MP2_OK;
     }
+    Ring *ring = nullptr;
+    MP2_TRY(ring_of_current_device(&ring));
+    Ring &g_ring = *ring;
     std::lock_guard<std::mutex> lk(g_ring.mu);
-    MP2_TRY(ring_init());
+    MP2_TRY(ring_init(g_ring));
     int slot = 0;
     for (size_t o = 0; o < bytes; o += RING_SLICE, slot = (slot + 1) % NRING) {
         size_t len = std::min(RING_SLICE, bytes - o);

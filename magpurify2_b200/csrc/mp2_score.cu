@@ -7,6 +7,8 @@
 // All MAGs of a batch are stacked row-wise; MAG m owns rows mag_off[m] .. mag_off[m+1].
 #include <cfloat>
 
+#include <mutex>
+
 #include "mp2_common.h"
 
 namespace mp2 {
@@ -227,16 +229,25 @@ __global__ void log_lut_kernel() {
     if (i < LOG_LUT) g_log_lut[i] = i ? log((double)i) : 0.0;
 }
 
-static int ensure_log_lut(cudaStream_t stream) {
+// Per-device, once: the table of ln(i) and the shared-memory attribute of wmedian_kernel.  Callers may be
+// threads driving different GPUs (or different streams of one GPU), so this is serialised and the table is
+// complete (stream synchronised) before anyone is told it exists.
+static int ensure_device_state(cudaStream_t stream) {
+    static std::mutex mu;
     static bool done[64] = {false};
     int dev = 0;
     MP2_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && done[dev]) return MP2_OK;
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return MP2_OK;
     log_lut_kernel<<<LOG_LUT / 256, 256, 0, stream>>>();
     MP2_CUDA(cudaGetLastError());
-    if (dev < 64) done[dev] = true;
+    MP2_CUDA(cudaStreamSynchronize(stream));
+    MP2_CUDA(cudaFuncSetAttribute(wmedian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(VW) * WM_SMEM_CAP)));
+    if (dev >= 0 && dev < 64) done[dev] = true;
     return MP2_OK;
 }
+static int ensure_log_lut(cudaStream_t stream) { return ensure_device_state(stream); }
 
 // ---- CLR + centroid distance (self-specified: the reference has no such code) -----------------
 // clr_ij = ln(c_ij + 1) - rm_i, rm_i = mean_j ln(c_ij + 1); centroid_j = sum_i len_i clr_ij / sum_i len_i;
@@ -358,12 +369,7 @@ extern "C" int mp2_logratio_device(const void *d_data, const void *d_weights, co
     }
     // scratch for MAGs with more rows than fit in shared memory: 2x (power-of-two padding) pairs
     MP2_TRY(scratch.alloc(sizeof(VW) * 2 * (size_t)n_rows * n_cols, stream));
-    static bool attr_done = false;
-    if (!attr_done) {
-        MP2_CUDA(cudaFuncSetAttribute(wmedian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(VW) * WM_SMEM_CAP)));
-        attr_done = true;
-    }
+    MP2_TRY(ensure_device_state(stream));
     {
         Launch L("wmedian_kernel", stream);
         wmedian_kernel<<<(unsigned)(n_mags * n_cols), WM_THREADS, sizeof(VW) * WM_SMEM_CAP, stream>>>(

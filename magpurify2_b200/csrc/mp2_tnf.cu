@@ -15,6 +15,7 @@
 // wavefronts: one increment per TWO bases (5-mer table), a flush whose table reads are all
 // conflict-free LDS.128, and an interior row path without divergence (edge rows are out of line).
 #include <cstdlib>
+#include <mutex>
 
 #include "mp2_common.h"
 
@@ -50,10 +51,12 @@ __constant__ uint8_t c_lut256[256];             // code -> canonical class
 __constant__ uint16_t c_canon_pair[MP2_NCANON];  // class -> smallest code | revcomp code << 8
 
 static int upload_tables() {
+    static std::mutex mu;  // callers may be threads driving different GPUs
     static bool done[64] = {false};
     int dev = 0;
     MP2_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && done[dev]) return MP2_OK;
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return MP2_OK;
     MP2_CUDA(cudaMemcpyToSymbol(c_lut256, host_lut256(), 256));
     uint16_t pair[MP2_NCANON];
     const uint8_t *cc = host_canon_code136();
@@ -713,6 +716,7 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
     if (mode == 5 && ps == 16) MP2_TNF_LAUNCH(5, 16);
     else if (mode == 5 && ps == 15) MP2_TNF_LAUNCH(5, 15);
     else if (mode == 5) MP2_TNF_LAUNCH(5, 14);
+    else if (ps == 16) MP2_TNF_LAUNCH(4, 16);
     else if (ps == 15) MP2_TNF_LAUNCH(4, 15);
     else MP2_TNF_LAUNCH(4, 14);
 #undef MP2_TNF_LAUNCH
@@ -850,6 +854,7 @@ extern "C" int mp2_tnf_packed_device(const void *d_codes, const void *d_valid, c
         if (mode == 5 && ps == 16) MP2_TNFP_LAUNCH(5, 16);
         else if (mode == 5 && ps == 15) MP2_TNFP_LAUNCH(5, 15);
         else if (mode == 5) MP2_TNFP_LAUNCH(5, 14);
+        else if (ps == 16) MP2_TNFP_LAUNCH(4, 16);
         else if (ps == 15) MP2_TNFP_LAUNCH(4, 15);
         else MP2_TNFP_LAUNCH(4, 14);
 #undef MP2_TNFP_LAUNCH

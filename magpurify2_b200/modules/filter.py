@@ -62,6 +62,29 @@ def load_features(scores_directory, module_list, logger):
     return genome_contig_matrix, feature_matrix
 
 
+def warn_uncalibrated(scores_directory, logger):
+    """The reference's trees were fitted on the reference's features.  Two columns of this build's tables are
+    not those features (tnf_score is a CLR / centroid-distance score, coverage_cluster_score is the constant
+    1.0), so the probabilities -- and with them the contigs that get removed -- are NOT calibrated when the
+    tables come from this build.  Say so, loudly, whenever the provenance note shows that."""
+    import json
+
+    note = scores_directory.joinpath("provenance.json")
+    try:
+        known = json.loads(note.read_text()) if note.exists() else {}
+    except ValueError:
+        known = {}
+    ours = sorted(m for m, v in known.items() if isinstance(v, dict) and v.get("producer") == "magpurify2_b200")
+    if ours:
+        logger.warning(
+            f"The {' and '.join(ours)} score table(s) were written by the B200 build: `tnf_score` is a CLR / "
+            "centroid-distance score and `coverage_cluster_score` is the constant 1.0, not the UMAP + HDBSCAN "
+            "scores the gradient-boosted model was trained on.  The contamination probabilities below are "
+            "therefore NOT calibrated and are not comparable with the reference's; treat the filtered genomes as "
+            "a screening result.")
+    return ours
+
+
 def main(args):
     logger = logging.getLogger("timestamp")
     args.probability_threshold = tools.validade_input(args.probability_threshold, "probability_threshold", [0.0, 1.0])
@@ -90,6 +113,7 @@ def main(args):
     logger.info(f"Reading contig scores from the {', '.join(module_list)} modules.")
     genome_contig_matrix, feature_matrix = load_features(scores_directory, module_list, logger)
 
+    warn_uncalibrated(scores_directory, logger)
     logger.info("Estimating contamination probabilities and identifying contaminant contigs.")
     classification = ContigClassifier(genome_contig_matrix, feature_matrix, model_file, args.fast_mode,
                                       args.probability_threshold, args.checkm_file, getattr(args, "threads", 1))

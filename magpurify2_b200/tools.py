@@ -45,15 +45,14 @@ class Compression(Enum):  # tools.py:45-49
 
 
 def validade_input(value, parameter_name, interval):
-    """Clamp a numeric option into `interval` with a warning (tools.py:54-82)."""
-    interval = sorted(interval)
-    if value > interval[1] or value < interval[0]:
-        value = min(max(value, interval[0]), interval[1])
-        logger.warning(
-            f"The value of the `{parameter_name}` parameter must be between {interval[0]} and "
-            f"{interval[1]}. Setting it to {value}."
-        )
-    return value
+    """A numeric option forced into [min(interval), max(interval)]; the user is told when that changes it
+    (behaviour of tools.py:54-82)."""
+    lo, hi = min(interval), max(interval)
+    clamped = lo if value < lo else hi if value > hi else value
+    if clamped != value:
+        logger.warning(f"The value of the `{parameter_name}` parameter must be between {lo} and {hi}. "
+                       f"Setting it to {clamped}.")
+    return clamped
 
 
 def check_output_directory(output_directory):  # tools.py:85-97
@@ -133,32 +132,41 @@ def read_fasta(filepath):
 
 
 def get_tsv_coverages(filepath, contig_set=None):
-    """Tabular coverages: first column names, remaining columns per-sample coverage (tools.py:243-280)."""
+    """Coverage table in a text file: contig name, then one coverage per sample, tab-separated, no header
+    (behaviour of tools.py:243-280).  Returns (names str[n], float64[n, n_samples]); with `contig_set` only the
+    rows of those contigs.  Every line is a data line ('#' is not a comment)."""
+    names, rows, width = [], [], None
     with open(filepath) as fin:
-        ncols = len(fin.readline().split("\t"))
-    if ncols < 2:
-        logger.error("The tabular coverage file must have at least two columns.")
-        sys.exit(1)
-    contig_names_vector = np.genfromtxt(filepath, dtype=str, comments=None, delimiter="\t", usecols=0)
-    coverage_vector = np.genfromtxt(filepath, dtype=float, comments=None, delimiter="\t", usecols=range(1, ncols))
-    contig_names_vector = np.atleast_1d(contig_names_vector)
-    if coverage_vector.ndim <= 1:
-        coverage_vector = coverage_vector.reshape(len(contig_names_vector), -1)
-    if contig_set:
-        mask = np.array([contig in contig_set for contig in contig_names_vector])
-        contig_names_vector = contig_names_vector[mask]
-        coverage_vector = coverage_vector[mask, :]
-    return (contig_names_vector, coverage_vector)
+        for line in fin:
+            cells = line.rstrip("\n").split("\t")
+            if width is None:
+                width = len(cells)
+                if width < 2:
+                    logger.error("The tabular coverage file must have at least two columns.")
+                    sys.exit(1)
+            if not line.strip():
+                continue
+            if contig_set and cells[0] not in contig_set:
+                continue
+            names.append(cells[0])
+            # short or non-numeric cells read as NaN, as numpy.genfromtxt reports them
+            vals = [np.nan] * (width - 1)
+            for k, cell in enumerate(cells[1:width]):
+                try:
+                    vals[k] = float(cell)
+                except ValueError:
+                    pass
+            rows.append(vals)
+    matrix = np.array(rows, dtype=float).reshape(len(names), (width or 2) - 1)
+    return np.array(names, dtype=str), matrix
 
 
-def write_module_output(score_list, score_output_file):  # tools.py:607-626
+def write_module_output(score_list, score_output_file):
+    """One TSV for a module: the attribute names of the first score object as header, then the rows every
+    score object yields (format of tools.py:607-626)."""
     with open(score_output_file, "w") as fout:
-        header = "\t".join(score_list[0].attributes)
-        fout.write(f"{header}\n")
-        for mag_score in score_list:
-            for attributes in mag_score:
-                line = "\t".join(map(str, attributes))
-                fout.write(f"{line}\n")
+        fout.write("\t".join(score_list[0].attributes) + "\n")
+        fout.writelines("\t".join(str(cell) for cell in row) + "\n" for scores in score_list for row in scores)
 
 
 def get_checkm_contamination(filepath):

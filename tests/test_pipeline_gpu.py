@@ -209,3 +209,113 @@ def test_cli_composition_and_coverage(tmp_path, oracle):
     for b in bams[1:]:
         b.write_bytes(b.read_bytes())  # same content, same signature
     assert cli.cli(["coverage", *map(str, genomes), str(out), "--bam_files", *map(str, bams), "-q"]) == 0
+
+
+def test_dropin_modules_on_gpu(tmp_path, oracle, monkeypatch):
+    """The alias modules magpurify2_b200.dropin writes (`magpurify2._composition`, `magpurify2._coverage`: the
+    module paths magpurify2/tools.py:40-41 imports) resolve and compute on the GPU."""
+    import importlib
+    import sys
+
+    from magpurify2_b200 import dropin, synth
+
+    pkg = tmp_path / "site" / "magpurify2"
+    pkg.mkdir(parents=True)
+    (pkg / "__init__.py").write_text("")
+    assert "_composition.py" in dropin.install(pkg)
+    for name in [m for m in sys.modules if m == "magpurify2" or m.startswith("magpurify2.")]:
+        monkeypatch.delitem(sys.modules, name)
+    monkeypatch.syspath_prepend(str(tmp_path / "site"))
+    importlib.invalidate_caches()
+    comp = importlib.import_module("magpurify2._composition")
+    cov = importlib.import_module("magpurify2._coverage")
+    d = synth.make_mags(1, seed=3, mean_bp=5e4, n_contigs=12)
+    seqs = [d["bases"][d["offsets"][i]:d["offsets"][i + 1]].tobytes().decode() for i in range(len(d["lengths"]))]
+    assert np.array_equal(comp.get_tnf(seqs, False, 2), oracle.get_tnf_concat(d["bases"], d["offsets"], relative=False))
+    assert np.array_equal(comp.get_tnf(seqs), oracle.get_tnf_concat(d["bases"], d["offsets"], relative=True))
+    assert np.array_equal(comp.get_gc(seqs), oracle.get_gc_concat(d["bases"], d["offsets"]), equal_nan=True)
+    assert cov.get_bam_coverages.__module__ == "magpurify2_b200._coverage"
+    with pytest.raises(NotImplementedError):
+        importlib.import_module("magpurify2._codon").get_cai()
+
+
+def test_shards_on_one_gpu_equal_unsharded(tmp_path, oracle):
+    """the MAGs LPT-split into 3 shards, every shard through the kernels (three host
+    threads on the same GPU), rows gathered back -- bit-identical to the unsharded run; the same for BAM files
+    dealt out to "devices"."""
+    from magpurify2_b200 import multi, tools
+    from magpurify2_b200.core import read_mags
+
+    d, names, genomes, bams, events = _write_dataset(tmp_path, n_mags=7, n_samples=3, seed=31)
+    mags = read_mags(genomes, threads=2)
+    one = multi.composition_of(mags, 0)
+    parts = multi.shard_mags(mags, 3)
+    assert sorted(np.concatenate(parts).tolist()) == list(range(7)) and all(len(p) for p in parts)
+    three = multi.composition_on_devices(mags, [0, 0, 0])
+    for k in ("counts", "rel", "gc", "tnf_score", "gc_score"):
+        assert np.array_equal(one[k], three[k], equal_nan=True), k
+    assert np.array_equal(one["counts"], oracle.get_tnf_concat(d["bases"], d["offsets"], relative=False, threads=4))
+    n1, m1 = tools.get_bam_coverages([str(b) for b in bams], trim_lower=0.05, trim_upper=0.05, threads=4)
+    n2, m2 = multi.bam_coverages_on_devices([str(b) for b in bams], [0, 0], trim_lower=0.05, trim_upper=0.05, threads=4)
+    assert n1 == n2 and np.array_equal(m1.view(np.uint32), m2.view(np.uint32))
+
+
+def test_cli_devices_cache_and_coverage_file(tmp_path, oracle):
+    """--devices; tnfs.pickle.gz is reused when it holds every genome of the run (extra genomes survive) and
+    replaced otherwise (modules/composition.py:48-60); --coverage_file (modules/coverage.py:101-106)."""
+    from magpurify2_b200 import cli
+
+    d, names, genomes, bams, events = _write_dataset(tmp_path, n_mags=4, n_samples=2, seed=17)
+    out = tmp_path / "out"
+    assert cli.cli(["composition", *map(str, genomes), str(out), "-q", "--devices", "0"]) == 0
+    first = (out / "scores" / "composition_scores.tsv").read_text()
+    with gzip.open(out / "tnfs.pickle.gz") as f:
+        assert sorted(pickle.load(f)) == ["mag0", "mag1", "mag2", "mag3"]
+    # a run on a subset finds everything it needs in the cache: the file (all four genomes) stays
+    assert cli.cli(["composition", *map(str, genomes[:2]), str(out), "-q"]) == 0
+    with gzip.open(out / "tnfs.pickle.gz") as f:
+        assert sorted(pickle.load(f)) == ["mag0", "mag1", "mag2", "mag3"]
+    # a cache that lacks a genome is thrown away and rewritten for this run's genomes
+    with gzip.open(out / "tnfs.pickle.gz", "wb") as f:
+        pickle.dump({"mag0": np.zeros((1, 136), np.float32)}, f)
+    assert cli.cli(["composition", *map(str, genomes), str(out), "-q"]) == 0
+    with gzip.open(out / "tnfs.pickle.gz") as f:
+        tn = pickle.load(f)
+    assert sorted(tn) == ["mag0", "mag1", "mag2", "mag3"] and tn["mag0"].shape[0] == d["mag_off"][1]
+    assert (out / "scores" / "composition_scores.tsv").read_text() == first
+    assert "magpurify2_b200" in (out / "scores" / "provenance.json").read_text()
+    with pytest.raises(ValueError):
+        cli.cli(["composition", *map(str, genomes), str(out), "-q", "--devices", "0,99"])
+    # ---- --coverage_file: float64 table, one line per contig, shuffled, with a contig no MAG has ----
+    rng = np.random.default_rng(17)
+    cov = np.round(rng.gamma(2.0, 8.0, (len(names), 4)), 3)
+    cov[:, 3] *= 0.01  # a sample below min_average_coverage
+    table = tmp_path / "cov.tsv"
+    order = rng.permutation(len(names))
+    lines = [names[i] + "\t" + "\t".join(repr(float(v)) for v in cov[i]) for i in order] + ["stray_contig\t1\t2\t3\t4"]
+    table.write_text("\n".join(lines) + "\n" + "x" * 130000 + "\t0\t0\t0\t0\n")  # >= 128000 bytes (tools.py:150-166)
+    out2 = tmp_path / "out2"
+    assert cli.cli(["coverage", *map(str, genomes), str(out2), "--coverage_file", str(table), "-q"]) == 0
+    rows = [l.rstrip("\n").split("\t") for l in open(out2 / "scores" / "coverage_scores.tsv")]
+    assert [r[1] for r in rows[1:]] == names
+    for m in range(4):
+        sl = slice(d["mag_off"][m], d["mag_off"][m + 1])
+        c32 = cov[sl].astype(np.float32)
+        sel, _ = oracle.select_samples(c32, d["lengths"][sl], 1.0)
+        assert sel.tolist() == [True, True, True, False]
+        want, _ = oracle.log_ratio_scores(c32[:, sel], d["lengths"][sl], 25)
+        got = np.array([float(r[2]) for r in rows[1:][sl]])
+        assert np.allclose(got, np.round(want, 5), atol=1.1e-5)
+        assert {int(r[4]) for r in rows[1:][sl]} == {3}
+
+
+def test_composition_object_accepts_the_relative_profile(tmp_path, oracle):
+    """Reference-shaped call: Composition(mag, {genome: get_tnf(mag.sequences)}, get_gc(mag.sequences), ...)."""
+    from magpurify2_b200 import tools
+    from magpurify2_b200.core import Composition, Mag
+
+    d, names, genomes, _b, _e = _write_dataset(tmp_path, n_mags=1, n_samples=0, seed=5)
+    mag = Mag(genomes[0])
+    a = Composition(mag, {mag.genome: tools.get_tnf(mag.sequences)}, tools.get_gc(mag.sequences), 4, 3, 0.1, 15, 1.0)
+    b = Composition(mag, {mag.genome: tools.get_tnf(mag.sequences, relative=False)}, tools.get_gc(mag.sequences))
+    assert np.array_equal(a.tnf_scores, b.tnf_scores) and np.array_equal(a.gc_content_scores, b.gc_content_scores)
