@@ -87,6 +87,20 @@ int mp2_tnf_packed_device(const void *d_codes, const void *d_valid, const void *
 int mp2_pack_device(const void *d_bases, int64_t n_bases, void *d_codes, void *d_valid,
                     void *stream);
 
+/* The same layout produced on the HOST (multi-threaded; AVX-512BW when the CPU has it), from the virtual
+ * concatenation of `n_parts` byte buffers -- the genomes of a run as the FASTA reader left them (replaces the
+ * per-contig Python str hand-over of magpurify2/core.py:35-50, modules/composition.py:63-66).  codes and valid
+ * must hold mp2_packed_words() words (whole quads of 64 bases: 4 code words + 2 validity words each); pinned
+ * memory makes the upload a plain DMA.  Returns MP2_OK / MP2_EINVAL (no message: this function has no CUDA in it). */
+int64_t mp2_packed_words(int64_t n_bases, int64_t *valid_words); /* returns the number of code words */
+int mp2_pack_host(const uint8_t *const *parts, const int64_t *part_len, int64_t n_parts, uint32_t *codes,
+                  uint32_t *valid, int threads);
+
+/* mp2_tnf on the packed host arrays: 0.375 bytes per base cross PCIe instead of 1 (offsets in bases, as above;
+ * n_bases = offsets[n]).  Same outputs as mp2_tnf, any of them may be NULL. */
+int mp2_tnf_packed(const uint32_t *codes, const uint32_t *valid, const int64_t *offsets, int64_t n,
+                   int device, uint32_t *counts, float *rel, float *gc);
+
 /* ---- coverage: replaces the coverm arithmetic behind _coverage.get_bam_coverages ------- */
 /* (src/coverage.rs:99-142; coverm 0.3.2 contig_coverage / add_contig / calculate_coverage,
  *  SURVEY.md Appendix A).  One call = ONE sample (one BAM).                                */
@@ -135,6 +149,14 @@ int mp2_cov_events_device(const void *d_starts, const void *d_ends, const void *
                           int64_t n_positions, uint32_t max_span, uint32_t max_disorder,
                           uint32_t end_excl, float trim_lower, float trim_upper, void *d_cov,
                           int64_t cov_stride, void *d_stats, void *stream);
+
+/* Measures, exactly, the two numbers the call above can be vouched for with (longest block; largest distance
+ * of a start below the largest start before it in its contig) for events resident on the device.  One pass over
+ * the events; synchronous (the results are host integers).  mp2_bam_open reports the same numbers for the BAMs it
+ * decodes, so get_bam_coverages never needs this. */
+int mp2_cov_order_device(const void *d_starts, const void *d_ends, const void *d_ev_off,
+                         const void *d_contig_off, int64_t n_contigs, int64_t n_events,
+                         uint32_t *max_span, uint32_t *max_disorder, void *stream);
 
 /* Host-buffer form of the same call (stages H2D/D2H itself). */
 int mp2_cov_events(const uint32_t *starts, const uint32_t *ends, const int64_t *ev_off,

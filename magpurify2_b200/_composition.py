@@ -90,6 +90,50 @@ def _run(bases, offsets, counts, rel, gc, device=-1):
                                    _lib.ptr(counts), _lib.ptr(rel), _lib.ptr(gc)))
 
 
+def pack_parts(parts, threads=None):
+    """2-bit packs the virtual concatenation of `parts` (uint8 arrays: the genomes of a run as the FASTA reader
+    left them) on the host: (codes uint32[4q], valid uint32[2q]) for q quads of 64 bases, in page-locked
+    memory when there is a GPU to copy them to.  0.375 bytes per base instead of 1."""
+    import os
+
+    parts = [np.ascontiguousarray(p, dtype=np.uint8) for p in parts]
+    lens = np.array([len(p) for p in parts], dtype=np.int64)
+    total = int(lens.sum())
+    quads = (total + 63) // 64
+    codes = _out((4 * quads,), np.uint32) if quads else np.zeros(0, np.uint32)
+    valid = _out((2 * quads,), np.uint32) if quads else np.zeros(0, np.uint32)
+    ptrs = (_lib.C.c_void_p * max(1, len(parts)))(*[p.ctypes.data for p in parts])
+    rc = _lib.load().mp2_pack_host(ptrs, _lib.ptr(lens), len(parts), _lib.ptr(codes), _lib.ptr(valid),
+                                   int(threads or os.cpu_count() or 1))
+    if rc != _lib.OK:
+        raise ValueError("mp2_pack_host: bad argument")
+    return codes, valid
+
+
+def tnf_from_packed(codes, valid, offsets, relative=True, want_gc=False, want_counts=False, device=-1,
+                    out_counts=None, out_rel=None, out_gc=None):
+    """tnf_from_concat on the 2-bit packed stream of pack_parts (offsets in bases)."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint32)
+    valid = np.ascontiguousarray(valid, dtype=np.uint32)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    quads = (int(offsets[-1]) + 63) // 64 if n >= 0 and len(offsets) else 0
+    if len(codes) < 4 * quads or len(valid) < 2 * quads:
+        raise ValueError("codes / valid are shorter than offsets[-1] bases")
+    counts = rel = gc = None
+    if want_counts or not relative or out_counts is not None:
+        counts = _check_out(out_counts, (n, NCANON), np.uint32, "out_counts") if out_counts is not None \
+            else _out((n, NCANON), np.uint32)
+    if relative or out_rel is not None:
+        rel = _check_out(out_rel, (n, NCANON), np.float32, "out_rel") if out_rel is not None \
+            else _out((n, NCANON), np.float32)
+    if want_gc or out_gc is not None:
+        gc = _check_out(out_gc, (n,), np.float32, "out_gc") if out_gc is not None else np.empty(n, dtype=np.float32)
+    _lib.check(_lib.load().mp2_tnf_packed(_lib.ptr(codes), _lib.ptr(valid), _lib.ptr(offsets), n, device,
+                                          _lib.ptr(counts), _lib.ptr(rel), _lib.ptr(gc)))
+    return counts, rel, gc
+
+
 def get_tnf(seq_list, relative=True, threads=1):
     """Canonical 4-mer profile of every sequence (rows in input order).
 

@@ -642,7 +642,9 @@ cov_order_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict
     long long tmax = -1, tmin = LLONG_MAX;
     unsigned int span = 0;
     if (e0 < n_events) {
-        int64_t c = last_le(ev_off, ev_first[blockIdx.x], n, e0);
+        // contigs of this tile: ev_first[tile] .. ev_first[tile + 1] (the map has one entry beyond the last tile)
+        const int64_t c_hi = (int64_t)ev_first[blockIdx.x + 1] + 1;
+        int64_t c = last_le(ev_off, ev_first[blockIdx.x], c_hi < n ? c_hi : n, e0);
         int64_t next = ev_off[c + 1], base = off[c], len = off[c + 1] - base;
         uint32_t sv[PER], ev[PER];
         if (e0 + PER <= n_events && ((reinterpret_cast<uintptr_t>(starts + e0) | reinterpret_cast<uintptr_t>(ends + e0)) & 15) == 0) {
@@ -733,35 +735,49 @@ cov_order_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict
     }
 }
 
-// disorder across tiles: max over the tiles of (largest key before the tile) - (smallest key of the tile)
+// disorder across tiles: max over the tiles of (largest key before the tile) - (smallest key of the tile).
+// One CTA, 8 consecutive tiles per thread.
 __global__ void __launch_bounds__(1024)
 cov_order_scan_kernel(const OrderTile *__restrict__ tiles, int64_t n_tiles, unsigned int *__restrict__ flag) {
+    constexpr int PER = 8;
     __shared__ long long s_w[32];
     __shared__ long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = -1;
     __syncthreads();
     unsigned long long dis = 0;
-    for (int64_t b = 0; b < n_tiles; b += 1024) {
-        const int64_t i = b + tid;
-        const long long v = i < n_tiles ? tiles[i].kmax : -1;
-        const long long mn = i < n_tiles ? tiles[i].kmin : LLONG_MAX;
-        long long incl = v;
+    for (int64_t b = 0; b < n_tiles; b += 1024 * PER) {
+        const int64_t i0 = b + (int64_t)tid * PER;
+        long long mx[PER], mn[PER];
+        long long tmax = -1;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const bool in = i0 + k < n_tiles;
+            mx[k] = in ? tiles[i0 + k].kmax : -1;
+            mn[k] = in ? tiles[i0 + k].kmin : LLONG_MAX;
+            tmax = mx[k] > tmax ? mx[k] : tmax;
+        }
+        long long incl = tmax;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const long long t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o && t > incl) incl = t;
         }
-        long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) excl = -1;
+        long long pre = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) pre = -1;
         if (lane == 31) s_w[warp] = incl;
         __syncthreads();
-        long long pre = s_carry;
-        for (int w = 0; w < warp; w++) pre = s_w[w] > pre ? s_w[w] : pre;
-        pre = excl > pre ? excl : pre;  // largest key before tile i
-        if (mn != LLONG_MAX && pre > mn && (unsigned long long)(pre - mn) > dis) dis = (unsigned long long)(pre - mn);
+        const long long carry = s_carry;
+        pre = carry > pre ? carry : pre;
+        for (int w = 0; w < warp; w++) pre = s_w[w] > pre ? s_w[w] : pre;  // largest key before this thread's tiles
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            if (mn[k] != LLONG_MAX && pre > mn[k] && (unsigned long long)(pre - mn[k]) > dis)
+                dis = (unsigned long long)(pre - mn[k]);
+            pre = mx[k] > pre ? mx[k] : pre;
+        }
         __syncthreads();
-        if (tid == 1023) s_carry = incl > pre ? incl : pre;
+        if (tid == 1023) s_carry = pre;
         __syncthreads();
     }
     unsigned int d32 = dis > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned int)dis;
@@ -1516,9 +1532,13 @@ cov_stream_kernel(const __grid_constant__ TileArgs a) {
 // =====================================================================================================
 // cov_stream2_kernel: the streaming algorithm again, leaner and order-tolerant.
 //
-//   * Events reach the warp through a ring in its shared memory filled by the bulk-copy engine
-//     (cp.async.bulk + mbarrier, 4 stages of 64 events per array): no registers, no scoreboard and no
-//     re-alignment when a window ends in the middle of a batch -- the next batch simply starts at e_cur.
+//   * Events reach the warp through a ring in its shared memory filled by asynchronous copies (cp.async =
+//     LDGSTS, 4 stages of 64 events per array, one commit group per stage): no registers, no scoreboard and
+//     no re-alignment when a window ends in the middle of a batch -- the next batch simply starts at e_cur.
+//     (A first version used the bulk-copy engine, cp.async.bulk + mbarrier: UBLKCP takes its operands from
+//     uniform registers, and since the compiler cannot prove the per-run addresses warp-uniform it wraps every
+//     copy in an elect / R2UR.BROADCAST / retry loop -- about 100 instructions per stage, a third of all
+//     instructions of the kernel.  Per-lane 4-byte copies cost 12.)
 //   * Bounded disorder: the blocks of a BAM are ordered by READ position, so the second block of a read with
 //     a D / N operation starts after the first blocks of the following reads.  Events are consumed by the
 //     running maximum of their starts: a batch is taken whole while max(pm, batch max) < t_hi + delta
@@ -1546,10 +1566,9 @@ constexpr int C4_LIMIT4 = 4 * (COV_BINS - 1);
 // The histogram sits at a shared-window address that is a multiple of its own size (2 KB; the window of a CTA
 // starts with 1 KB the system reserves): base | offset == base + offset for every offset inside it, which the
 // position walk uses to test 16 bins with one OR chain.  (Checked when the kernel starts.)
-constexpr int C4_PAD = (2048 - (1024 + (int)sizeof(int32_t) * C3_WORDS + 8 * C4_NST) % 2048) % 2048;
+constexpr int C4_PAD = (2048 - (1024 + (int)sizeof(int32_t) * C3_WORDS) % 2048) % 2048;
 struct __align__(1024) C4Smem {
     int32_t T[C3_WORDS];         // 4 * difference array: window + overflow region, 4 pad words per 64 slots
-    unsigned long long bar[C4_NST];
     uint8_t pad[C4_PAD];
     uint32_t hist[COV_BINS];
     uint32_t ring_s[C4_RING];
@@ -1568,26 +1587,16 @@ __device__ __forceinline__ int4 lds_v4(uint32_t saddr) {
     return v;
 }
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+// cp.async (LDGSTS): global -> shared without a register in between; 4-byte copies take any alignment
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int V> __device__ __forceinline__ void smem_add_lit(uint32_t saddr) {
+    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(saddr), "n"(V) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "MP2_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra MP2_DONE;\n\t"
-        "bra MP2_WAIT;\n\t"
-        "MP2_DONE:\n\t}" ::"r"(bar), "r"(parity)
-        : "memory");
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void smem_add_if(uint32_t saddr, int v, bool cond) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.s32 [%0], %1;\n\t}" ::"r"(saddr), "r"(v),
@@ -1651,7 +1660,7 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
     const int lane = threadIdx.x;
     const uint32_t sT0 = smem_base_opaque(sm.T);
     const uint32_t rS0 = smem_base_opaque(sm.ring_s), rE0 = smem_base_opaque(sm.ring_e);
-    const uint32_t bar0 = smem_base_opaque(sm.bar), h0 = smem_base_opaque(sm.hist);
+    const uint32_t h0 = smem_base_opaque(sm.hist);
     if (h0 & 2047u) {  // the shared window is not laid out as assumed: leave the sample to the general path
         if (lane == 0) *a.gate_out = 1;
         return;
@@ -1662,21 +1671,7 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
     // (cov_bounds_run_kernel sends anything else to the general path)
     const int delta = C3_S - (int)(span < (uint32_t)C3_S ? span : (uint32_t)C3_S);
     for (int i = lane; i < COV_BINS; i += 32) sm.hist[i] = 0;
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < C4_NST; i++) mbar_init(bar0 + 8u * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
     __syncwarp();
-    // bulk copies need 16-byte aligned global addresses: copy from the aligned address at or before the array
-    // (the extra bytes are inside the first / last 16-byte granule of the allocation)
-    const uint32_t ms = ((uint32_t)reinterpret_cast<uintptr_t>(a.starts) >> 2) & 3u;
-    const uint32_t me = ((uint32_t)reinterpret_cast<uintptr_t>(a.ends) >> 2) & 3u;
-    const uint32_t *__restrict__ s_al = a.starts - ms;
-    const uint32_t *__restrict__ e_al = a.ends - me;
-    const int64_t lim_s = ((int64_t)ms + a.n_events + 3) & ~3ll, lim_e = ((int64_t)me + a.n_events + 3) & ~3ll;
-    uint32_t sq = 0;  // stages issued so far by this warp: slot = sq & 3, phase parity of the slot = (sq >> 2) & 1
 
     for (;;) {
         int64_t run = 0;
@@ -1688,51 +1683,39 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
         const int64_t e_base = a.e_lo[run];
         const int64_t n_ev64 = a.e_hi[run] - e_base;
         const int n_ev = n_ev64 > 0 ? (int)n_ev64 : 0;
-        // ---- staging geometry: stage s holds s_al[gs0 + ST s ..) and e_al[ge0 + ST s ..) ----
+        // ---- staging: stage s = events [ST s, ST s + ST) of the run, in ring slot s % NST; one commit group per
+        // stage, and always floor(e_cur / ST) + NST groups committed (empty ones beyond the run's last event), so
+        // that "all but the NST - 2 most recent groups" covers every stage the next 64 events can be in
         constexpr int ST = C4_STAGE, RM = C4_RING - 1;
-        const int64_t gs0 = (e_base + ms) & ~3ll, ge0 = (e_base + me) & ~3ll;
-        const int r_s = (int)((e_base + ms) & 3), r_e = (int)((e_base + me) & 3);
-        const int rmax = r_s > r_e ? r_s : r_e, rmin = r_s < r_e ? r_s : r_e;
-        const int n_st = n_ev > 0 ? (rmax + n_ev - 1) / ST + 1 : 0;
-        // stages below `full` are whole for both arrays (only the last stage of the whole sample can be short)
-        const int64_t fs = (lim_s - gs0) / ST, fe = (lim_e - ge0) / ST;
-        const int full = (int)((fs < fe ? fs : fe) < n_st ? (fs < fe ? fs : fe) : n_st);
-        const uint32_t sq0 = sq;
-        int issued = 0, waited = 0;
-        int avail = -rmax;             // events [0, avail) of the run are in the ring (ST * waited - rmax)
-        int next_issue = -(1 << 30);   // the next stage may be issued once e_cur reaches this event
-        const uint32_t *src_s = s_al + gs0, *src_e = e_al + ge0;
-        const int bs = r_s + ST * (int)(sq0 & (C4_NST - 1)) + lane, be = r_e + ST * (int)(sq0 & (C4_NST - 1)) + lane;
-        auto issue = [&]() {  // stage `issued`; its slot was read for the last time before e_cur
-            if (lane == 0) {
-                const uint32_t slot = (sq0 + (uint32_t)issued) & (uint32_t)(C4_NST - 1), bar = bar0 + 8u * slot;
-                const uint32_t ds = rS0 + 4u * ST * slot, de = rE0 + 4u * ST * slot;
-                if (issued < full) {
-                    mbar_expect_tx(bar, 8u * ST);
-                    bulk_g2s(ds, src_s, 4u * ST, bar);
-                    bulk_g2s(de, src_e, 4u * ST, bar);
-                } else {
-                    int64_t cs = lim_s - (gs0 + (int64_t)ST * issued), ce = lim_e - (ge0 + (int64_t)ST * issued);
-                    cs = cs > ST ? ST : (cs < 0 ? 0 : cs);
-                    ce = ce > ST ? ST : (ce < 0 ? 0 : ce);
-                    mbar_expect_tx(bar, (uint32_t)(4 * (cs + ce)));
-                    if (cs > 0) bulk_g2s(ds, src_s, (uint32_t)(4 * cs), bar);
-                    if (ce > 0) bulk_g2s(de, src_e, (uint32_t)(4 * ce), bar);
+        const uint32_t *__restrict__ ev_s = a.starts + e_base;
+        const uint32_t *__restrict__ ev_e = a.ends + e_base;
+        int issued = 0;   // stages (= groups) committed
+        int avail = 0;    // events [0, avail) of the run are in the ring and visible to every lane
+        int next_issue = 0;  // the next stage may be issued once e_cur reaches this event: ST * (issued - NST + 1)
+        // this lane's next copy: event ST * issued + lane, ring byte offset 4 * (that & RM)
+        const uint32_t *p_s = ev_s + lane, *p_e = ev_e + lane;
+        uint32_t off = 4u * (uint32_t)lane;
+        int e_next = lane;
+        auto issue = [&]() {
+#pragma unroll
+            for (int h = 0; h < ST / 32; h++) {
+                if (e_next + 32 * h < n_ev) {
+                    cp_async4(rS0 + off + 128u * h, p_s + 32 * h);
+                    cp_async4(rE0 + off + 128u * h, p_e + 32 * h);
                 }
             }
-            src_s += ST;
-            src_e += ST;
+            cp_async_commit();
+            p_s += ST;
+            p_e += ST;
+            e_next += ST;
+            off = (off + 4u * ST) & (uint32_t)(4 * C4_RING - 1);
             issued++;
-            next_issue = ST * (issued - C4_NST + 1) - rmin;
+            next_issue += ST;
         };
-        auto wait_next = [&]() {
-            const uint32_t q = sq0 + (uint32_t)waited;
-            mbar_wait(bar0 + 8u * (q & (uint32_t)(C4_NST - 1)), (q / (uint32_t)C4_NST) & 1u);
-            waited++;
-            avail += ST;
-        };
-        __syncwarp();  // the previous run's reads of the ring are done
-        while (issued < n_st && issued < C4_NST) issue();
+        cp_async_wait<0>();
+        __syncwarp();  // the previous run's copies have landed and its reads of the ring are done
+        for (int s_ = 0; s_ < C4_NST; s_++) issue();
+        next_issue = ST;  // stage NST goes into the slot of stage 0: after the first ST events
 
         int e_cur = 0;  // next event to consume, relative to e_base
         int4 cur = make_int4(0, 0, 0, 0);
@@ -1762,15 +1745,16 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
             int open = 0;
             while (e_cur < n_ev) {
                 // ---- staging: refill the slots behind e_cur, wait for the stages the next 64 events are in ----
-                if (e_cur >= next_issue && issued < n_st) {
-                    __syncwarp();
-                    do issue(); while (e_cur >= next_issue && issued < n_st);
+                if (e_cur >= next_issue) {
+                    __syncwarp();  // every lane is done reading the slots that are about to be overwritten
+                    do issue(); while (e_cur >= next_issue);
                 }
-                {
-                    const int want = e_cur + 64 < n_ev ? e_cur + 64 : n_ev;
-                    while (want > avail) wait_next();
+                if ((e_cur + 64 < n_ev ? e_cur + 64 : n_ev) > avail) {
+                    cp_async_wait<C4_NST - 2>();  // this lane's copies of all but the NST - 2 newest stages
+                    __syncwarp();                 // ... and everybody else's
+                    avail = ST * (issued - (C4_NST - 2));
                 }
-                const int i0 = (bs + e_cur) & RM, j0 = (be + e_cur) & RM;
+                const int i0 = (e_cur + lane) & RM, j0 = i0;
                 const int room = (n_ev < cur.y ? n_ev : cur.y) - e_cur;  // events ahead in this contig
                 if (k > 0 && room >= 64) {
                     // ---- 64 events of one contig: both batches are taken whole if none is beyond the limit ----
@@ -1790,12 +1774,12 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
                         const int re0 = rs0 + (int)b0, re1 = rs1 + (int)b1;
                         const bool in0 = rs0 >= 0 && re0 < C3_W + C3_S, in1 = rs1 >= 0 && re1 < C3_W + C3_S;
                         if (in0) {
-                            smem_add(sT0 + 4u * (uint32_t)c3_phys(rs0), 4);
-                            smem_add(sT0 + 4u * (uint32_t)c3_phys(re0), -4);
+                            smem_add_lit<4>(sT0 + 4u * (uint32_t)c3_phys(rs0));
+                            smem_add_lit<-4>(sT0 + 4u * (uint32_t)c3_phys(re0));
                         }
                         if (in1) {
-                            smem_add(sT0 + 4u * (uint32_t)c3_phys(rs1), 4);
-                            smem_add(sT0 + 4u * (uint32_t)c3_phys(re1), -4);
+                            smem_add_lit<4>(sT0 + 4u * (uint32_t)c3_phys(rs1));
+                            smem_add_lit<-4>(sT0 + 4u * (uint32_t)c3_phys(re1));
                         }
                         const int mre = re0 > re1 ? re0 : re1, mrs = rs0 < rs1 ? rs0 : rs1;
                         const uint32_t mb = b0 > b1 ? b0 : b1;
@@ -1962,8 +1946,7 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
         if (have && whi >= wlo && in_run > 0) c4_close_window(a, c, false, deep_max, in_run, sm.hist);
         viol |= v_re >= C3_W + C3_S || v_rs < 0 || v_blk > span;
         if (__any_sync(0xffffffffu, viol) && lane == 0) *a.gate_out = 1;  // unreliable ranges: the general path redoes the sample
-        while (waited < issued) wait_next();  // no copy may be in flight when the ring is reused
-        sq = sq0 + (uint32_t)issued;
+
     }
 }
 
@@ -2053,10 +2036,10 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
             off, n_contigs, end_excl, (float *)d_cov, cov_stride, (mp2_cov_stats *)d_stats, gate);
     }
     MP2_CUDA(cudaGetLastError());
-    if (n_events > 0) {
+    if (n_events > 0) {  // one entry beyond the last tile: the contigs of tile t are first[t] .. first[t + 1]
         Launch L("cov_map_kernel", stream);
-        cov_map_kernel<<<(unsigned)((n_ev_tiles + 255) / 256), 256, 0, stream>>>(ev_off, n_contigs, COV_EV_TILE,
-                                                                               n_ev_tiles, ev_first.as<int32_t>());
+        cov_map_kernel<<<(unsigned)((n_ev_tiles + 1 + 255) / 256), 256, 0, stream>>>(ev_off, n_contigs, COV_EV_TILE,
+                                                                                   n_ev_tiles + 1, ev_first.as<int32_t>());
     }
     MP2_CUDA(cudaGetLastError());
 
@@ -2163,6 +2146,48 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
     }
     return cov_general_path(starts, ends, ev_off, off, n_contigs, n_events, n_pos, ev_first.as<int32_t>(), tp,
                             ctrs.as<int>(), (float *)d_cov, cov_stride, (mp2_cov_stats *)d_stats, stream);
+}
+
+// The two numbers mp2_cov_events_device can be vouched for with, measured exactly on the device: what a producer
+// that does not know them (unlike mp2_bam_open, which measures while it decodes) calls once per sample.
+extern "C" int mp2_cov_order_device(const void *d_starts, const void *d_ends, const void *d_ev_off,
+                                    const void *d_contig_off, int64_t n_contigs, int64_t n_events,
+                                    uint32_t *max_span, uint32_t *max_disorder, void *stream_) {
+    if (n_contigs < 0 || n_events < 0) return fail(MP2_EINVAL, "negative size");
+    if (!max_span || !max_disorder || !d_contig_off || !d_ev_off || (n_events > 0 && (!d_starts || !d_ends)))
+        return fail(MP2_EINVAL, "NULL argument");
+    MP2_TRY(require_device(-1));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    *max_span = *max_disorder = 0;
+    if (n_contigs == 0 || n_events == 0) return MP2_OK;
+    const int64_t n_ev_tiles = (n_events + COV_EV_TILE - 1) / COV_EV_TILE;
+    Temp flags, ev_first, tiles;
+    MP2_TRY(flags.alloc(sizeof(unsigned int) * 4, stream));
+    MP2_TRY(ev_first.alloc(sizeof(int32_t) * (n_ev_tiles + 1), stream));
+    MP2_TRY(tiles.alloc(sizeof(OrderTile) * n_ev_tiles, stream));
+    MP2_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(unsigned int) * 4, stream));
+    {
+        Launch L("cov_map_kernel", stream);
+        cov_map_kernel<<<(unsigned)((n_ev_tiles + 1 + 255) / 256), 256, 0, stream>>>(
+            (const int64_t *)d_ev_off, n_contigs, COV_EV_TILE, n_ev_tiles + 1, ev_first.as<int32_t>());
+    }
+    {
+        Launch L("cov_order_kernel", stream);
+        cov_order_kernel<<<(unsigned)n_ev_tiles, 256, 0, stream>>>(
+            (const uint32_t *)d_starts, (const uint32_t *)d_ends, (const int64_t *)d_ev_off, (const int64_t *)d_contig_off,
+            n_contigs, n_events, ev_first.as<int32_t>(), tiles.as<OrderTile>(), flags.as<unsigned int>());
+    }
+    {
+        Launch L("cov_order_scan_kernel", stream);
+        cov_order_scan_kernel<<<1, 1024, 0, stream>>>(tiles.as<OrderTile>(), n_ev_tiles, flags.as<unsigned int>());
+    }
+    MP2_CUDA(cudaGetLastError());
+    unsigned int h[4] = {0, 0, 0, 0};
+    MP2_CUDA(cudaMemcpyAsync(h, flags.p, sizeof h, cudaMemcpyDeviceToHost, stream));
+    MP2_CUDA(cudaStreamSynchronize(stream));
+    *max_span = h[1];
+    *max_disorder = h[2];
+    return MP2_OK;
 }
 
 // ---------------- general path: difference array in HBM (any order, any span, any depth) ----------------

@@ -479,8 +479,8 @@ template <int MODE, int PS>
 __global__ void __launch_bounds__(TNF_THREADS)
 tnf_packed_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ valid, int64_t n_bases,
                   const int64_t *__restrict__ offsets, int64_t n, const int32_t *__restrict__ first_contig,
-                  int64_t n_chunks, uint32_t *__restrict__ counts, unsigned long long *__restrict__ gc_counts,
-                  int *__restrict__ work_counter) {
+                  int64_t chunk_begin, int64_t n_chunks, uint32_t *__restrict__ counts,
+                  unsigned long long *__restrict__ gc_counts, int *__restrict__ work_counter) {
     constexpr int WORDS = TnfTab<MODE>::WORDS;
     constexpr int TNF_PIECE = 1 << PS;
     uint32_t *tab = tnf_tab;
@@ -497,7 +497,7 @@ tnf_packed_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict
         if (lane == 0) kc = atomicAdd(work_counter, 1);
         kc = __shfl_sync(0xffffffffu, kc, 0);
         if (kc >= n_chunks) break;
-        const int64_t base = kc * TNF_PIECE;
+        const int64_t base = (chunk_begin + kc) * TNF_PIECE;
         const uint32_t *__restrict__ pc = codes + (base >> 4);
         const uint32_t *__restrict__ pv = valid + (base >> 5);
         const int piece_hi = (int)(n_bases - base < TNF_PIECE ? n_bases - base : TNF_PIECE);
@@ -807,6 +807,65 @@ extern "C" int mp2_pack_device(const void *d_bases, int64_t n_bases, void *d_cod
     return MP2_OK;
 }
 
+namespace mp2 {
+
+int64_t tnf_packed_num_chunks(int64_t n_bases) {
+    const int ps = tnf_piece_shift(n_bases);
+    return (n_bases + ((int64_t)1 << ps) - 1) >> ps;
+}
+
+// Pieces wholly inside the first `done` bases (host staging pipelines on this): a piece reads its own quads and
+// the last group of the quad before it.
+int64_t tnf_packed_chunks_ready(int64_t done, int64_t n_bases) {
+    return done >> tnf_piece_shift(n_bases);
+}
+
+// Enqueue the packed counting kernel for pieces [chunk_begin, chunk_end).  d_counts / d_gc_counts must have been
+// zeroed (once) before the first range.
+int tnf_packed_launch_range(const uint32_t *d_codes, const uint32_t *d_valid, const int64_t *d_offsets, int64_t n,
+                            int64_t n_bases, int64_t chunk_begin, int64_t chunk_end, uint32_t *d_counts,
+                            unsigned long long *d_gc_counts, cudaStream_t stream) {
+    MP2_TRY(upload_tables());
+    const int64_t n_chunks = chunk_end - chunk_begin;
+    if (n_chunks <= 0) return MP2_OK;
+    const int ps = tnf_piece_shift(n_bases);
+    Temp map, adj, ctr;  // the packed kernel keeps the nominal boundaries (snap = 0)
+    MP2_TRY(map.alloc(sizeof(int32_t) * (n_chunks + 1), stream));
+    MP2_TRY(adj.alloc(sizeof(int32_t) * (n_chunks + 1), stream));
+    MP2_TRY(ctr.alloc(sizeof(int), stream));
+    MP2_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int), stream));
+    {
+        Launch L("tnf_chunk_map_kernel", stream);
+        tnf_chunk_map_kernel<<<(unsigned)((n_chunks + 1 + 255) / 256), 256, 0, stream>>>(
+            d_offsets, n, 0, ps, 0, chunk_begin, n_chunks, map.as<int32_t>(), adj.as<int32_t>());
+    }
+    MP2_CUDA(cudaGetLastError());
+    const int mode = tnf_mode();
+#define MP2_TNFP_LAUNCH(M, PS)                                                                                  \
+    do {                                                                                                        \
+        int occ = 0;                                                                                            \
+        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_packed_kernel<M, PS>, TNF_THREADS, 0));\
+        if (occ < 1) occ = 1;                                                                                   \
+        int64_t grid = (int64_t)num_sms() * occ;                                                                \
+        if (grid > n_chunks) grid = n_chunks;                                                                   \
+        Launch L("tnf_packed_kernel", stream);                                                                  \
+        tnf_packed_kernel<M, PS><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(                                   \
+            d_codes, d_valid, n_bases, d_offsets, n, map.as<int32_t>(), chunk_begin, n_chunks, d_counts,        \
+            d_gc_counts, ctr.as<int>());                                                                        \
+    } while (0)
+    if (mode == 5 && ps == 16) MP2_TNFP_LAUNCH(5, 16);
+    else if (mode == 5 && ps == 15) MP2_TNFP_LAUNCH(5, 15);
+    else if (mode == 5) MP2_TNFP_LAUNCH(5, 14);
+    else if (ps == 16) MP2_TNFP_LAUNCH(4, 16);
+    else if (ps == 15) MP2_TNFP_LAUNCH(4, 15);
+    else MP2_TNFP_LAUNCH(4, 14);
+#undef MP2_TNFP_LAUNCH
+    MP2_CUDA(cudaGetLastError());
+    return MP2_OK;
+}
+
+}  // namespace mp2
+
 extern "C" int mp2_tnf_packed_device(const void *d_codes, const void *d_valid, const void *d_offsets, int64_t n,
                                      int64_t n_bases, void *d_counts, void *d_rel, void *d_gc, void *stream_) {
     using namespace mp2;
@@ -819,47 +878,13 @@ extern "C" int mp2_tnf_packed_device(const void *d_codes, const void *d_valid, c
     MP2_TRY(require_device(-1));
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return MP2_OK;
-    MP2_TRY(upload_tables());
-    Temp gcc, map, ctr;
+    Temp gcc;
     MP2_TRY(gcc.alloc(sizeof(unsigned long long) * n, stream));
     MP2_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * MP2_NCANON * n, stream));
     MP2_CUDA(cudaMemsetAsync(gcc.p, 0, sizeof(unsigned long long) * n, stream));
-    const int ps = tnf_piece_shift(n_bases);
-    const int64_t n_chunks = (n_bases + ((int64_t)1 << ps) - 1) >> ps;
-    if (n_chunks > 0) {
-        Temp adj;  // the packed kernel keeps the nominal boundaries (snap = 0)
-        MP2_TRY(map.alloc(sizeof(int32_t) * (n_chunks + 1), stream));
-        MP2_TRY(adj.alloc(sizeof(int32_t) * (n_chunks + 1), stream));
-        MP2_TRY(ctr.alloc(sizeof(int), stream));
-        MP2_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int), stream));
-        {
-            Launch L("tnf_chunk_map_kernel", stream);
-            tnf_chunk_map_kernel<<<(unsigned)((n_chunks + 1 + 255) / 256), 256, 0, stream>>>(
-                (const int64_t *)d_offsets, n, 0, ps, 0, 0, n_chunks, map.as<int32_t>(), adj.as<int32_t>());
-        }
-        MP2_CUDA(cudaGetLastError());
-        const int mode = tnf_mode();
-#define MP2_TNFP_LAUNCH(M, PS)                                                                                  \
-    do {                                                                                                        \
-        int occ = 0;                                                                                            \
-        MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tnf_packed_kernel<M, PS>, TNF_THREADS, 0));\
-        if (occ < 1) occ = 1;                                                                                   \
-        int64_t grid = (int64_t)num_sms() * occ;                                                                \
-        if (grid > n_chunks) grid = n_chunks;                                                                   \
-        Launch L("tnf_packed_kernel", stream);                                                                  \
-        tnf_packed_kernel<M, PS><<<(unsigned)grid, TNF_THREADS, 0, stream>>>(                                   \
-            (const uint32_t *)d_codes, (const uint32_t *)d_valid, n_bases, (const int64_t *)d_offsets, n,       \
-            map.as<int32_t>(), n_chunks, (uint32_t *)d_counts, gcc.as<unsigned long long>(), ctr.as<int>());    \
-    } while (0)
-        if (mode == 5 && ps == 16) MP2_TNFP_LAUNCH(5, 16);
-        else if (mode == 5 && ps == 15) MP2_TNFP_LAUNCH(5, 15);
-        else if (mode == 5) MP2_TNFP_LAUNCH(5, 14);
-        else if (ps == 16) MP2_TNFP_LAUNCH(4, 16);
-        else if (ps == 15) MP2_TNFP_LAUNCH(4, 15);
-        else MP2_TNFP_LAUNCH(4, 14);
-#undef MP2_TNFP_LAUNCH
-        MP2_CUDA(cudaGetLastError());
-    }
+    MP2_TRY(tnf_packed_launch_range((const uint32_t *)d_codes, (const uint32_t *)d_valid, (const int64_t *)d_offsets, n,
+                                    n_bases, 0, tnf_packed_num_chunks(n_bases), (uint32_t *)d_counts,
+                                    gcc.as<unsigned long long>(), stream));
     MP2_TRY(tnf_finalize((const uint32_t *)d_counts, gcc.as<unsigned long long>(), (const int64_t *)d_offsets, n,
                          (float *)d_rel, (float *)d_gc, stream));
     return MP2_OK;

@@ -25,7 +25,7 @@ def main(args):
 
     # counts, relative TNF, GC and both scores of every contig; MAGs are split over the devices by base pairs
     logger.info("Computing tetranucleotide frequencies and contig scores.")
-    res = composition_on_devices(mags, parse_devices(args))
+    res = composition_on_devices(mags, parse_devices(args), threads=getattr(args, "threads", None))
 
     cache = PickleCache(args.output_directory.joinpath("tnfs.pickle.gz"), "tetranucleotide frequencies")
     wanted = {m.genome for m in mags}

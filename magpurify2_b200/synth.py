@@ -82,13 +82,23 @@ def make_mags(n_mags, seed=0, long_contigs=False, mean_bp=3.0e6, n_contigs=300, 
     return dict(bases=bases, offsets=offsets, mag_off=mag_off, lengths=clen)
 
 
+def subset_layout(clen, mag_off, gc, mags):
+    """The layout (mag_layout's triple) of the MAGs `mags` (indices) of a larger layout, in that order."""
+    rows = np.concatenate([np.arange(mag_off[m], mag_off[m + 1]) for m in mags]) if len(mags) else np.zeros(0, np.int64)
+    sizes = np.array([mag_off[m + 1] - mag_off[m] for m in mags], dtype=np.int64)
+    return clen[rows], np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64), gc[rows]
+
+
 def make_mags_device(n_mags, device, seed=0, long_contigs=False, mean_bp=3.0e6, n_contigs=300,
-                     mags_per_block=64):
+                     mags_per_block=64, layout=None):
     """Same model, bases generated on `device` with torch (bench sizes: 3 Gbp would take minutes
-    on the host).  Returns dict(bases torch.uint8[L] on device, offsets/mag_off/lengths NumPy)."""
+    on the host).  Returns dict(bases torch.uint8[L] on device, offsets/mag_off/lengths NumPy).
+    layout: a (contig_len, mag_off, gc) triple to fill instead of mag_layout(n_mags, ...) (a rank's share of a
+    larger MAG set)."""
     import torch
 
-    clen, mag_off, gc = mag_layout(n_mags, seed, long_contigs, mean_bp, n_contigs)
+    clen, mag_off, gc = layout if layout is not None else mag_layout(n_mags, seed, long_contigs, mean_bp, n_contigs)
+    n_mags = len(mag_off) - 1
     offsets = np.zeros(len(clen) + 1, dtype=np.int64)
     np.cumsum(clen, out=offsets[1:])
     L = int(offsets[-1])
@@ -211,40 +221,69 @@ def make_events_device(lengths, mag_off, sample, device, seed=0, read_len=READ_L
     R = int(ev_off[-1])
     gen = torch.Generator(device=device)
     gen.manual_seed((SEED_COV ^ (sample << 20)) + seed)
-    d_n = torch.from_numpy(n_reads).to(device)
-    cid = torch.repeat_interleave(torch.arange(len(lengths), device=device, dtype=torch.int64), d_n,
-                                  output_size=R)
-    span = torch.from_numpy(lengths - read_len + 1).to(device)[cid]
-    st = torch.floor(torch.rand(R, device=device, generator=gen, dtype=torch.float64) * span).to(torch.int64)
-    key = (cid << 32) | st
-    del cid, span
-    key, _ = torch.sort(key)
-    st = (key & 0xFFFFFFFF)
-    del key
+    # contigs are handled in blocks of ~64 M reads so that the temporaries (64-bit sort keys) stay small next to
+    # the result: a C4 shard has billions of reads per sample
+    n_c = len(lengths)
+    cuts = [0]
+    while cuts[-1] < n_c:
+        k = int(np.searchsorted(ev_off, ev_off[cuts[-1]] + (64 << 20), side="left"))
+        cuts.append(min(n_c, max(k, cuts[-1] + 1)))
+    n_out = None
+    if variant:
+        out_s, out_e, per_contig_blocks = [], [], []
+    else:
+        starts = torch.empty(R, dtype=torch.int32, device=device)
+        ends = torch.empty(R, dtype=torch.int32, device=device)
+    for c0, c1 in zip(cuts[:-1], cuts[1:]):
+        r0, r1 = int(ev_off[c0]), int(ev_off[c1])
+        Rb = r1 - r0
+        if Rb == 0:
+            if variant:
+                per_contig_blocks.append(np.zeros(c1 - c0, dtype=np.int64))
+            continue
+        d_n = torch.from_numpy(n_reads[c0:c1]).to(device)
+        cid = torch.repeat_interleave(torch.arange(c1 - c0, device=device, dtype=torch.int64), d_n, output_size=Rb)
+        span = torch.from_numpy((lengths[c0:c1] - read_len + 1)).to(device)[cid]
+        st = torch.floor(torch.rand(Rb, device=device, generator=gen, dtype=torch.float64) * span).to(torch.int64)
+        key, _ = torch.sort((cid << 32) | st)
+        del cid, span
+        st = key & 0xFFFFFFFF
+        if not variant:
+            starts[r0:r1] = st.to(torch.int32)  # bit pattern == uint32 (contigs are < 2^31)
+            ends[r0:r1] = (st + read_len).to(torch.int32)
+            del key, st
+            continue
+        cid = key >> 32
+        del key
+        clen = torch.from_numpy(lengths[c0:c1].astype(np.int64)).to(device)[cid]
+        rl = torch.clamp(torch.round(torch.randn(Rb, device=device, generator=gen) * 15.0 + read_len), 50, 250).to(torch.int64)
+        two = torch.rand(Rb, device=device, generator=gen) < 0.02
+        a = torch.floor(torch.rand(Rb, device=device, generator=gen) * (rl - 20)).to(torch.int64) + 10
+        k = torch.randint(1, 4, (Rb,), device=device, generator=gen)
+        dele = torch.rand(Rb, device=device, generator=gen) < 0.5
+        s2 = st + a + torch.where(dele, k, torch.zeros_like(k))
+        e2 = s2 + (rl - a - torch.where(dele, torch.zeros_like(k), k))
+        two &= (e2 <= clen) & (e2 > s2)
+        nb = 1 + two.to(torch.int64)
+        at = torch.zeros(Rb + 1, dtype=torch.int64, device=device)
+        torch.cumsum(nb, 0, out=at[1:])
+        nblk = int(at[-1].item())
+        S = torch.empty(nblk, dtype=torch.int32, device=device)
+        E = torch.empty(nblk, dtype=torch.int32, device=device)
+        first = at[:-1]
+        S[first] = st.to(torch.int32)
+        E[first] = torch.where(two, st + a, torch.minimum(st + rl, clen)).to(torch.int32)
+        S[first[two] + 1] = s2[two].to(torch.int32)
+        E[first[two] + 1] = e2[two].to(torch.int32)
+        out_s.append(S)
+        out_e.append(E)
+        per_contig_blocks.append(torch.bincount(cid, weights=nb.to(torch.float64), minlength=c1 - c0).to(torch.int64).cpu().numpy())
+        del cid, clen, rl, two, a, k, dele, s2, e2, nb, at, first, st
     if not variant:
-        starts = st.to(torch.int32)  # bit pattern == uint32 (contigs are < 2^31)
-        ends = (st + read_len).to(torch.int32)
         return starts, ends, torch.from_numpy(ev_off).to(device), R
-    cid = torch.repeat_interleave(torch.arange(len(lengths), device=device, dtype=torch.int64), d_n, output_size=R)
-    clen = torch.from_numpy(lengths.astype(np.int64)).to(device)[cid]
-    del cid
-    rl = torch.clamp(torch.round(torch.randn(R, device=device, generator=gen) * 15.0 + read_len), 50, 250).to(torch.int64)
-    two = torch.rand(R, device=device, generator=gen) < 0.02
-    a = torch.floor(torch.rand(R, device=device, generator=gen) * (rl - 20)).to(torch.int64) + 10
-    k = torch.randint(1, 4, (R,), device=device, generator=gen)
-    dele = torch.rand(R, device=device, generator=gen) < 0.5
-    s2 = st + a + torch.where(dele, k, torch.zeros_like(k))
-    e2 = s2 + (rl - a - torch.where(dele, torch.zeros_like(k), k))
-    two &= (e2 <= clen) & (e2 > s2)
-    at = torch.zeros(R + 1, dtype=torch.int64, device=device)
-    torch.cumsum(1 + two.to(torch.int64), 0, out=at[1:])
-    n_blocks = int(at[-1].item())
-    S = torch.empty(n_blocks, dtype=torch.int32, device=device)
-    E = torch.empty(n_blocks, dtype=torch.int32, device=device)
-    first = at[:-1]
-    S[first] = st.to(torch.int32)
-    E[first] = torch.where(two, st + a, torch.minimum(st + rl, clen)).to(torch.int32)
-    S[first[two] + 1] = s2[two].to(torch.int32)
-    E[first[two] + 1] = e2[two].to(torch.int32)
-    ev_off2 = at[torch.from_numpy(ev_off).to(device)]
-    return S, E, ev_off2, n_blocks
+    S = torch.cat(out_s) if out_s else torch.empty(0, dtype=torch.int32, device=device)
+    E = torch.cat(out_e) if out_e else torch.empty(0, dtype=torch.int32, device=device)
+    blocks = np.concatenate(per_contig_blocks) if per_contig_blocks else np.zeros(0, np.int64)
+    ev_off2 = np.concatenate([[0], np.cumsum(blocks)]).astype(np.int64)
+    return S, E, torch.from_numpy(ev_off2).to(device), int(S.numel())
+

@@ -205,3 +205,40 @@ def test_validade_input_and_signature(tmp_path):
     small.write_bytes(b"x" * 10)
     with pytest.raises(OSError):  # as the reference: seek(-128000) fails on small files
         tools.get_file_signature(small)
+
+
+def _pack_reference(b):
+    L = len(b)
+    nq = (L + 63) // 64
+    hb = np.frombuffer(bytes(b).upper(), dtype=np.uint8)
+    lut = np.full(256, 255, np.uint8)
+    lut[[65, 67, 71, 84]] = [0, 1, 2, 3]
+    c = lut[hb]
+    v = c != 255
+    pad = nq * 64 - L
+    c2 = np.concatenate([np.where(v, c, 0), np.zeros(pad, np.uint8)]).reshape(-1, 16).astype(np.uint32)
+    codes = (c2 << (2 * (15 - np.arange(16, dtype=np.uint32)))).sum(axis=1).astype(np.uint32)
+    v2 = np.concatenate([v, np.zeros(pad, bool)]).reshape(-1, 32).astype(np.uint64)
+    valid = (v2 << (31 - np.arange(32, dtype=np.uint64))).sum(axis=1).astype(np.uint32)
+    return codes, valid
+
+
+def test_host_packer_matches_the_layout_definition():
+    """mp2_pack_host (AVX-512 / scalar, threaded) on the virtual concatenation of several buffers: 2 bits per base,
+    first base most significant, validity bit per base, padded to quads of 64 -- against a NumPy restatement."""
+    from magpurify2_b200 import _composition
+
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTacgtNRYnX-*\x00\xff", dtype=np.uint8)
+    for trial in range(40):
+        k = 8 if trial % 3 == 0 else len(alphabet)
+        parts = [alphabet[rng.integers(0, k, int(rng.integers(0, 900)))].copy() for _ in range(int(rng.integers(1, 9)))]
+        if trial == 7:
+            parts = [np.zeros(0, np.uint8)]
+        codes, valid = _composition.pack_parts(parts, threads=int(rng.integers(1, 5)))
+        want_c, want_v = _pack_reference(np.concatenate(parts))
+        assert np.array_equal(codes, want_c) and np.array_equal(valid, want_v), trial
+    big = alphabet[rng.integers(0, 9, 3_000_001)].copy()  # many tasks, a tail that is not a whole quad
+    codes, valid = _composition.pack_parts([big[:1_000_003], big[1_000_003:]], threads=4)
+    want_c, want_v = _pack_reference(big)
+    assert np.array_equal(codes, want_c) and np.array_equal(valid, want_v)

@@ -57,6 +57,37 @@ def test_packed_path_matches_ascii_and_oracle(oracle):
         assert np.array_equal(gc.cpu().numpy(), want_gc, equal_nan=True)
 
 
+def test_packed_host_path_matches_ascii_path_and_oracle(oracle):
+    """pack_parts (host) + tnf_from_packed (0.375 B/base upload) == tnf_from_concat == oracle, bit for bit; the
+    host packer and the device packer produce the same words."""
+    import torch
+
+    from magpurify2_b200 import _composition, _lib, synth
+
+    d = synth.make_mags(5, seed=23, mean_bp=7e5, n_contigs=70)
+    bases, offsets = d["bases"], d["offsets"]
+    cut = [0, int(offsets[40]), int(offsets[41]) + 17, int(offsets[200]), len(bases)]  # parts need not end at contigs
+    parts = [bases[a:b] for a, b in zip(cut[:-1], cut[1:])]
+    codes, valid = _composition.pack_parts(parts, threads=3)
+    L = len(bases)
+    nq = (L + 63) // 64
+    d_b = torch.from_numpy(bases).cuda()
+    d_codes = torch.zeros(nq * 4, dtype=torch.int32, device="cuda")
+    d_valid = torch.zeros(nq * 2, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.load().mp2_pack_device(d_b.data_ptr(), L, d_codes.data_ptr(), d_valid.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+    assert np.array_equal(d_codes.cpu().numpy().view(np.uint32), codes)
+    assert np.array_equal(d_valid.cpu().numpy().view(np.uint32), valid)
+    c1, r1, g1 = _composition.tnf_from_packed(codes, valid, offsets, relative=True, want_gc=True, want_counts=True)
+    c2, r2, g2 = _composition.tnf_from_concat(bases, offsets, relative=True, want_gc=True, want_counts=True)
+    assert np.array_equal(c1, c2) and np.array_equal(r1.view(np.uint32), r2.view(np.uint32))
+    assert np.array_equal(g1, g2, equal_nan=True)
+    assert np.array_equal(c1, oracle.get_tnf_concat(bases, offsets, relative=False, threads=4))
+    assert np.array_equal(g1, oracle.get_gc_concat(bases, offsets), equal_nan=True)
+    with pytest.raises(ValueError):
+        _composition.tnf_from_packed(codes[:8], valid, offsets)
+
+
 def _write_dataset(tmp, n_mags=4, n_samples=3, seed=9):
     """FASTA files + coordinate-sorted BAMs of a small synthetic community."""
     from magpurify2_b200 import bamio, synth
