@@ -711,7 +711,8 @@ def main():
     torch.cuda.synchronize()
     hb = h_bases.numpy()
     e2e_steps = max(1, min(args.steps, 3))
-    o_rel, o_gc = _composition.pinned_empty((n, 136), np.float32), np.empty(n, dtype=np.float32)
+    o_rel = _composition.pinned_empty((n, 136), np.float32)
+    o_gc = torch.empty(n, dtype=torch.float32, pin_memory=True).numpy()
     _composition.tnf_from_concat(hb, offsets, relative=True, device=local, out_rel=o_rel, out_gc=o_gc)  # warm-up
     barrier()
     t0 = time.perf_counter()
@@ -738,13 +739,25 @@ def main():
     _lib.load().mp2_pack_host((C.c_void_p * 1)(hb.ctypes.data), _lib.ptr(np.array([L], dtype=np.int64)), 1,
                               _lib.ptr(codes), _lib.ptr(valid), host_threads)
     pack_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    runs = _composition.invalid_runs(valid, L, threads=host_threads)
+    runs_s = time.perf_counter() - t0
+    # (a) codes + validity mask, 0.375 B/base
     _composition.tnf_from_packed(codes, valid, offsets, relative=True, device=local, out_rel=o_rel, out_gc=o_gc)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _composition.tnf_from_packed(codes, valid, offsets, relative=True, device=local, out_rel=o_rel, out_gc=o_gc)
+    torch.cuda.synchronize()
+    e2e_mask = L * e2e_steps / (time.perf_counter() - t0) / 1e9
+    # (b) codes + runs of invalid bases, 0.25 B/base: what the composition driver uploads
+    _composition.tnf_from_packed(codes, None, offsets, relative=True, device=local, out_rel=o_rel, out_gc=o_gc, runs=runs)
     barrier()
     e2e_times = []
     for _ in range(e2e_steps):
         t0 = time.perf_counter()
-        _c, h_rel, h_gc = _composition.tnf_from_packed(codes, valid, offsets, relative=True, device=local,
-                                                       out_rel=o_rel, out_gc=o_gc)
+        _c, h_rel, h_gc = _composition.tnf_from_packed(codes, None, offsets, relative=True, device=local,
+                                                       out_rel=o_rel, out_gc=o_gc, runs=runs)
         torch.cuda.synchronize()
         e2e_times.append(time.perf_counter() - t0)
     e2e_p = float(np.sum(e2e_times))
@@ -755,7 +768,7 @@ def main():
     e2e_val = L_all * e2e_steps / e2e_p / 1e9
     assert np.array_equal(h_gc.view(np.uint32), d_gc.cpu().numpy().view(np.uint32))
     assert np.array_equal(h_rel.view(np.uint32), d_rel.cpu().numpy().view(np.uint32))
-    h2d = codes.nbytes + valid.nbytes + 8 * (n + 1)
+    h2d = codes.nbytes + runs.nbytes + 8 * (n + 1)
     d2h = n * 136 * 4 + n * 4
 
     if rank != 0:
@@ -794,9 +807,12 @@ def main():
                      "launches_timed": k_n.value, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step_min_median_max": [round(float(f(e2e_times)) * 1e3, 3) for f in (np.min, np.median, np.max)],
-                "api": "magpurify2_b200._composition.tnf_from_packed(out_rel=, out_gc=) -> mp2_tnf_packed: 2-bit codes + "
-                       "validity bits in pinned host memory in (0.375 B/base over PCIe), relative TNF + GC in pinned "
-                       "host memory out",
+                "api": "magpurify2_b200._composition.tnf_from_packed(runs=, out_rel=, out_gc=) -> mp2_tnf_packed: 2-bit codes "
+                       "in pinned host memory + the runs of invalid bases in (0.25 B/base over PCIe; the device rebuilds "
+                       "the validity mask), relative TNF + GC in pinned host memory out, rows of finished contigs copied "
+                       "back under the upload of the later slices",
+                "invalid_runs": {"count": int(len(runs)), "extract_ms": runs_s * 1e3},
+                "with_validity_mask_0.375_B_per_base": {"value": e2e_mask, "unit": UNIT},
                 "input": "the run's stream as the ingest leaves it: packed on the host by mp2_pack_host from the FASTA "
                          "reader's buffers, once per run, OUTSIDE the timed region (see host_pack); covers counts, TNF "
                          "and GC, not the CLR / log-ratio scores and not FASTA parsing",

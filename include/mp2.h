@@ -96,10 +96,17 @@ int64_t mp2_packed_words(int64_t n_bases, int64_t *valid_words); /* returns the 
 int mp2_pack_host(const uint8_t *const *parts, const int64_t *part_len, int64_t n_parts, uint32_t *codes,
                   uint32_t *valid, int threads);
 
-/* mp2_tnf on the packed host arrays: 0.375 bytes per base cross PCIe instead of 1 (offsets in bases, as above;
- * n_bases = offsets[n]).  Same outputs as mp2_tnf, any of them may be NULL. */
-int mp2_tnf_packed(const uint32_t *codes, const uint32_t *valid, const int64_t *offsets, int64_t n,
-                   int device, uint32_t *counts, float *rel, float *gc);
+/* Runs of invalid bases of a validity mask as ascending (begin, end) pairs -- a few thousand pairs for a real
+ * genome, where the mask itself is 0.125 bytes per base.  Returns the number of runs, -(needed) when `cap` pairs
+ * are too few, or MP2_EINVAL. */
+int64_t mp2_invalid_runs(const uint32_t *valid, int64_t n_bases, int64_t *runs, int64_t cap, int threads);
+
+/* mp2_tnf on the packed host arrays (offsets in bases, as above; n_bases = offsets[n]).  Give EITHER the validity
+ * mask (0.375 bytes per base cross PCIe in all) OR, with valid = NULL, the runs of invalid bases (0.25 bytes per
+ * base: the device rebuilds the mask).  The rows of finished contigs are copied back while later slices are still
+ * being uploaded.  Same outputs as mp2_tnf, any of them may be NULL. */
+int mp2_tnf_packed(const uint32_t *codes, const uint32_t *valid, const int64_t *invalid_runs, int64_t n_runs,
+                   const int64_t *offsets, int64_t n, int device, uint32_t *counts, float *rel, float *gc);
 
 /* ---- coverage: replaces the coverm arithmetic behind _coverage.get_bam_coverages ------- */
 /* (src/coverage.rs:99-142; coverm 0.3.2 contig_coverage / add_contig / calculate_coverage,

@@ -36,11 +36,11 @@ def _concat(seq_list):
     return bases, offsets
 
 
-def _out(shape, dtype):
+def _out(shape, dtype, small_too=False):
     """Result buffer: page-locked when it is large (the D2H copy of a pageable 160 MB array costs
     more than the kernels), plain NumPy otherwise.  torch is used as the pinned allocator only."""
     nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-    if nbytes >= (8 << 20):
+    if nbytes >= (8 << 20) or (small_too and nbytes > 0):
         try:
             import torch
 
@@ -110,16 +110,47 @@ def pack_parts(parts, threads=None):
     return codes, valid
 
 
-def tnf_from_packed(codes, valid, offsets, relative=True, want_gc=False, want_counts=False, device=-1,
-                    out_counts=None, out_rel=None, out_gc=None):
-    """tnf_from_concat on the 2-bit packed stream of pack_parts (offsets in bases)."""
-    codes = np.ascontiguousarray(codes, dtype=np.uint32)
+def invalid_runs(valid, n_bases, threads=None):
+    """int64[k, 2] (begin, end) runs of invalid bases of a validity mask -- what tnf_from_packed uploads instead of
+    the mask when it is the smaller of the two (it nearly always is: a genome is ACGT almost everywhere)."""
+    import os
+
     valid = np.ascontiguousarray(valid, dtype=np.uint32)
+    lib = _lib.load()
+    th = int(threads or os.cpu_count() or 1)
+    cap = 4096
+    while True:
+        runs = np.empty((cap, 2), dtype=np.int64)
+        k = lib.mp2_invalid_runs(_lib.ptr(valid), int(n_bases), _lib.ptr(runs), cap, th)
+        if k >= 0:
+            return runs[:k]
+        if k == _lib.EINVAL:
+            raise ValueError("mp2_invalid_runs: bad argument")
+        cap = -k
+
+
+def tnf_from_packed(codes, valid, offsets, relative=True, want_gc=False, want_counts=False, device=-1,
+                    out_counts=None, out_rel=None, out_gc=None, runs=None):
+    """tnf_from_concat on the 2-bit packed stream of pack_parts (offsets in bases).  `runs` (invalid_runs(valid))
+    is uploaded instead of the mask when given and smaller; pass valid=None to send only the runs."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint32)
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     n = len(offsets) - 1
     quads = (int(offsets[-1]) + 63) // 64 if n >= 0 and len(offsets) else 0
-    if len(codes) < 4 * quads or len(valid) < 2 * quads:
-        raise ValueError("codes / valid are shorter than offsets[-1] bases")
+    if valid is None and runs is None:
+        raise ValueError("give the validity mask, the runs of invalid bases, or both")
+    if valid is not None:
+        valid = np.ascontiguousarray(valid, dtype=np.uint32)
+        if len(valid) < 2 * quads:
+            raise ValueError("valid is shorter than offsets[-1] bases")
+    if runs is not None:
+        runs = np.ascontiguousarray(runs, dtype=np.int64).reshape(-1, 2)
+        if valid is not None and runs.nbytes >= 8 * quads:  # the mask is the smaller upload
+            runs = None
+        else:
+            valid = None
+    if len(codes) < 4 * quads:
+        raise ValueError("codes is shorter than offsets[-1] bases")
     counts = rel = gc = None
     if want_counts or not relative or out_counts is not None:
         counts = _check_out(out_counts, (n, NCANON), np.uint32, "out_counts") if out_counts is not None \
@@ -128,9 +159,9 @@ def tnf_from_packed(codes, valid, offsets, relative=True, want_gc=False, want_co
         rel = _check_out(out_rel, (n, NCANON), np.float32, "out_rel") if out_rel is not None \
             else _out((n, NCANON), np.float32)
     if want_gc or out_gc is not None:
-        gc = _check_out(out_gc, (n,), np.float32, "out_gc") if out_gc is not None else np.empty(n, dtype=np.float32)
-    _lib.check(_lib.load().mp2_tnf_packed(_lib.ptr(codes), _lib.ptr(valid), _lib.ptr(offsets), n, device,
-                                          _lib.ptr(counts), _lib.ptr(rel), _lib.ptr(gc)))
+        gc = _check_out(out_gc, (n,), np.float32, "out_gc") if out_gc is not None else _out((n,), np.float32, small_too=n > 4096)
+    _lib.check(_lib.load().mp2_tnf_packed(_lib.ptr(codes), _lib.ptr(valid), _lib.ptr(runs), 0 if runs is None else len(runs),
+                                          _lib.ptr(offsets), n, device, _lib.ptr(counts), _lib.ptr(rel), _lib.ptr(gc)))
     return counts, rel, gc
 
 

@@ -67,7 +67,8 @@ SIGNATURES = {
     "mp2_pack_device": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "mp2_packed_words": (_i64, [_i64, C.POINTER(_i64)]),
     "mp2_pack_host": (_i32, [_vp, _vp, _i64, _vp, _vp, _i32]),
-    "mp2_tnf_packed": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "mp2_invalid_runs": (_i64, [_vp, _i64, _vp, _i64, _i32]),
+    "mp2_tnf_packed": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
     "mp2_cov_events_device": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _u32, _u32, _u32, _f32, _f32, _vp, _i64, _vp, _vp]),
     "mp2_cov_order_device": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(_u32), C.POINTER(_u32), _vp]),
     "mp2_cov_events": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _u32, _u32, _u32, _f32, _f32, _i32, _vp, _i64, _vp]),

@@ -20,7 +20,9 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
                      unsigned long long *d_gc_counts, cudaStream_t stream);
 int64_t tnf_num_chunks(const void *d_bases, int64_t n_bases);
 int64_t tnf_chunks_ready(const void *d_bases, int64_t done, int64_t n_bases);
+int tnf_valid_from_runs(const int64_t *d_runs, int64_t n_runs, int64_t n_bases, uint32_t *d_valid, cudaStream_t stream);
 int64_t tnf_packed_num_chunks(int64_t n_bases);
+int64_t tnf_packed_bases_done(int64_t chunks, int64_t n_bases);
 int64_t tnf_packed_chunks_ready(int64_t done, int64_t n_bases);
 int tnf_packed_launch_range(const uint32_t *d_codes, const uint32_t *d_valid, const int64_t *d_offsets, int64_t n,
                             int64_t n_bases, int64_t chunk_begin, int64_t chunk_end, uint32_t *d_counts,
@@ -220,26 +222,40 @@ extern "C" int mp2_tnf(const uint8_t *bases, const int64_t *offsets, int64_t n, 
     return MP2_OK;
 }
 
-// Host-buffer form of the packed path: 0.375 bytes per base cross PCIe instead of 1.  The two arrays are
-// uploaded in slices of 64 Mbases (16 MB of codes + 8 MB of validity bits); the pieces wholly inside what has
-// been enqueued run behind the copy of the next slice.
-extern "C" int mp2_tnf_packed(const uint32_t *codes, const uint32_t *valid, const int64_t *offsets, int64_t n,
-                              int device, uint32_t *counts, float *rel, float *gc) {
-    if (n < 0) return fail(MP2_EINVAL, "negative n");
+// Host-buffer form of the packed path.  What crosses PCIe: the codes (0.25 bytes per base) and either the
+// validity mask (0.125 bytes per base) or, far smaller for real genomes, the runs of invalid bases from which
+// the device rebuilds the mask.  The codes are uploaded in slices of 64 Mbases; the pieces wholly inside what has
+// been enqueued run behind the copy of the next slice, and the rows of the contigs that are complete by then are
+// finalised and copied back on a third stream, so the device-to-host copy of the results runs under the upload.
+extern "C" int mp2_tnf_packed(const uint32_t *codes, const uint32_t *valid, const int64_t *invalid_runs, int64_t n_runs,
+                              const int64_t *offsets, int64_t n, int device, uint32_t *counts, float *rel, float *gc) {
+    if (n < 0 || n_runs < 0) return fail(MP2_EINVAL, "negative size");
     if (!offsets) return fail(MP2_EINVAL, "offsets is NULL");
     if (n > INT32_MAX) return fail(MP2_EINVAL, "too many sequences in one call");
     if (offsets[0] != 0) return fail(MP2_EINVAL, "offsets[0] must be 0");
     for (int64_t i = 0; i < n; i++)
         if (offsets[i + 1] < offsets[i]) return fail(MP2_EINVAL, "offsets must be non-decreasing");
     const int64_t total = offsets[n];
-    if (total > 0 && (!codes || !valid)) return fail(MP2_EINVAL, "codes / valid is NULL");
+    if (total > 0 && !codes) return fail(MP2_EINVAL, "codes is NULL");
+    if (total > 0 && !valid && !(invalid_runs || n_runs == 0)) return fail(MP2_EINVAL, "neither valid nor invalid_runs given");
+    if (!valid)
+        for (int64_t r = 0; r < n_runs; r++)
+            if (invalid_runs[2 * r] < 0 || invalid_runs[2 * r + 1] > total || invalid_runs[2 * r + 1] < invalid_runs[2 * r])
+                return fail(MP2_EINVAL, "invalid_runs[%lld] is not inside the stream", (long long)r);
     MP2_TRY(require_device(device));
     if (n == 0) return MP2_OK;
 
     Streams st;
     MP2_TRY(st.init());
+    cudaStream_t out = nullptr;
+    MP2_CUDA(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
+    struct OutGuard { cudaStream_t s; ~OutGuard() { if (s) cudaStreamDestroy(s); } } og{out};
+    cudaEvent_t rows_done = nullptr;
+    MP2_CUDA(cudaEventCreateWithFlags(&rows_done, cudaEventDisableTiming));
+    struct EvGuard { cudaEvent_t e; ~EvGuard() { if (e) cudaEventDestroy(e); } } eg{rows_done};
+
     const int64_t nq = (total + 63) / 64;
-    Temp d_codes, d_valid, d_off, d_counts, d_gcc, d_rel, d_gc;
+    Temp d_codes, d_valid, d_runs, d_off, d_counts, d_gcc, d_rel, d_gc;
     MP2_TRY(d_codes.alloc(sizeof(uint32_t) * 4 * (size_t)nq + 16, st.copy));
     MP2_TRY(d_valid.alloc(sizeof(uint32_t) * 2 * (size_t)nq + 16, st.copy));
     MP2_TRY(d_off.alloc(sizeof(int64_t) * (n + 1), st.copy));
@@ -250,14 +266,32 @@ extern "C" int mp2_tnf_packed(const uint32_t *codes, const uint32_t *valid, cons
     MP2_CUDA(cudaMemsetAsync(d_counts.p, 0, sizeof(uint32_t) * MP2_NCANON * n, st.comp));
     MP2_CUDA(cudaMemsetAsync(d_gcc.p, 0, sizeof(unsigned long long) * n, st.comp));
     MP2_TRY(upload(d_off.p, offsets, sizeof(int64_t) * (n + 1), st.copy));
+    if (valid) {
+        MP2_TRY(upload(d_valid.p, valid, sizeof(uint32_t) * 2 * (size_t)nq, st.copy));
+    } else {  // the whole mask before the first slice: a memset and a few thousand word updates
+        int64_t tail[2] = {total, nq * 64};
+        MP2_TRY(d_runs.alloc(sizeof(int64_t) * 2 * (size_t)(n_runs + 1), st.copy));
+        if (n_runs) MP2_TRY(upload(d_runs.p, invalid_runs, sizeof(int64_t) * 2 * (size_t)n_runs, st.copy));
+        MP2_CUDA(cudaMemcpyAsync(d_runs.as<int64_t>() + 2 * n_runs, tail, sizeof tail, cudaMemcpyHostToDevice, st.copy));
+        MP2_CUDA(cudaStreamSynchronize(st.copy));  // `tail` lives on this stack frame
+        MP2_TRY(tnf_valid_from_runs(d_runs.as<int64_t>(), n_runs + 1, total, d_valid.as<uint32_t>(), st.copy));
+    }
     const int64_t n_chunks = tnf_packed_num_chunks(total);
-    const int64_t QS = 1 << 20;  // quads per slice
-    int64_t next_chunk = 0;
+    const int64_t QS = 1 << 20;  // quads per slice (64 Mbases: 16 MB of codes)
+    int64_t next_chunk = 0, rows_out = 0;
+    // rows go home early only into page-locked outputs: a copy into pageable memory blocks this thread until the
+    // slice's kernels are done, which would serialise the upload behind the compute
+    const bool early_out = (!counts || is_pinned(counts)) && (!rel || is_pinned(rel)) && (!gc || is_pinned(gc));
+    const bool trace = getenv("MP2_TRACE") != nullptr;
+    const double t0 = omp_get_wtime();
+    auto stamp = [&](const char *what) {
+        if (trace) fprintf(stderr, "[mp2_tnf_packed] %-28s %8.2f ms\n", what, (omp_get_wtime() - t0) * 1e3);
+    };
     for (int64_t q0 = 0; q0 < nq; q0 += QS) {
         const int64_t q1 = std::min(nq, q0 + QS);
         MP2_TRY(upload(d_codes.as<uint32_t>() + 4 * q0, codes + 4 * q0, sizeof(uint32_t) * 4 * (size_t)(q1 - q0), st.copy));
-        MP2_TRY(upload(d_valid.as<uint32_t>() + 2 * q0, valid + 2 * q0, sizeof(uint32_t) * 2 * (size_t)(q1 - q0), st.copy));
-        const int64_t upto = q1 == nq ? n_chunks : tnf_packed_chunks_ready(q1 * 64, total);
+        const bool last = q1 == nq;
+        const int64_t upto = last ? n_chunks : tnf_packed_chunks_ready(q1 * 64, total);
         if (upto > next_chunk) {
             MP2_CUDA(cudaEventRecord(st.ev, st.copy));
             MP2_CUDA(cudaStreamWaitEvent(st.comp, st.ev, 0));
@@ -266,14 +300,29 @@ extern "C" int mp2_tnf_packed(const uint32_t *codes, const uint32_t *valid, cons
                                             st.comp));
             next_chunk = upto;
         }
+        // rows whose contig ends inside the pieces counted so far are final: normalise and send them home now
+        const int64_t done_bases = tnf_packed_bases_done(next_chunk, total);
+        int64_t rows_now = last ? n : early_out ? (int64_t)(std::upper_bound(offsets + 1, offsets + n + 1, done_bases) - (offsets + 1)) : 0;
+        if (rows_now > n) rows_now = n;
+        if (rows_now > rows_out) {
+            const int64_t r0 = rows_out, k = rows_now - rows_out;
+            MP2_TRY(tnf_finalize(d_counts.as<uint32_t>() + r0 * MP2_NCANON, d_gcc.as<unsigned long long>() + r0,
+                                 d_off.as<int64_t>() + r0, k, rel ? d_rel.as<float>() + r0 * MP2_NCANON : nullptr,
+                                 gc ? d_gc.as<float>() + r0 : nullptr, st.comp));
+            MP2_CUDA(cudaEventRecord(rows_done, st.comp));
+            MP2_CUDA(cudaStreamWaitEvent(out, rows_done, 0));
+            if (counts) MP2_TRY(download(counts + r0 * MP2_NCANON, d_counts.as<uint32_t>() + r0 * MP2_NCANON, sizeof(uint32_t) * MP2_NCANON * k, out));
+            if (rel) MP2_TRY(download(rel + r0 * MP2_NCANON, d_rel.as<float>() + r0 * MP2_NCANON, sizeof(float) * MP2_NCANON * k, out));
+            if (gc) MP2_TRY(download(gc + r0, d_gc.as<float>() + r0, sizeof(float) * k, out));
+            rows_out = rows_now;
+        }
     }
-    MP2_TRY(tnf_finalize(d_counts.as<uint32_t>(), d_gcc.as<unsigned long long>(), d_off.as<int64_t>(), n,
-                         d_rel.as<float>(), d_gc.as<float>(), st.comp));
-    if (counts) MP2_TRY(download(counts, d_counts.p, sizeof(uint32_t) * MP2_NCANON * n, st.comp));
-    if (rel) MP2_TRY(download(rel, d_rel.p, sizeof(float) * MP2_NCANON * n, st.comp));
-    if (gc) MP2_TRY(download(gc, d_gc.p, sizeof(float) * n, st.comp));
+    stamp("everything enqueued");
+    if (trace) { cudaStreamSynchronize(st.copy); stamp("copy stream done"); cudaStreamSynchronize(st.comp); stamp("compute stream done"); }
     MP2_CUDA(cudaStreamSynchronize(st.comp));
+    MP2_CUDA(cudaStreamSynchronize(out));
     MP2_CUDA(cudaStreamSynchronize(st.copy));
+    stamp("results on host");
     return MP2_OK;
 }
 

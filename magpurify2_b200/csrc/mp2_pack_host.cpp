@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "mp2.h"
 
@@ -125,4 +126,67 @@ extern "C" int mp2_pack_host(const uint8_t *const *parts, const int64_t *part_le
         }
     }
     return MP2_OK;
+}
+
+// Runs of invalid bases of a validity mask, as (begin, end) pairs in ascending order.  A genome is ACGT almost
+// everywhere, so the runs are a few thousand pairs where the mask is 0.125 bytes per base: the upload path sends
+// the codes and these pairs (0.25 bytes per base in all) and the device rebuilds the mask.  Bits beyond n_bases
+// do not count.  Returns the number of runs, or -(needed) when `cap` pairs are not enough (nothing is written
+// beyond cap), or MP2_EINVAL.
+extern "C" int64_t mp2_invalid_runs(const uint32_t *valid, int64_t n_bases, int64_t *runs, int64_t cap, int threads) {
+    if (n_bases < 0 || (n_bases > 0 && !valid) || cap < 0 || (cap > 0 && !runs)) return MP2_EINVAL;
+    const int64_t words = (n_bases + 31) / 32;
+    if (words == 0) return 0;
+    if (threads < 1) threads = 1;
+    const int64_t grain = 1 << 16;  // words per task (2 Mbases)
+    const int64_t tasks = (words + grain - 1) / grain;
+    std::vector<std::vector<int64_t>> local((size_t)tasks);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+    for (int64_t t = 0; t < tasks; t++) {
+        std::vector<int64_t> &out = local[(size_t)t];
+        const int64_t w0 = t * grain, w1 = std::min(words, w0 + grain);
+        int64_t open = -1;  // begin of the run being extended
+        for (int64_t w = w0; w < w1; w++) {
+            uint32_t v = valid[w];
+            const int64_t base = w * 32;
+            if (base + 32 > n_bases) v |= (n_bases - base >= 32) ? 0u : (0xFFFFFFFFu >> (n_bases - base));  // beyond the end: not a run
+            if (v == 0xFFFFFFFFu) {
+                if (open >= 0) { out.push_back(open); out.push_back(base); open = -1; }
+                continue;
+            }
+            uint32_t inv = ~v;  // first base = most significant bit
+            int pos = 0;
+            while (pos < 32) {
+                const uint32_t rest = inv << pos;  // bit 31 = base `pos`
+                if (open < 0) {
+                    if (rest == 0) break;
+                    const int z = __builtin_clz(rest);  // valid bases before the next invalid one
+                    pos += z;
+                    open = base + pos;
+                } else {
+                    const uint32_t ones = ~rest;  // bit 31 set <=> base `pos` valid
+                    if (ones == 0) { pos = 32; break; }  // the run continues through the word
+                    const int z = __builtin_clz(ones);     // invalid bases from pos on
+                    pos += z;
+                    if (pos < 32) { out.push_back(open); out.push_back(base + pos); open = -1; }
+                }
+            }
+        }
+        if (open >= 0) { out.push_back(open); out.push_back(std::min<int64_t>(w1 * 32, n_bases)); }
+    }
+    // concatenate, merging runs that touch across task (and word) boundaries
+    int64_t n = 0, last_end = -1;
+    for (int64_t t = 0; t < tasks; t++) {
+        const std::vector<int64_t> &v = local[(size_t)t];
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+            if (n > 0 && v[i] == last_end) {
+                if (n <= cap) runs[2 * (n - 1) + 1] = v[i + 1];
+            } else {
+                if (n < cap) { runs[2 * n] = v[i]; runs[2 * n + 1] = v[i + 1]; }
+                n++;
+            }
+            last_end = v[i + 1];
+        }
+    }
+    return n <= cap ? n : -n;
 }

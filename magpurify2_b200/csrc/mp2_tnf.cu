@@ -809,9 +809,46 @@ extern "C" int mp2_pack_device(const void *d_bases, int64_t n_bases, void *d_cod
 
 namespace mp2 {
 
+// valid mask from the runs of invalid bases (the mask was memset to all ones): one warp per run, interior words
+// are stored, the two edge words are and-ed.  First base of a word = most significant bit.
+__global__ void tnf_valid_runs_kernel(const int64_t *__restrict__ runs, int64_t n_runs, uint32_t *__restrict__ valid) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_runs) return;
+    const int64_t b = runs[2 * r], e = runs[2 * r + 1];
+    if (e <= b) return;
+    const int64_t w0 = b >> 5, w1 = (e - 1) >> 5;
+    for (int64_t w = w0 + lane; w <= w1; w += 32) {
+        const int lo = w == w0 ? (int)(b & 31) : 0, hi = w == w1 ? (int)((e - 1) & 31) + 1 : 32;  // bases [lo, hi) of word w
+        const uint32_t m = (hi - lo == 32) ? 0xFFFFFFFFu : (((1u << (hi - lo)) - 1u) << (32 - hi));
+        if (m == 0xFFFFFFFFu) valid[w] = 0u;
+        else atomicAnd(&valid[w], ~m);
+    }
+}
+
+// d_valid (2 words per quad of 64 bases) from `n_runs` (begin, end) pairs on the device; positions from n_bases to
+// the end of the last quad are invalid.
+int tnf_valid_from_runs(const int64_t *d_runs, int64_t n_runs, int64_t n_bases, uint32_t *d_valid, cudaStream_t stream) {
+    const int64_t nq = (n_bases + 63) / 64;
+    if (nq == 0) return MP2_OK;
+    MP2_CUDA(cudaMemsetAsync(d_valid, 0xFF, sizeof(uint32_t) * 2 * (size_t)nq, stream));
+    if (n_runs > 0) {
+        Launch L("tnf_valid_runs_kernel", stream);
+        tnf_valid_runs_kernel<<<(unsigned)((n_runs * 32 + 255) / 256), 256, 0, stream>>>(d_runs, n_runs, d_valid);
+    }
+    MP2_CUDA(cudaGetLastError());
+    return MP2_OK;
+}
+
 int64_t tnf_packed_num_chunks(int64_t n_bases) {
     const int ps = tnf_piece_shift(n_bases);
     return (n_bases + ((int64_t)1 << ps) - 1) >> ps;
+}
+
+// Bases covered by the first `chunks` pieces: every k-mer ending before that position has been counted.
+int64_t tnf_packed_bases_done(int64_t chunks, int64_t n_bases) {
+    const int64_t b = chunks << tnf_piece_shift(n_bases);
+    return b < n_bases ? b : n_bases;
 }
 
 // Pieces wholly inside the first `done` bases (host staging pipelines on this): a piece reads its own quads and

@@ -49,8 +49,9 @@ def composition_of(mags, device=-1, threads=None, packed=True):
         np.cumsum(np.concatenate([m.lengths for m in mags]), out=offsets[1:])
     if packed:
         codes, valid = _composition.pack_parts([m.bases for m in mags], threads=threads)
+        runs = _composition.invalid_runs(valid, int(offsets[-1]), threads=threads)
         counts, rel, gc = _composition.tnf_from_packed(codes, valid, offsets, relative=True, want_gc=True,
-                                                       want_counts=True, device=device)
+                                                       want_counts=True, device=device, runs=runs)
     else:
         bases = np.concatenate([m.bases for m in mags]) if mags else np.zeros(0, np.uint8)
         counts, rel, gc = _composition.tnf_from_concat(bases, offsets, relative=True, want_gc=True, want_counts=True,

@@ -86,6 +86,26 @@ def test_packed_host_path_matches_ascii_path_and_oracle(oracle):
     assert np.array_equal(g1, oracle.get_gc_concat(bases, offsets), equal_nan=True)
     with pytest.raises(ValueError):
         _composition.tnf_from_packed(codes[:8], valid, offsets)
+    # the runs of invalid bases instead of the mask (0.25 B/base): the device rebuilds the mask
+    runs = _composition.invalid_runs(valid, L, threads=3)
+    inv = ~np.isin(bases, np.frombuffer(b"ACGTacgt", dtype=np.uint8))
+    edge = np.diff(np.concatenate([[0], inv.astype(np.int8), [0]]))
+    assert np.array_equal(runs, np.stack([np.nonzero(edge == 1)[0], np.nonzero(edge == -1)[0]], axis=1))
+    c3, r3, g3 = _composition.tnf_from_packed(codes, None, offsets, relative=True, want_gc=True, want_counts=True, runs=runs)
+    assert np.array_equal(c3, c2) and np.array_equal(r3.view(np.uint32), r2.view(np.uint32)) and np.array_equal(g3, g2, equal_nan=True)
+    # a stream whose invalid bases are everywhere: long runs, runs at both ends, a tail that is not a whole quad
+    rng = np.random.default_rng(23)
+    b2 = bases[:1_000_037].copy()
+    off2 = np.concatenate([offsets[offsets < len(b2)], [len(b2)]])
+    b2[:100] = ord("N")
+    b2[-70:] = ord("n")
+    b2[500_000:640_000] = ord("N")
+    b2[rng.integers(0, len(b2), 20000)] = ord("R")
+    cd, vd = _composition.pack_parts([b2], threads=2)
+    want = oracle.get_tnf_concat(b2, off2, relative=False, threads=4)
+    for kw in (dict(valid=vd), dict(valid=None, runs=_composition.invalid_runs(vd, len(b2)))):
+        got, _r, gg = _composition.tnf_from_packed(cd, kw.pop("valid"), off2, relative=False, want_gc=True, **kw)
+        assert np.array_equal(got, want) and np.array_equal(gg, oracle.get_gc_concat(b2, off2), equal_nan=True)
 
 
 def _write_dataset(tmp, n_mags=4, n_samples=3, seed=9):
