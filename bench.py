@@ -547,6 +547,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: magpurify2_b200 has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from magpurify2_b200 import numa
+
+    placement = numa.bind_to_gpu_node(local) if world > 1 else {"device": local, "bound": False, "why": "single GPU"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -731,7 +734,7 @@ def main():
     assert np.array_equal(h_rel.view(np.uint32), d_rel.cpu().numpy().view(np.uint32))
     # ---- the product's upload path: the run's stream 2-bit packed on the host (once, when the genomes are read:
     # multi.composition_of -> pack_parts), then 0.375 B/base over PCIe.  Timed from the packed pinned buffers.
-    host_threads = max(1, (os.cpu_count() or 1) // max(1, world))
+    host_threads = max(1, min(len(os.sched_getaffinity(0)), (os.cpu_count() or 1) // max(1, world)))
     t0 = time.perf_counter()
     codes, valid = _composition.pack_parts([hb], threads=host_threads)
     pack_first_s = time.perf_counter() - t0  # includes page-locking the two output buffers
@@ -826,6 +829,8 @@ def main():
         "packed_2bit_path": packed,
         "gpu_launches": int(launches) + (cov_rec["gpu_launches"] if cov_rec else 0),
         "clocks": clocks,
+        "host": {"cpus": os.cpu_count(), "placement_rank0": placement,
+                 "topology": numa.topology_text() if world > 1 else ""},
     }
     if cov_rec:
         line["coverage"] = cov_rec

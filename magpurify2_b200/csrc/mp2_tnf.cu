@@ -47,6 +47,15 @@ template <int MODE> struct TnfTab {
     static constexpr int WORDS = T5W + 256;
 };
 
+#ifndef MP2_TNF_TMAZERO
+#define MP2_TNF_TMAZERO 1
+#endif
+// MODE 5 flush: the 4 KB 5-mer table is cleared by the bulk-copy engine (cp.async.bulk from a page of zeros in
+// L2) instead of 8 STS.128 per lane: the kernel is bound by the LSU data pipe (1 wavefront per clock), the copy
+// engine writes shared memory without going through it, and the copy runs while the warp folds the 4-mer sums
+// into the 136 classes and sends them to the contig's row.
+__device__ __align__(128) uint32_t g_zero_page[1024];
+
 __constant__ uint8_t c_lut256[256];             // code -> canonical class
 __constant__ uint16_t c_canon_pair[MP2_NCANON];  // class -> smallest code | revcomp code << 8
 
@@ -136,9 +145,14 @@ __global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_
 
 // Fold the warp's table into the contig's row: 256 codes -> 136 canonical classes, integer global
 // reductions, then zero the table.  MODE 4: T4 is the 4-mer table already.
+__device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__restrict__ row, uint32_t &phase);
+
 template <int MODE>
-__device__ __forceinline__ void tnf_flush(uint32_t *tab, int lane, uint32_t *__restrict__ row) {
-    static_assert(MODE == 4, "MODE 5 has its own flush");
+__device__ __forceinline__ void tnf_flush(uint32_t *tab, int lane, uint32_t *__restrict__ row, uint32_t &phase) {
+    if (MODE == 5) {
+        tnf_flush5(tab, lane, row, phase);
+        return;
+    }
     __syncwarp();
 #pragma unroll
     for (int k = lane; k < MP2_NCANON + 24; k += 32) {
@@ -168,7 +182,19 @@ __device__ __forceinline__ void tnf_flush(uint32_t *tab, int lane, uint32_t *__r
 // The two read orders leave the registers permuted by the lane number; two conditional-swap stages
 // bring the prefix sums into the order of the suffix sums, whose uint4 halves go back to the T4
 // region at the very address they came from.  The 136 classes are then gathered from T4.
-__device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__restrict__ row) {
+__shared__ __align__(8) unsigned long long tnf_bar;   // completion of the table's bulk clear (one warp per CTA)
+
+__device__ __forceinline__ void tnf_bar_init(int lane) {
+#if MP2_TNF_TMAZERO
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tnf_bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+#endif
+}
+
+__device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__restrict__ row, uint32_t &phase) {
     const uint4 *t5v = reinterpret_cast<const uint4 *>(tab);
     uint4 *t4v = reinterpret_cast<uint4 *>(tab + 1024);
     const int sg = lane & 7, hx = (lane >> 2) & 1;
@@ -196,8 +222,21 @@ __device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__
         t4v[2 * lane + h] = sum;  // only this lane touches these words
     }
     __syncwarp();  // every lane is done reading T5; the 4-mer counts are visible in T4
+#if MP2_TNF_TMAZERO
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tnf_bar);
+    if (lane == 0) {
+        // generic-proxy reads of T5 (above) before the async-proxy writes of the copy engine
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4096u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(tab)),
+                     "l"(g_zero_page), "r"(4096u), "r"(bar)
+                     : "memory");
+    }
+#else
 #pragma unroll
     for (int i = 0; i < 8; i++) *reinterpret_cast<uint4 *>(tab + (i * 32 + lane) * 4) = make_uint4(0, 0, 0, 0);
+#endif
 #pragma unroll
     for (int k = lane; k < MP2_NCANON + 24; k += 32) {
         if (k < MP2_NCANON) {
@@ -211,11 +250,22 @@ __device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__
     __syncwarp();
     t4v[lane] = make_uint4(0, 0, 0, 0);
     t4v[32 + lane] = make_uint4(0, 0, 0, 0);
+#if MP2_TNF_TMAZERO
+    {   // the table is clear when the copy has landed
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "TNF_WAIT:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra TNF_DONE;\n\t"
+            "bra TNF_WAIT;\n\t"
+            "TNF_DONE:\n\t}" ::"r"(bar), "r"(phase)
+            : "memory");
+        phase ^= 1u;
+    }
+#else
+    (void)phase;
+#endif
     __syncwarp();
-}
-template <>
-__device__ __forceinline__ void tnf_flush<5>(uint32_t *tab, int lane, uint32_t *__restrict__ row) {
-    tnf_flush5(tab, lane, row);
 }
 
 // Vector path of one group of 16 valid bases whose 3 halo bases are valid too: 8 (MODE 5) or 16
@@ -368,6 +418,8 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
     const int src_lane = (lane + 31) & 31;
 
     for (int i = lane; i < WORDS; i += 32) tab[i] = 0;
+    uint32_t zero_phase = 0;  // parity of the bulk-clear barrier's current phase
+    tnf_bar_init(lane);
     __syncwarp();
 
     for (;;) {
@@ -465,7 +517,7 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
             }
             gcl = __reduce_add_sync(0xffffffffu, gcl);
             if (lane == 0 && gcl) atomicAdd(&gc_counts[c], (unsigned long long)gcl);
-            tnf_flush<MODE>(tab, lane, counts + c * MP2_NCANON);
+            tnf_flush<MODE>(tab, lane, counts + c * MP2_NCANON, zero_phase);
         }
     }
 }
@@ -490,6 +542,8 @@ tnf_packed_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict
     const uint32_t t4 = t5 + 4u * TnfTab<MODE>::T5W;
     const int src_lane = (lane + 31) & 31;
     for (int i = lane; i < WORDS; i += 32) tab[i] = 0;
+    uint32_t zero_phase = 0;
+    tnf_bar_init(lane);
     __syncwarp();
 
     for (;;) {
@@ -563,7 +617,7 @@ tnf_packed_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict
             }
             gcl = __reduce_add_sync(0xffffffffu, gcl);
             if (lane == 0 && gcl) atomicAdd(&gc_counts[c], (unsigned long long)gcl);
-            tnf_flush<MODE>(tab, lane, counts + c * MP2_NCANON);
+            tnf_flush<MODE>(tab, lane, counts + c * MP2_NCANON, zero_phase);
         }
     }
 }

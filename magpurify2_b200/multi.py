@@ -39,6 +39,15 @@ def shard_mags(mags, n_parts):
     return sharding.lpt_partition([int(m.offsets[-1]) for m in mags], n_parts)
 
 
+def _bound(fn, device, *a, **k):
+    """Runs fn on a worker thread that first moves to the CPUs of the device's NUMA node (numa.bind_to_gpu_node)."""
+    from . import numa
+
+    if device is not None and device >= 0:
+        numa.bind_to_gpu_node(device)
+    return fn(*a, **k)
+
+
 def composition_of(mags, device=-1, threads=None, packed=True):
     """counts, relative TNF, GC and the two scores of every contig of `mags` (stacked in order) on ONE device.
     The genomes are 2-bit packed on the host straight from the buffers the FASTA reader filled (no ASCII
@@ -71,7 +80,7 @@ def composition_on_devices(mags, devices, threads=None):
     parts = shard_mags(mags, len(devices))
     per = max(1, threads // len(devices))  # host threads of every shard's packer
     with ThreadPoolExecutor(max_workers=len(devices)) as pool:
-        futs = [pool.submit(composition_of, [mags[i] for i in part.tolist()], dev, per) if len(part) else None
+        futs = [pool.submit(_bound, composition_of, dev, [mags[i] for i in part.tolist()], dev, per) if len(part) else None
                 for part, dev in zip(parts, devices)]
         shards = [f.result() if f is not None else None for f in futs]
     return gather_shards(mags, parts, shards)
