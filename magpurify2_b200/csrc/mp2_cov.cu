@@ -1604,10 +1604,21 @@ __device__ __forceinline__ void smem_add_if(uint32_t saddr, int v, bool cond) {
                  : "memory");
 }
 
-// contig cursor (see c3_seek) found by galloping from contig c0, which is at or before the event's contig
+// contig cursor (see c3_seek) of event e_abs, which belongs to contig c0 or a later one.  Nearly always it is
+// the NEXT contig that has events, so the four numbers of contigs c0+1 / c0+2 are fetched at once (one memory
+// latency instead of a chain of five dependent loads: a seek happens at every contig boundary of the event
+// stream, and the warp does nothing else while it waits); anything else gallops on from there.
 __device__ __noinline__ int4 c4_seek(const int64_t *__restrict__ ev_off, const int64_t *__restrict__ off, int c0, int64_t n,
                                      int64_t e_abs, int64_t e_base, int64_t run_lo) {
-    int64_t lo = c0, step = 1;
+    int64_t lo = c0;
+    if (lo + 2 <= n) {
+        const int64_t e1 = __ldg(ev_off + lo + 1), e2 = __ldg(ev_off + lo + 2);
+        const int64_t o1 = __ldg(off + lo + 1), o2 = __ldg(off + lo + 2);
+        if (e1 <= e_abs && e_abs < e2)
+            return make_int4((int)(lo + 1), clamp_rel(e2 - e_base), clamp_rel(o1 - run_lo), (int)(o2 - o1));
+        if (e1 <= e_abs) lo += 2;  // e2 <= e_abs as well
+    }
+    int64_t step = 1;
     while (lo + step < n && ev_off[lo + step] <= e_abs) { lo += step; step <<= 1; }
     const int64_t hi = lo + step < n ? lo + step : n;
     const int64_t c = last_le(ev_off, lo, hi, e_abs);
