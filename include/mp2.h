@@ -145,9 +145,9 @@ typedef struct {
  *           path (difference array in HBM, any order, any span).
  *           max_span = 0 = nothing is known: both numbers are measured on the device first (three small
  *           kernels, one extra pass over the events) and the path is chosen from them.
- * The call returns after the sample's kernels were enqueued AND the 4-byte "fall back" flag of the fast
- * path was read (one stream synchronisation): the general path's scratch (4 bytes per position) is only
- * allocated when it is needed.
+ * The call only enqueues work (the fallback is enqueued behind the fast path, gated on a device flag) unless
+ * the fallback's scratch -- 4 bytes per position -- would take more than a quarter of the device's memory: then
+ * the flag is read back first (one stream synchronisation) and the scratch is only allocated when it is needed.
  * Contigs that reach depth >= 511 are counted in a pool of global histograms (2048 contigs per call, depth
  * < 4607); a sample that needs more goes through the general path (exact for any depth).
  * trim_lower + trim_upper must be < 1 (the CLI clamps both, magpurify2/modules/coverage.py:39-49). */

@@ -254,9 +254,11 @@ struct PinVec {
     PinBlock blk{nullptr, 0, false};
     size_t n = 0;
     uint32_t *data() { return (uint32_t *)blk.p; }
-    bool reserve(size_t want, int threads) {
+    // `expect` = how many elements the array will probably hold in the end (0 = unknown): page-locking is the
+    // expensive part, so the first block is taken at that size and growth is the exception
+    bool reserve(size_t want, int threads, size_t expect = 0) {
         if (want * 4 <= blk.bytes) return true;
-        size_t cap = std::max(want * 4, blk.bytes + blk.bytes / 2);
+        size_t cap = std::max(std::max(want, expect) * 4, blk.bytes + blk.bytes / 2);
         PinBlock nb = pin_get(cap);
         if (!nb.p) return false;
         if (n) {
@@ -332,6 +334,8 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
         const long kb = atol(e);
         if (kb > 0) BATCH = (int64_t)kb << 10;
     }
+    int64_t total_usize = 0, done_usize = 0;  // uncompressed bytes of the file / inflated so far
+    for (const Block &blk : blocks) total_usize += blk.usize;
     size_t bi = 0;
     int64_t have = 0;   // valid bytes in buf
     bool header_done = false;
@@ -363,6 +367,7 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
         const bool last_batch = bj == blocks.size();
         bi = bj;
         have += add;
+        done_usize += add;
         const uint8_t *p = buf.data();
         int64_t o = 0;
         // ---- header ----
@@ -471,7 +476,10 @@ extern "C" int mp2_bam_open(const char *path, float min_identity, int threads, m
             }
             ev_pos[nr] = pos;
             b->n_records += nr;
-            if (!ev_s.reserve((size_t)pos, threads) || !ev_e.reserve((size_t)pos, threads))
+            // blocks per uncompressed byte so far, extrapolated to the whole file (+ 6 %)
+            const double seen = (double)(done_usize - (have - o));
+            const size_t expect = seen > 0 ? (size_t)((double)pos * ((double)total_usize / seen) * 1.06) + 1024 : 0;
+            if (!ev_s.reserve((size_t)pos, threads, expect) || !ev_e.reserve((size_t)pos, threads, expect))
                 return fail(MP2_ENOMEM, "%s: out of host memory for %lld alignment blocks", path, (long long)pos);
             ev_s.n = ev_e.n = (size_t)pos;
         }

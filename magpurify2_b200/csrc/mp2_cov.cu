@@ -2001,8 +2001,8 @@ static int cov_fast_version() {
 
 static int cov_general_path(const uint32_t *starts, const uint32_t *ends, const int64_t *ev_off, const int64_t *off,
                             int64_t n_contigs, int64_t n_events, int64_t n_pos, const int32_t *ev_first,
-                            const TrimParams &tp, int *ctrs, float *d_cov, int64_t cov_stride, mp2_cov_stats *d_stats,
-                            cudaStream_t stream);
+                            const TrimParams &tp, int *ctrs, const int *gate, float *d_cov, int64_t cov_stride,
+                            mp2_cov_stats *d_stats, cudaStream_t stream);
 
 extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, const void *d_ev_off,
                                      const void *d_contig_off, int64_t n_contigs, int64_t n_events,
@@ -2148,15 +2148,26 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
             cov_stream2_kernel<<<(unsigned)grid, 32, 0, stream>>>(t);
         }
         MP2_CUDA(cudaGetLastError());
-        // The general path needs 4 bytes per position of scratch (12 GB at C3): it is only allocated when the
-        // gate says the sample has to be redone, which costs one 4-byte read of the gate here.
+        // The general path needs 4 bytes per position of scratch (12 GB at C3, 120 GB for a 30 Gbp sample).
+        //  * scratch that is small next to the device (<= a quarter of its memory): the fallback is enqueued right
+        //    behind the fast path with every kernel gated on the flag (they exit at once when it is clear) -- the
+        //    call stays asynchronous and the host keeps running ahead of the device;
+        //  * larger: the flag is read back first (one stream synchronisation) and the scratch is only allocated
+        //    when the sample really has to be redone.
+        size_t free_b = 0, total_b = 0;
+        MP2_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t scratch = sizeof(int32_t) * (size_t)(n_pos + 4) +
+                               sizeof(uint32_t) * COV_BINS * (size_t)((n_pos + COV_TILE - 1) / COV_TILE);
+        if (scratch <= total_b / 4)
+            return cov_general_path(starts, ends, ev_off, off, n_contigs, n_events, n_pos, ev_first.as<int32_t>(), tp,
+                                    ctrs.as<int>(), gate, (float *)d_cov, cov_stride, (mp2_cov_stats *)d_stats, stream);
         int h_gate = 0;
         MP2_CUDA(cudaMemcpyAsync(&h_gate, gate, sizeof(int), cudaMemcpyDeviceToHost, stream));
         MP2_CUDA(cudaStreamSynchronize(stream));
         if (!h_gate) return MP2_OK;
     }
     return cov_general_path(starts, ends, ev_off, off, n_contigs, n_events, n_pos, ev_first.as<int32_t>(), tp,
-                            ctrs.as<int>(), (float *)d_cov, cov_stride, (mp2_cov_stats *)d_stats, stream);
+                            ctrs.as<int>(), nullptr, (float *)d_cov, cov_stride, (mp2_cov_stats *)d_stats, stream);
 }
 
 // The two numbers mp2_cov_events_device can be vouched for with, measured exactly on the device: what a producer
@@ -2204,11 +2215,11 @@ extern "C" int mp2_cov_order_device(const void *d_starts, const void *d_ends, co
 // ---------------- general path: difference array in HBM (any order, any span, any depth) ----------------
 static int cov_general_path(const uint32_t *starts, const uint32_t *ends, const int64_t *ev_off, const int64_t *off,
                             int64_t n_contigs, int64_t n_events, int64_t n_pos, const int32_t *ev_first,
-                            const TrimParams &tp, int *ctrs, float *d_cov, int64_t cov_stride, mp2_cov_stats *d_stats,
-                            cudaStream_t stream) {
+                            const TrimParams &tp, int *ctrs, const int *gate, float *d_cov, int64_t cov_stride,
+                            mp2_cov_stats *d_stats, cudaStream_t stream) {
     const int64_t n_ev_tiles = (n_events + COV_EV_TILE - 1) / COV_EV_TILE;
     const int64_t n_tiles = (n_pos + COV_TILE - 1) / COV_TILE;
-    const int *g = nullptr;  // the kernels below are not gated any more: this function only runs when needed
+    const int *g = gate;  // NULL = run; else every kernel below exits at once unless *gate != 0
     Temp D, tile_sum, tile_pre, first, rows, meta, deep_list;
     MP2_TRY(D.alloc(sizeof(int32_t) * (size_t)(n_pos + 4), stream));
     MP2_TRY(tile_sum.alloc(sizeof(int32_t) * n_tiles, stream));

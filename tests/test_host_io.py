@@ -242,3 +242,46 @@ def test_host_packer_matches_the_layout_definition():
     codes, valid = _composition.pack_parts([big[:1_000_003], big[1_000_003:]], threads=4)
     want_c, want_v = _pack_reference(big)
     assert np.array_equal(codes, want_c) and np.array_equal(valid, want_v)
+
+
+def test_get_bam_coverages_propagates_decode_errors_without_hanging(tmp_path):
+    """The decoder thread runs ahead of the device threads: a file that cannot be decoded (no NM tag: the reference
+    panics there) or whose @SQ lines differ must surface as the call's exception, not as a stuck pipeline.  Both
+    fail on the host, before any GPU work."""
+    from magpurify2_b200 import _coverage
+
+    names, lengths = ["a", "b"], [5000, 6000]
+    bad = tmp_path / "no_nm.bam"
+    bamio.write_bam(str(bad), names, lengths, [dict(tid=0, pos=10, cigar=[("M", 100)], nm=None)])
+    with pytest.raises(_lib.Mp2Error):
+        _coverage.get_bam_coverages([str(bad)], threads=2)
+    ok = tmp_path / "ok.bam"
+    bamio.write_bam(str(ok), names, lengths, [dict(tid=0, pos=10, cigar=[("M", 100)], nm=0)])
+    with pytest.raises(_lib.Mp2Error):  # the good file first: its device thread fails on the CPU box, or runs on a GPU box
+        _coverage.get_bam_coverages([str(ok), str(bad), str(ok)], threads=2, devices=[0, 0])
+    with pytest.raises((FileNotFoundError, OSError)):
+        _coverage.get_bam_coverages([str(tmp_path / "missing.bam")])
+
+
+def test_bam_reader_reports_block_span_and_disorder(tmp_path, oracle):
+    """max_block / max_disorder: what get_bam_coverages vouches for; the CG:B,I tag of a read with a placeholder CIGAR."""
+    import struct
+
+    names, lengths = ["c0"], [100000]
+    real = [("M", 40), ("D", 7), ("M", 50), ("N", 200), ("M", 60)]
+    packed = [(ln << 4) | bamio.CIGAR_OPS.index(op) for op, ln in real]
+    cg = b"CGBI" + struct.pack("<I", len(packed)) + b"".join(struct.pack("<I", c) for c in packed)
+    recs = [
+        dict(tid=0, pos=100, cigar=[("M", 150)], nm=0),
+        dict(tid=0, pos=120, cigar=[("M", 30), ("D", 2), ("M", 120)], nm=2),       # second block starts at 152
+        dict(tid=0, pos=130, cigar=[("S", 150), ("N", 357)], nm=0, seq_len=150, extra_aux=cg),  # placeholder + CG tag
+        dict(tid=0, pos=140, cigar=[("M", 150)], nm=0),
+    ]
+    path = tmp_path / "cg.bam"
+    bamio.write_bam(str(path), names, lengths, recs)
+    with _bam.BamEvents(path, 0.0, threads=2) as b:
+        got = list(zip(b.starts.tolist(), b.ends.tolist()))
+        assert got == [(100, 250), (120, 150), (152, 272), (130, 170), (177, 227), (427, 487), (140, 290)]
+        assert b.max_block == 150
+        assert b.max_disorder == 427 - 130          # the last block of the spliced read starts 297 after its position
+        assert b.max_span == 487 - 130
