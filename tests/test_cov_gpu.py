@@ -317,3 +317,67 @@ def test_sparse_and_empty_contigs(covmod, oracle):
     st = st[order].astype(np.uint32)
     en = (st + 150).astype(np.uint32)
     check_sample(covmod, oracle, st, en, ev_off, lengths, 75, 0.05, 0.05)
+
+
+def _random_sample(rng, n_contigs, len_lo, len_hi, depth, read_len, jitter, indel_frac, gap_hi):
+    """Reads sorted by position; `indel_frac` of them split into two blocks with a reference gap of 0..gap_hi."""
+    lengths = rng.integers(len_lo, len_hi, n_contigs).astype(np.int64)
+    lengths[rng.random(n_contigs) < 0.1] = rng.integers(0, 160, int((rng.random(n_contigs) < 0.1).sum()) or 1)[0]
+    starts, ends, ev_off = [], [], [0]
+    for ln in lengths.tolist():
+        n = int(rng.poisson(depth * max(ln - read_len, 0) / read_len)) if ln > read_len + 5 else 0
+        pos = np.sort(rng.integers(0, max(1, ln - read_len), n))
+        rl = np.clip(read_len + rng.integers(-jitter, jitter + 1, n), 20, None)
+        two = rng.random(n) < indel_frac
+        a = (rl * rng.uniform(0.2, 0.8, n)).astype(np.int64)
+        gap = rng.integers(0, gap_hi + 1, n)
+        for p, r, t, aa, g in zip(pos.tolist(), rl.tolist(), two.tolist(), a.tolist(), gap.tolist()):
+            if t:
+                starts += [p, p + aa + g]
+                ends += [p + aa, min(p + g + r, ln)]
+            else:
+                starts.append(p)
+                ends.append(min(p + r, ln))
+        ev_off.append(len(starts))
+    st, en = np.array(starts, dtype=np.uint32), np.array(ends, dtype=np.uint32)
+    keep = en > st  # the generator may produce an empty second block at a contig end: keep it, every path drops it
+    return st, en, np.array(ev_off, dtype=np.int64), lengths, keep
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_fuzz_shapes_depths_and_disorder(covmod, oracle, case):
+    """Random shapes around every limit of the streaming kernel: contigs spanning several 65 536-slot runs, tiny and
+    empty contigs, depths beyond the 511-bin shared histogram (deep pool) with out-of-order blocks, block span +
+    disorder just inside and just outside the 512-slot overflow region (the latter must come back from the general
+    path), vouched and measured."""
+    rng = np.random.default_rng(1000 + case)
+    shapes = [
+        dict(n_contigs=40, len_lo=200, len_hi=30000, depth=20, read_len=150, jitter=20, indel_frac=0.1, gap_hi=5),
+        dict(n_contigs=6, len_lo=100000, len_hi=400000, depth=8, read_len=150, jitter=30, indel_frac=0.2, gap_hi=60),
+        dict(n_contigs=30, len_lo=1000, len_hi=9000, depth=700, read_len=150, jitter=10, indel_frac=0.05, gap_hi=3),   # deep pool
+        dict(n_contigs=200, len_lo=1, len_hi=900, depth=5, read_len=100, jitter=40, indel_frac=0.3, gap_hi=10),        # tiny contigs
+        dict(n_contigs=20, len_lo=5000, len_hi=60000, depth=15, read_len=250, jitter=0, indel_frac=0.3, gap_hi=5),     # 250 + ~200: inside
+        dict(n_contigs=20, len_lo=5000, len_hi=60000, depth=15, read_len=250, jitter=0, indel_frac=0.3, gap_hi=300),   # beyond 512: general
+        dict(n_contigs=10, len_lo=70000, len_hi=140000, depth=40, read_len=100, jitter=50, indel_frac=0.5, gap_hi=200),
+        dict(n_contigs=3, len_lo=300000, len_hi=700000, depth=3, read_len=60, jitter=30, indel_frac=0.0, gap_hi=0),
+        dict(n_contigs=50, len_lo=151, len_hi=400, depth=30, read_len=60, jitter=20, indel_frac=0.2, gap_hi=20),       # windows of a few slots
+        dict(n_contigs=6, len_lo=2000, len_hi=8000, depth=5000, read_len=150, jitter=0, indel_frac=0.0, gap_hi=0),     # beyond the deep pool's range
+        dict(n_contigs=25, len_lo=3000, len_hi=50000, depth=60, read_len=200, jitter=60, indel_frac=0.4, gap_hi=40),
+        dict(n_contigs=8, len_lo=65000, len_hi=66500, depth=25, read_len=150, jitter=15, indel_frac=0.1, gap_hi=8),    # contig ends near run boundaries
+    ]
+    st, en, ev_off, lengths, _keep = _random_sample(rng, **shapes[case])
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    wcov, wst = oracle.cov_sample(st, en, ev_off, lengths, 75, 0.05, 0.05, threads=8)
+    span = int((en.astype(np.int64) - st.astype(np.int64)).clip(0).max()) if len(st) else 0
+    dis = _disorder(st, ev_off, lengths)
+    for kw in ({}, dict(max_span=max(span, 1), max_disorder=dis)):
+        cov, stats = covmod.cov_from_events(st, en, ev_off, off, 75, 0.05, 0.05, want_stats=True, **kw)
+        for f in INT_FIELDS:
+            bad = np.nonzero(stats[f] != wst[f])[0]
+            assert bad.size == 0, (case, kw, f, bad[:5], stats[f][bad[:5]], wst[f][bad[:5]])
+        assert np.array_equal(cov.view(np.uint32), wcov.view(np.uint32)), (case, kw)
+        general = bool((stats["flags"] & GENERAL).any())
+        if case == 5:
+            assert general, "span + disorder beyond the overflow region must take the general path"
+        elif case not in (2, 9):  # very deep samples may (9: must) overflow the deep pool
+            assert not general, (case, kw, span, dis)
