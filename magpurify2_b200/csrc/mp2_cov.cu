@@ -1575,6 +1575,13 @@ struct __align__(1024) C4Smem {
     uint32_t ring_e[C4_RING];
 };
 static_assert(sizeof(uint32_t) * COV_BINS == 2048 && (1024 + offsetof(C4Smem, hist)) % 2048 == 0, "histogram alignment");
+// Shared-window address of the histogram: the window of a CTA starts with 1 KB the system reserves and C4Smem is the
+// kernel's only shared object.  Known at compile time, it is the immediate of the histogram's red.shared, so the
+// position walk runs on plain bin OFFSETS (checked against the real address when the kernel starts).
+constexpr uint32_t C4_HIST_ADDR = 1024 + (uint32_t)offsetof(C4Smem, hist);
+__device__ __forceinline__ void c4_hist_inc(uint32_t byte_off) {
+    asm volatile("red.shared.add.u32 [%0+%1], 1;" ::"r"(byte_off), "n"(C4_HIST_ADDR) : "memory");
+}
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
     uint32_t v;
@@ -1626,14 +1633,43 @@ __device__ __noinline__ int4 c4_seek(const int64_t *__restrict__ ev_off, const i
     return make_int4((int)c, clamp_rel(ev_off[c + 1] - e_base), clamp_rel(o0 - run_lo), (int)(off[c + 1] - o0));
 }
 
-// 16 positions that are not all inside the contig window, or that reach the last bin: exact, one by one.
-// chunk = 4 * differences, d4_before = 4 * depth just before the chunk, m = positions inside the window.
-// Returns the largest depth among them.
+// ---- depths outside the warp's 511 bins -----------------------------------------------------------------------
+// The shared histogram covers the depths [base, base + 511) of the contig being walked; `base` starts at 0 and
+// FOLLOWS the contig's depth (c4_rebase), so an organism at 700x is histogrammed in shared memory like one at 20x.
+// Everything else -- positions outside the current range, and the bins of a range that was left -- is counted at
+// its ABSOLUTE depth in the contig's row of the deep pool (claimed on first use; CT_DEEP_BINS depths).  A contig's
+// histogram is then pool[d] + (d in range ? shared[d - base] : 0).  Round 1 (and the first version of this kernel)
+// kept base = 0 and sent every position at depth >= 511 to the pool with a global atomic of its own: exact, but a
+// sample with a few very abundant organisms ran 20 % slower than its neighbours (C4 on 8 GPUs).
+constexpr int C4_RANGE = COV_BINS - 1;  // bins 0 .. 510 are depths base .. base + 510
+
+// row of the deep pool for contig c (claimed if need be), by ONE lane; -3 = pool exhausted
+__device__ __forceinline__ int c4_claim_row(const TileArgs &a, int64_t c) {
+    int r = atomicAdd(&a.deep_row_of[c], 0);
+    if (r == -1) {
+        const int old = atomicCAS(&a.deep_row_of[c], -1, -2);
+        if (old == -1) {
+            const int k2 = atomicAdd(a.deep_rows_used, 1);
+            r = k2 < CT_DEEP_ROWS ? k2 : -3;
+            atomicExch(&a.deep_row_of[c], r);
+        } else {
+            r = old;
+        }
+    }
+    while (r == -2) r = atomicAdd(&a.deep_row_of[c], 0);
+    return r;
+}
+
+// 16 positions that are not all inside the contig window, or not all inside the histogram's depth range: exact,
+// one by one.  chunk = 4 * differences, d4_before = 4 * (absolute) depth just before the chunk, m = positions
+// inside the window.  Called by any subset of the lanes.  Returns the largest depth among the positions that went to
+// the POOL (-1: none did; the largest depth inside the shared bins is read off the bins when the contig closes).
 __device__ __noinline__ int c4_slow_chunk(const TileArgs &a, int64_t c, const int32_t *chunk, int d4_before, uint32_t m,
-                                          uint32_t *hist) {
+                                          int base, uint32_t *hist) {
+    const int lane = threadIdx.x & 31;
     int dd[COV_ITEMS];
-    int run = d4_before, mx = 0;
-    bool deep = false;
+    int run = d4_before, mx = -1;
+    uint32_t out = 0;  // positions whose depth is outside [base, base + 511)
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         run += chunk[i];
@@ -1641,27 +1677,146 @@ __device__ __noinline__ int c4_slow_chunk(const TileArgs &a, int64_t c, const in
         d = d < 0 ? 0 : d;
         dd[i] = d;
         if (m & (1u << i)) {
-            mx = d > mx ? d : mx;
-            if (d < COV_BINS - 1) atomicAdd(&hist[d], 1u);
-            else deep = true;
+            if ((unsigned)(d - base) < (unsigned)C4_RANGE) {
+                atomicAdd(&hist[d - base], 1u);
+            } else {
+                out |= 1u << i;
+                mx = d > mx ? d : mx;
+            }
         }
     }
-    if (deep) ct_deep_positions(a, c, dd, m);
+    if (out) {
+        const unsigned grp = __activemask();
+        const int leader = __ffs(grp) - 1;
+        int r = 0;
+        if (lane == leader) r = c4_claim_row(a, c);
+        r = __shfl_sync(grp, r, leader);
+        if (r >= 0) {
+            uint32_t *dr = a.deep_pool + (size_t)r * CT_DEEP_BINS;
+            for (int k = 0; k < COV_ITEMS; k++)
+                if ((out & (1u << k)) && dd[k] < CT_DEEP_BINS) atomicAdd(&dr[dd[k]], 1u);  // deeper: the finish gates
+            __threadfence();
+        }
+    }
     return mx;
 }
 
-// The window of contig c is complete (or the run ends): the highest occupied bin is read off the histogram.
-__device__ __noinline__ void c4_close_window(const TileArgs &a, int64_t c, bool local, int deep_max, int in_run,
-                                             uint32_t *s_hist) {
+// Empties the shared histogram (range [base, base + 511)) into the pool at the bins' absolute depths, so that the
+// caller can give it another range.  Whole warp.  Returns the largest depth that has left shared memory so far
+// (warp-uniform; arguments and result by value: references would live on the stack).
+__device__ __noinline__ int c4_rebase(const TileArgs &a, int64_t c, uint32_t *hist, int base, int deep_max) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
-    int top = 0;
+    uint32_t v[COV_BINS / 32];
+    int top = -1;
+#pragma unroll
+    for (int j = 0; j < COV_BINS / 32; j++) {
+        v[j] = hist[lane + 32 * j];
+        if (v[j]) top = lane + 32 * j;
+    }
+    top = __reduce_max_sync(0xffffffffu, top);
+    deep_max = __reduce_max_sync(0xffffffffu, deep_max);
+    if (top >= 0) {
+        int r = 0;
+        if (lane == 0) r = c4_claim_row(a, c);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= 0) {
+            uint32_t *dr = a.deep_pool + (size_t)r * CT_DEEP_BINS;
+#pragma unroll
+            for (int j = 0; j < COV_BINS / 32; j++) {
+                const int d = base + lane + 32 * j;
+                if (v[j] && d < CT_DEEP_BINS) atomicAdd(&dr[d], v[j]);
+            }
+            __threadfence();
+        }
+        deep_max = base + top > deep_max ? base + top : deep_max;
+#pragma unroll
+        for (int j = 0; j < COV_BINS / 32; j++)
+            if (v[j]) hist[lane + 32 * j] = 0;
+    }
+    __syncwarp();
+    return deep_max;
+}
+
+// Trimmed mean of contig c from `local(d)` (this warp's shared bins or the contig's global row) + its pool row.
+// use_pool: somebody counted positions of this contig in the pool (otherwise its row is not even looked up).
+template <class Local>
+__device__ __forceinline__ void c4_finish(const TileArgs &a, int64_t c, uint64_t N, uint32_t maxd, bool use_pool, Local local) {
+    const int lane = threadIdx.x & 31;
+    const int r = use_pool ? *((volatile int32_t *)&a.deep_row_of[c]) : -1;
+    if (maxd >= (uint32_t)CT_DEEP_BINS || r == -3 || r == -2) {  // beyond the pool's range / pool exhausted
+        if (lane == 0) {
+            a.deep_list[atomicAdd(a.deep_count, 1)] = (int32_t)c;
+            *a.gate_out = 1;  // the exact general path redoes this sample
+        }
+        return;
+    }
+    const uint32_t *deep = r >= 0 ? a.deep_pool + (size_t)r * CT_DEEP_BINS : nullptr;
+    auto cnt = [&](uint32_t d) { return local(d) + (deep ? __ldcg(deep + d) : 0u); };
+    uint64_t mn, mx;
+    trim_indices(N, a.tp, mn, mx);
+    const uint64_t covered = N - (uint64_t)cnt(0);
+    unsigned long long acc = 0, total = 0;
+    if (covered) trim_walk_warp(cnt, 0, maxd + 1, mn, mx, acc, total);
+    if (lane == 0) write_result(c, N, covered, mn, mx, total, maxd, 0, a.cov, a.cov_stride, a.stats);
+}
+
+// The window of contig c is complete (or the run ends).  Inside this run: finish from the warp's bins (+ pool).
+// Otherwise: bring the bins back to base 0 semantics (what is not in [0, 511) goes to the pool), merge them into the
+// row of the run the window started in; the last contributor finishes from that row (+ pool).
+__device__ __noinline__ void c4_close_window(const TileArgs &a, int64_t c, bool local, int deep_max, int in_run, int base,
+                                             uint32_t *s_hist) {
+    const int lane = threadIdx.x & 31;
+    const int64_t excl = a.tp.excl;
+    const int64_t o0g = a.off[c], o1g = a.off[c + 1];
+    const uint64_t N = (uint64_t)(o1g - o0g - 2 * excl);
+    __syncwarp();
+    if (!local && base != 0) {
+        deep_max = c4_rebase(a, c, s_hist, base, deep_max);
+        base = 0;
+    }
+    int top = -1;
 #pragma unroll
     for (int j = 0; j < COV_BINS / 32; j++)  // lane + 32 j: conflict-free
         if (s_hist[lane + 32 * j]) top = lane + 32 * j;
     top = __reduce_max_sync(0xffffffffu, top);
     deep_max = __reduce_max_sync(0xffffffffu, deep_max);
-    c3_close_window(a, c, local, deep_max > top ? deep_max : top, in_run, s_hist);
+    const bool pooled = deep_max >= 0;  // this warp put positions of c into the pool (deep_max starts at -1)
+    int maxd = top >= 0 && base + top > deep_max ? base + top : deep_max;
+    maxd = maxd < 0 ? 0 : maxd;
+    if (local) {
+        const int b0 = base;
+        c4_finish(a, c, N, (uint32_t)maxd, pooled, [&](uint32_t d) {
+            return (d - (uint32_t)b0) < (uint32_t)C4_RANGE ? s_hist[d - (uint32_t)b0] : 0u;
+        });
+    } else {
+        const int64_t row = (o0g + excl) / C3_RUN;
+        uint32_t *r = a.rows + row * COV_BINS;
+        for (int i = lane; i <= top; i += 32) {
+            const uint32_t v = s_hist[i];
+            if (v) atomicAdd(&r[i], v);
+        }
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+            atomicMax(&a.meta[row].maxd, (unsigned)maxd);
+            if (pooled) atomicOr(&a.meta[row].pad, 1u);
+            __threadfence();
+            const unsigned long long old = atomicAdd(&a.meta[row].done, (unsigned long long)in_run);
+            last = (old + (unsigned long long)in_run == N);
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence();
+            const uint32_t gm = *((volatile unsigned int *)&a.meta[row].maxd);
+            const bool any_pooled = *((volatile unsigned int *)&a.meta[row].pad) != 0;
+            c4_finish(a, c, N, gm, any_pooled, [&](uint32_t d) { return d < (uint32_t)C4_RANGE ? __ldcg(r + d) : 0u; });
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i <= top; i += 32) s_hist[i] = 0;
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(32)
@@ -1672,7 +1827,7 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
     const uint32_t sT0 = smem_base_opaque(sm.T);
     const uint32_t rS0 = smem_base_opaque(sm.ring_s), rE0 = smem_base_opaque(sm.ring_e);
     const uint32_t h0 = smem_base_opaque(sm.hist);
-    if (h0 & 2047u) {  // the shared window is not laid out as assumed: leave the sample to the general path
+    if (h0 != C4_HIST_ADDR) {  // the shared window is not laid out as assumed: leave the sample to the general path
         if (lane == 0) *a.gate_out = 1;
         return;
     }
@@ -1739,7 +1894,8 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
         bool have = false;
         int wlo = 0, whi = -1;      // run-relative window of contig c
         int in_run = 0;             // window slots of c accumulated in this run
-        int deep_max = 0;           // largest depth seen by the exact chunk path for c in this run (per lane)
+        int deep_max = -1;          // largest depth that was counted outside the shared bins for c in this run (per lane; -1: none)
+        int base = 0;               // the shared bins are the depths [base, base + 511) of contig c (warp-uniform)
         int carry4 = 0;             // 4 * depth just before the current window
         int pm = INT_MIN;           // running maximum of the starts consumed so far (run-relative)
         // the vouched bounds are checked on three running extremes (per lane) instead of per event:
@@ -1889,14 +2045,28 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
                     else { wlo = 0; whi = -1; }
                     have = true;
                     in_run = 0;
-                    deep_max = 0;
+                    deep_max = -1;
+                    base = 0;
                 }
                 if (whi < wlo || whi < 0) { c++; have = false; continue; }  // no window / ended before this run
                 if (wlo >= t_hi) break;
                 const int lo = wlo > t_lo ? wlo : t_lo, hi = whi + 1 < t_hi ? whi + 1 : t_hi;
                 if (hi > lo) {
-                    if (lo < q0 + C3_SPL && hi > q0) {  // this lane's slots intersect the window
-                        uint32_t x = h0 + (uint32_t)dstart4;  // address of the current depth's bin
+                    const bool mine = lo < q0 + C3_SPL && hi > q0;  // this lane's slots intersect the window
+                    // keep the bins' range around the depth, judged by the depth at the start of every lane's slots: one
+                    // vote in the common case (nothing near the edges of the range)
+                    if (__any_sync(0xffffffffu, mine && (dstart4 >= 4 * (base + 384) || (base > 0 && dstart4 < 4 * (base + 32))))) {
+                        const int ds = dstart4 >> 2;
+                        const int dmin = __reduce_min_sync(0xffffffffu, mine ? ds : INT_MAX);
+                        int nb = dmin - 128;
+                        nb = nb < 0 ? 0 : nb;
+                        if (nb - base >= 64 || base - nb >= 64) {
+                            deep_max = c4_rebase(a, c, sm.hist, base, deep_max);
+                            base = nb;
+                        }
+                    }
+                    if (mine) {
+                        uint32_t x = (uint32_t)(dstart4 - 4 * base);  // byte offset of the current depth's bin
 #pragma unroll 1
                         for (int ch = 0; ch < C3_SPL / 16; ch++) {
                             const int q = q0 + 16 * ch;
@@ -1914,21 +2084,22 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
 #pragma unroll
                             for (int i = 0; i < 16; i++) orr |= d[i];
                             const int l2 = lo > q ? lo : q, h2 = hi < q + 16 ? hi : q + 16;
-                            // depths are never negative, so every bin below the last one <=> (OR ^ base) below it
-                            if (h2 - l2 == 16 && (orr ^ h0) < (uint32_t)C4_LIMIT4) {
+                            // offsets below the range wrap to huge unsigned values: one OR tests all 16 both ways
+                            if (h2 - l2 == 16 && orr < (uint32_t)C4_LIMIT4) {
 #pragma unroll
-                                for (int i = 0; i < 16; i++) smem_inc(d[i]);
+                                for (int i = 0; i < 16; i++) c4_hist_inc(d[i]);
                             } else if (h2 > l2) {
                                 const uint32_t m = ((1u << (h2 - q)) - 1u) & ~((1u << (l2 - q)) - 1u);
-                                const int mx = c4_slow_chunk(a, c, sm.T + myb + 16 * ch, (int)(x_before - h0), m, sm.hist);
-                                deep_max = mx > deep_max ? mx : deep_max;
+                                const int mx = c4_slow_chunk(a, c, sm.T + myb + 16 * ch, (int)x_before + 4 * base, m, base, sm.hist);
+                                deep_max = mx > deep_max ? mx : deep_max;  // what went to the pool (-1: nothing)
                             }
                         }
                     }
                     in_run += hi - lo;
                 }
                 if (whi >= t_hi) break;  // the window continues in the next 2048 slots
-                c4_close_window(a, c, wlo >= 0, deep_max, in_run, sm.hist);
+                c4_close_window(a, c, wlo >= 0, deep_max, in_run, base, sm.hist);
+                base = 0;
                 c++;
                 have = false;
             }
@@ -1954,7 +2125,7 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
             }
         }
         // ---- run end ----
-        if (have && whi >= wlo && in_run > 0) c4_close_window(a, c, false, deep_max, in_run, sm.hist);
+        if (have && whi >= wlo && in_run > 0) c4_close_window(a, c, false, deep_max, in_run, base, sm.hist);
         viol |= v_re >= C3_W + C3_S || v_rs < 0 || v_blk > span;
         if (__any_sync(0xffffffffu, viol) && lane == 0) *a.gate_out = 1;  // unreliable ranges: the general path redoes the sample
 

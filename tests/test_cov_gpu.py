@@ -379,5 +379,39 @@ def test_fuzz_shapes_depths_and_disorder(covmod, oracle, case):
         general = bool((stats["flags"] & GENERAL).any())
         if case == 5:
             assert general, "span + disorder beyond the overflow region must take the general path"
-        elif case not in (2, 9):  # very deep samples may (9: must) overflow the deep pool
+        elif case != 9:  # 5000x is beyond the deep pool's range: general path
             assert not general, (case, kw, span, dis)
+
+
+def test_depth_that_wanders_across_the_histogram_range(covmod, oracle):
+    """One long contig (five 65 536-slot runs) whose depth ramps 60x -> 1500x -> 30x, next to shallow and uniformly
+    deep (800x) ones: the shared histogram's range follows the depth (several re-bases per run, bins migrating to
+    the pool, partial histograms of different bases merged across runs).  Bit-exact and not the fallback."""
+    rng = np.random.default_rng(77)
+    lengths = np.array([5000, 330000, 12000, 9000, 140], dtype=np.int64)
+    starts, ev_off = [], [0]
+    for c, ln in enumerate(lengths.tolist()):
+        if ln < 200:
+            ev_off.append(len(starts))
+            continue
+        pos = np.arange(0, ln - 150)
+        if c == 1:
+            x = pos / (ln - 150)
+            depth = np.where(x < 0.5, 60 + (1500 - 60) * (x / 0.5), 1500 - (1500 - 30) * ((x - 0.5) / 0.5))
+        else:
+            depth = np.full(len(pos), [20, 0, 800, 3][c], dtype=float)
+        n_at = rng.poisson(depth / 150.0)
+        starts += np.repeat(pos, n_at).tolist()
+        ev_off.append(len(starts))
+    st = np.array(starts, dtype=np.uint32)
+    en = (st + 150).astype(np.uint32)
+    ev_off = np.array(ev_off, dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    wcov, wst = oracle.cov_sample(st, en, ev_off, lengths, 75, 0.05, 0.05, threads=8)
+    assert wst["max_depth"][1] > 1200 and wst["max_depth"][2] > 700
+    for kw in ({}, dict(max_span=150, max_disorder=0)):
+        cov, stats = covmod.cov_from_events(st, en, ev_off, off, 75, 0.05, 0.05, want_stats=True, **kw)
+        for f in INT_FIELDS:
+            assert np.array_equal(stats[f], wst[f]), (f, stats[f], wst[f])
+        assert np.array_equal(cov.view(np.uint32), wcov.view(np.uint32))
+        assert not (stats["flags"] & GENERAL).any()
