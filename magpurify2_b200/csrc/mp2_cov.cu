@@ -807,6 +807,7 @@ struct TileArgs {
     int32_t *deep_list;
     int *deep_count;
     int *work_counter;
+    const int32_t *order;       // cov_stream2_kernel: runs in the order they are drawn (most events first), or NULL
     int32_t *deep_row_of;       // [n] -1 = none; row of the deep pool claimed by the contig
     uint32_t *deep_pool;        // [CT_DEEP_ROWS][CT_DEEP_BINS] counts of depths >= COV_BINS - 1
     int *deep_rows_used;
@@ -1192,6 +1193,15 @@ constexpr int C3_PF = MP2_C3_PF;             // events ahead of e_cur that are p
 
 __device__ __forceinline__ int c3_phys(int i) { return i + 4 * (i >> C3_SPL_LOG); }
 
+// weight class of a run with n_ev events: 0 = heaviest; a class is a factor sqrt(2) wide
+constexpr int C4_WEIGHT_CLASSES = 64;
+__device__ __forceinline__ int run_weight_class(int64_t n_ev) {
+    uint32_t v = n_ev < 0 ? 1u : n_ev >= 0x7fffffff ? 0x80000000u : (uint32_t)n_ev + 1u;
+    const int lz = 31 - __clz(v);                       // floor(log2 v)
+    const int half = lz ? (int)((v >> (lz - 1)) & 1u) : 0;
+    return C4_WEIGHT_CLASSES - 1 - (2 * lz + half);    // 2 * 31 + 1 = 63 at most
+}
+
 // Event range and contigs of every run.  `meas` = {unsorted, longest block, disorder} measured by
 // cov_order_kernel, or NULL when the caller vouched for (max_span, max_disorder).  The ranges are computed with
 // the LARGEST margins the kernels support (span + disorder <= C3_S), so they do not depend on the measured
@@ -1204,7 +1214,8 @@ __global__ void cov_bounds_run_kernel(const uint32_t *__restrict__ starts, const
                                       uint32_t max_disorder, int need_sorted, const unsigned int *__restrict__ meas,
                                       int64_t *__restrict__ e_lo, int64_t *__restrict__ e_hi,
                                       int32_t *__restrict__ c_lo, int32_t *__restrict__ c_hi,
-                                      int32_t *__restrict__ c_ev, int *__restrict__ gate) {
+                                      int32_t *__restrict__ c_ev, int *__restrict__ gate,
+                                      unsigned int *__restrict__ weight_count) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n_runs) return;
     if (meas) { max_span = meas[1]; max_disorder = meas[2]; }
@@ -1218,6 +1229,27 @@ __global__ void cov_bounds_run_kernel(const uint32_t *__restrict__ starts, const
     c_lo[k] = (int32_t)last_le(off, 0, n, k * C3_RUN);  // contig holding the run's first slot
     c_hi[k] = (int32_t)last_le(off, 0, n, B - 1 < off[n] ? B - 1 : off[n]);
     c_ev[k] = (int32_t)last_le(ev_off, 0, n, e_lo[k]);  // contig owning the run's first event (any, if there is none)
+    if (weight_count) atomicAdd(&weight_count[run_weight_class(e_hi[k] - e_lo[k])], 1u);
+}
+
+// Runs are drawn heaviest first.  A run's cost grows with its number of events (a run inside an organism at 1500x
+// holds 60 times the events of one at 25x and takes one warp ~15 times as long); drawn in array order, such runs at
+// the end of the array were a tail of several milliseconds with the rest of the device idle.  A counting sort by weight
+// class (order inside a class is whatever the atomics give: every result is an order-independent integer sum).
+__global__ void cov_run_order_kernel(const int64_t *__restrict__ e_lo, const int64_t *__restrict__ e_hi, int64_t n_runs,
+                                     const unsigned int *__restrict__ weight_count, unsigned int *__restrict__ fill,
+                                     int32_t *__restrict__ order, const int *__restrict__ gate) {
+    __shared__ unsigned int s_first[C4_WEIGHT_CLASSES];
+    if (*gate) return;
+    if (threadIdx.x == 0) {
+        unsigned int acc = 0;
+        for (int b = 0; b < C4_WEIGHT_CLASSES; b++) { s_first[b] = acc; acc += weight_count[b]; }
+    }
+    __syncthreads();
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n_runs) return;
+    const int b = run_weight_class(e_hi[k] - e_lo[k]);
+    order[s_first[b] + atomicAdd(&fill[b], 1u)] = (int32_t)k;
 }
 
 // Out-of-line pieces of cov_stream_kernel: they run once per contig (or never), keeping them out of the
@@ -1844,6 +1876,7 @@ cov_stream2_kernel(const __grid_constant__ TileArgs a) {
         if (lane == 0) run = atomicAdd(a.work_counter, 1);
         run = __shfl_sync(0xffffffffu, run, 0);
         if (run >= a.n_tiles) break;
+        if (a.order) run = a.order[run];
         const int64_t run_lo = run * C3_RUN;
         const int rlen = (int)(run_lo + C3_RUN < a.n_pos ? C3_RUN : a.n_pos - run_lo);
         const int64_t e_base = a.e_lo[run];
@@ -2175,6 +2208,13 @@ static int cov_general_path(const uint32_t *starts, const uint32_t *ends, const 
                             const TrimParams &tp, int *ctrs, const int *gate, float *d_cov, int64_t cov_stride,
                             mp2_cov_stats *d_stats, cudaStream_t stream);
 
+// MP2_COV_RUN_ORDER=0: cov_stream2_kernel draws its runs in array order (development / A-B switch)
+static bool cov_run_order_off() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MP2_COV_RUN_ORDER"); v = (e && e[0] == '0') ? 1 : 0; }
+    return v == 1;
+}
+
 extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, const void *d_ev_off,
                                      const void *d_contig_off, int64_t n_contigs, int64_t n_events,
                                      int64_t n_positions, uint32_t max_span, uint32_t max_disorder, uint32_t end_excl,
@@ -2233,7 +2273,7 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
                         (!measure && ((uint64_t)max_span + max_disorder > (uint64_t)C3_S || (need_sorted && max_disorder)));
     // ---------------- fast path: difference array in shared memory ----------------
     if (!general_only) {
-        Temp e_lo, e_hi, c_lo, c_hi, c_ev, t_rows, t_meta, t_deep, t_drow, t_dpool, k_max;
+        Temp e_lo, e_hi, c_lo, c_hi, c_ev, t_rows, t_meta, t_deep, t_drow, t_dpool, k_max, t_order, t_wcls;
         const int64_t unit = fast_ver == 1 ? CT_TILE : C3_RUN;
         const int64_t n_units = (n_pos + unit - 1) / unit;
         if (n_units > INT32_MAX / 2) return fail(MP2_EINVAL, "too many positions in one call");
@@ -2251,6 +2291,12 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
         MP2_CUDA(cudaMemsetAsync(t_meta.p, 0, sizeof(RowMeta) * n_units, stream));
         MP2_CUDA(cudaMemsetAsync(t_drow.p, 0xFF, sizeof(int32_t) * n_contigs, stream));
         MP2_CUDA(cudaMemsetAsync(t_dpool.p, 0, sizeof(uint32_t) * (size_t)CT_DEEP_ROWS * CT_DEEP_BINS, stream));
+        const bool ordered = fast_ver == 4 && !cov_run_order_off();
+        if (ordered) {  // [0, 64) runs per weight class, [64, 128) fill counters of the counting sort
+            MP2_TRY(t_order.alloc(sizeof(int32_t) * n_units, stream));
+            MP2_TRY(t_wcls.alloc(sizeof(unsigned int) * 2 * C4_WEIGHT_CLASSES, stream));
+            MP2_CUDA(cudaMemsetAsync(t_wcls.p, 0, sizeof(unsigned int) * 2 * C4_WEIGHT_CLASSES, stream));
+        }
         if (n_events > 0 && measure) {  // longest block and disorder of the starts, exactly (one pass over the events)
             MP2_TRY(k_max.alloc(sizeof(OrderTile) * n_ev_tiles, stream));
             {
@@ -2276,7 +2322,14 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
                 cov_bounds_run_kernel<<<(unsigned)((n_units + 127) / 128), 128, 0, stream>>>(
                     starts, ev_off, off, n_contigs, n_units, max_span, max_disorder, need_sorted ? 1 : 0, meas,
                     e_lo.as<int64_t>(), e_hi.as<int64_t>(), c_lo.as<int32_t>(), c_hi.as<int32_t>(), c_ev.as<int32_t>(),
-                    gate);
+                    gate, ordered ? t_wcls.as<unsigned int>() : nullptr);
+        }
+        MP2_CUDA(cudaGetLastError());
+        if (ordered) {
+            Launch L("cov_run_order_kernel", stream);
+            cov_run_order_kernel<<<(unsigned)((n_units + 255) / 256), 256, 0, stream>>>(
+                e_lo.as<int64_t>(), e_hi.as<int64_t>(), n_units, t_wcls.as<unsigned int>(),
+                t_wcls.as<unsigned int>() + C4_WEIGHT_CLASSES, t_order.as<int32_t>(), gate);
         }
         MP2_CUDA(cudaGetLastError());
         TileArgs t;
@@ -2288,6 +2341,7 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
         t.rows = t_rows.as<uint32_t>(); t.meta = t_meta.as<RowMeta>();
         t.deep_list = t_deep.as<int32_t>(); t.deep_count = ctrs.as<int>() + 0;
         t.work_counter = ctrs.as<int>() + 1;
+        t.order = ordered ? t_order.as<int32_t>() : nullptr;
         t.deep_row_of = t_drow.as<int32_t>(); t.deep_pool = t_dpool.as<uint32_t>(); t.deep_rows_used = ctrs.as<int>() + 6;
         t.check = measure ? flags.as<unsigned int>() : nullptr;  // tile kernel: flag[0] != 0 => not sorted
         t.span_host = max_span;
