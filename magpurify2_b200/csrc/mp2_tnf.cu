@@ -14,6 +14,7 @@
 // red.shared on 32 random words costs ~3.4 wavefronts (worst bank load), so the design minimises
 // wavefronts: one increment per TWO bases (5-mer table), a flush whose table reads are all
 // conflict-free LDS.128, and an interior row path without divergence (edge rows are out of line).
+#include <climits>
 #include <cstdlib>
 #include <mutex>
 
@@ -50,11 +51,32 @@ template <int MODE> struct TnfTab {
 #ifndef MP2_TNF_TMAZERO
 #define MP2_TNF_TMAZERO 1
 #endif
+#ifndef MP2_TNF_FLUSH1
+#define MP2_TNF_FLUSH1 1
+#endif
+#ifndef MP2_TNF_EDGE1
+#define MP2_TNF_EDGE1 1
+#endif
 // MODE 5 flush: the 4 KB 5-mer table is cleared by the bulk-copy engine (cp.async.bulk from a page of zeros in
 // L2) instead of 8 STS.128 per lane: the kernel is bound by the LSU data pipe (1 wavefront per clock), the copy
 // engine writes shared memory without going through it, and the copy runs while the warp folds the 4-mer sums
 // into the 136 classes and sends them to the contig's row.
 __device__ __align__(128) uint32_t g_zero_page[1024];
+
+#ifndef MP2_TNF_FMASH
+#define MP2_TNF_FMASH 0
+#endif
+// Right shifts of the streaming loop as IMAD.HI (x >> k = high word of x * 2^(32-k)): the ALU pipe (SHF / LOP3 / PRMT)
+// is the second-busiest resource of tnf_kernel (81 %), the FMA pipe is nearly idle (11 %).  The multipliers live in
+// constant memory so that the compiler cannot turn the multiplications back into shifts: c_shmul[k] = 2^(32-k).
+__constant__ uint32_t c_shmul[32];
+template <int K> __device__ __forceinline__ uint32_t shr_fma(uint32_t x) {
+#if MP2_TNF_FMASH
+    return __umulhi(x, c_shmul[K]);
+#else
+    return x >> K;
+#endif
+}
 
 __constant__ uint8_t c_lut256[256];             // code -> canonical class
 __constant__ uint16_t c_canon_pair[MP2_NCANON];  // class -> smallest code | revcomp code << 8
@@ -75,6 +97,10 @@ static int upload_tables() {
         pair[k] = (uint16_t)(a | (rc << 8));
     }
     MP2_CUDA(cudaMemcpyToSymbol(c_canon_pair, pair, sizeof pair));
+    uint32_t shmul[32];
+    shmul[0] = 0;
+    for (int k = 1; k < 32; k++) shmul[k] = 1u << (32 - k);
+    MP2_CUDA(cudaMemcpyToSymbol(c_shmul, shmul, sizeof shmul));
     if (dev < 64) done[dev] = true;
     return MP2_OK;
 }
@@ -86,7 +112,7 @@ static int upload_tables() {
 //   valid <=> (b & 0xD9) == (isT ? 0x50 : 0x41)
 // `sig` is 0x41414141 exactly when all four bytes are one of AaCcGgTt.
 __device__ __forceinline__ uint32_t decode4_hi(uint32_t w, uint32_t &sig) {
-    const uint32_t s1 = w >> 1, s2 = w >> 2;
+    const uint32_t s1 = shr_fma<1>(w), s2 = shr_fma<2>(w);
     const uint32_t x = (s1 ^ s2) & 0x03030303u;
     const uint32_t isT = s2 & ~s1 & 0x01010101u;
     sig = (w & 0xD9D9D9D9u) ^ (isT * 0x11u);
@@ -197,6 +223,40 @@ __device__ __forceinline__ void tnf_bar_init(int lane) {
 __device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__restrict__ row, uint32_t &phase) {
     const uint4 *t5v = reinterpret_cast<const uint4 *>(tab);
     uint4 *t4v = reinterpret_cast<uint4 *>(tab + 1024);
+#if MP2_TNF_FLUSH1
+    // T5 is read ONCE: the uint4 at word b*256 + 8L + 4h holds T5[b . c] for the four codes c = 8L + 4h + 0..3 (added
+    // element-wise over b: their suffix marginals) and, summed horizontally, is the prefix marginal of code
+    // 64b + 2L + h.  The eight prefix sums go through the T4 region (its own contents are in registers by then) to
+    // the lanes that own those codes.
+    const int hx = (lane >> 2) & 1;
+    __syncwarp();
+    uint4 sum[2];
+    uint32_t ps[2][4];
+#pragma unroll
+    for (int hp = 0; hp < 2; hp++) {
+        const int h = hp ^ hx;
+        sum[hp] = t4v[2 * lane + h];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint4 q = t5v[b * 64 + 2 * lane + h];
+            sum[hp].x += q.x; sum[hp].y += q.y; sum[hp].z += q.z; sum[hp].w += q.w;
+            ps[hp][b] = (q.x + q.y) + (q.z + q.w);
+        }
+    }
+    __syncwarp();  // every lane has read its T4 words: the region is free
+#pragma unroll
+    for (int b = 0; b < 4; b++)  // codes 64b + 2L (h = 0) and 64b + 2L + 1 (h = 1): one conflict-free 64-bit store
+        *reinterpret_cast<uint2 *>(tab + 1024 + 64 * b + 2 * lane) =
+            make_uint2(hx ? ps[1][b] : ps[0][b], hx ? ps[0][b] : ps[1][b]);
+    __syncwarp();
+#pragma unroll
+    for (int hp = 0; hp < 2; hp++) {
+        const int h = hp ^ hx;
+        const uint4 p = t4v[2 * lane + h];
+        sum[hp].x += p.x; sum[hp].y += p.y; sum[hp].z += p.z; sum[hp].w += p.w;
+        t4v[2 * lane + h] = sum[hp];  // only this lane touches these words
+    }
+#else
     const int sg = lane & 7, hx = (lane >> 2) & 1;
     __syncwarp();
     uint32_t P[8];
@@ -221,6 +281,7 @@ __device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__
         sum.x += P[4 * hp + 0]; sum.y += P[4 * hp + 1]; sum.z += P[4 * hp + 2]; sum.w += P[4 * hp + 3];
         t4v[2 * lane + h] = sum;  // only this lane touches these words
     }
+#endif
     __syncwarp();  // every lane is done reading T5; the 4-mer counts are visible in T4
 #if MP2_TNF_TMAZERO
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tnf_bar);
@@ -274,13 +335,16 @@ template <int MODE>
 __device__ __forceinline__ void tnf_count16(uint32_t cw, uint32_t halo, uint32_t t5, uint32_t t4) {
     if (MODE == 5) {
         // 5-mer ending at base j+1 (j even) = bits [2(14-j)+9 : 2(14-j)] of halo:cw; its counter is
-        // word index*4 bytes into T5
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-            const int sh = 2 * (14 - j);
-            const uint32_t t = sh >= 2 ? __funnelshift_r(cw, halo, sh - 2) : (cw << 2);
-            smem_inc(t5 + (t & 0xFFCu));
-        }
+        // word index*4 bytes into T5.  The two windows that reach into the halo take a funnel shift, the five
+        // that lie inside cw a plain shift (on the FMA pipe), the last one a left shift.
+        smem_inc(t5 + (__funnelshift_r(cw, halo, 26) & 0xFFCu));
+        smem_inc(t5 + (__funnelshift_r(cw, halo, 22) & 0xFFCu));
+        smem_inc(t5 + (shr_fma<18>(cw) & 0xFFCu));
+        smem_inc(t5 + (shr_fma<14>(cw) & 0xFFCu));
+        smem_inc(t5 + (shr_fma<10>(cw) & 0xFFCu));
+        smem_inc(t5 + (shr_fma<6>(cw) & 0xFFCu));
+        smem_inc(t5 + (shr_fma<2>(cw) & 0xFFCu));
+        smem_inc(t5 + ((cw << 2) & 0xFFCu));
     } else {
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -459,6 +523,81 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
             const int in_lo = o0 + 3 > seg_lo ? o0 + 3 : seg_lo;
             const int g_in_lo = (in_lo + 15) >> 4;
             const int g_in_hi = (seg_hi >> 4) > g_in_lo ? (seg_hi >> 4) : g_in_lo;  // [g_in_lo, g_in_hi)
+#if MP2_TNF_EDGE1
+            // The rows cover the INTERIOR groups only (whole groups inside the segment: always safe to load); the at
+            // most three partial groups of the segment (head: up to two, tail: one) are counted together afterwards.
+            // So the first row of a segment is an ordinary row, the last one an ordinary row with idle lanes, and the
+            // per-base masks are built once per segment instead of once per edge row.
+            if (g_in_hi > g_in_lo) {
+                // packed halo (last 3 codes | bit 8 "not usable") of the group before g_in_lo, kept by lane 31;
+                // its bytes lie inside the contig (16 g_in_lo >= o0 + 3) and inside the buffer (g_in_lo >= 1)
+                uint32_t carry = 0x100u;
+                if (lane == 31) {
+                    uint32_t sg;
+                    const uint32_t ph = decode4(__ldg(reinterpret_cast<const uint32_t *>(pb + (g_in_lo << 4) - 4)), sg);
+                    carry = (ph & 0x3Fu) | (((sg ^ 0x41414141u) & 0xFFFFFF00u) ? 0x100u : 0u);
+                }
+                for (int g0 = g_in_lo; g0 < g_in_hi; g0 += 32 * TNF_UNROLL) {
+                    uint4 v[TNF_UNROLL];
+                    if (g0 + 32 * TNF_UNROLL <= g_in_hi) {  // warp-uniform: the whole tile is interior
+#pragma unroll
+                        for (int u = 0; u < TNF_UNROLL; u++)
+                            v[u] = __ldg(reinterpret_cast<const uint4 *>(pb + ((g0 + 32 * u + lane) << 4)));
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < TNF_UNROLL; u++) {
+                            const int g = g0 + 32 * u + lane;
+                            v[u] = make_uint4(0, 0, 0, 0);
+                            if (g < g_in_hi) v[u] = __ldg(reinterpret_cast<const uint4 *>(pb + (g << 4)));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < TNF_UNROLL; u++) {
+                        if (g0 + 32 * u >= g_in_hi) break;  // warp-uniform
+                        const int g = g0 + 32 * u + lane;
+                        uint32_t s0, s1, s2, s3;
+                        const uint32_t m0 = decode4_hi(v[u].x, s0), m1 = decode4_hi(v[u].y, s1);
+                        const uint32_t m2 = decode4_hi(v[u].z, s2), m3 = decode4_hi(v[u].w, s3);
+                        const uint32_t cw = __byte_perm(__byte_perm(m3, m2, 0x0073), __byte_perm(m1, m0, 0x0073), 0x5410);
+                        // 16 valid bases (a group beyond the interior was loaded as zeros and is never clean)
+                        const bool clean = (((s0 ^ s1) | (s2 ^ s3) | (s0 ^ s2)) == 0) && (s0 == 0x41414141u);
+                        const uint32_t mine = (cw & 0x3Fu) | (clean ? 0u : 0x100u);
+                        const uint32_t give = lane == 31 ? carry : mine;
+                        const uint32_t halo = __shfl_sync(0xffffffffu, give, src_lane);
+                        carry = mine;  // only lane 31's copy is ever consumed
+                        const bool fast = clean && (halo < 0x100u);
+                        if (__all_sync(0xffffffffu, fast)) {
+                            gcl += __popc((cw ^ (cw >> 1)) & 0x55555555u);
+                            tnf_count16<MODE>(cw, halo, t5, t4);
+                        } else if (__all_sync(0xffffffffu, fast || g >= g_in_hi)) {  // the segment's last row
+                            if (g < g_in_hi) {
+                                gcl += __popc((cw ^ (cw >> 1)) & 0x55555555u);
+                                tnf_count16<MODE>(cw, halo, t5, t4);
+                            }
+                        } else {  // a group with a non-ACGT byte
+                            gcl += tnf_edge_row<MODE>(v[u], cw, halo, fast, g, g_in_hi - 1, o0, seg_lo, seg_hi, pb, head_ok);
+                        }
+                    }
+                }
+            }
+            {   // partial groups: g_first .. min(g_in_lo, g_last + 1) - 1 and, if the segment ends inside a group, g_in_hi
+                const int n_head = (g_in_lo < g_last + 1 ? g_in_lo : g_last + 1) - g_first;
+                const bool has_tail = g_in_hi <= g_last;
+                if (n_head > 0 || has_tail) {  // warp-uniform
+                    const int g = lane < n_head ? g_first + lane : (lane == n_head && has_tail) ? g_in_hi : INT_MAX;
+                    uint4 vv = make_uint4(0, 0, 0, 0);
+                    if (g != INT_MAX) {
+                        const int P = g << 4;
+                        vv = P + 16 <= safe_hi ? __ldg(reinterpret_cast<const uint4 *>(pb + P)) : tnf_load_tail(pb, P, safe_hi);
+                    }
+                    uint32_t s0, s1, s2, s3;
+                    const uint32_t m0 = decode4_hi(vv.x, s0), m1 = decode4_hi(vv.y, s1);
+                    const uint32_t m2 = decode4_hi(vv.z, s2), m3 = decode4_hi(vv.w, s3);
+                    const uint32_t cw = __byte_perm(__byte_perm(m3, m2, 0x0073), __byte_perm(m1, m0, 0x0073), 0x5410);
+                    gcl += tnf_edge_row<MODE>(vv, cw, 0u, false, g, g_last, o0, seg_lo, seg_hi, pb, head_ok);
+                }
+            }
+#else
             const unsigned g_in_n = (unsigned)(g_in_hi - g_in_lo);
             // groups below this one exist and may be read whole
             const int g_load_hi = (g_last + 1) < (safe_hi >> 4) ? (g_last + 1) : (safe_hi >> 4);
@@ -515,6 +654,7 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                     }
                 }
             }
+#endif
             gcl = __reduce_add_sync(0xffffffffu, gcl);
             if (lane == 0 && gcl) atomicAdd(&gc_counts[c], (unsigned long long)gcl);
             tnf_flush<MODE>(tab, lane, counts + c * MP2_NCANON, zero_phase);
