@@ -51,32 +51,11 @@ template <int MODE> struct TnfTab {
 #ifndef MP2_TNF_TMAZERO
 #define MP2_TNF_TMAZERO 1
 #endif
-#ifndef MP2_TNF_FLUSH1
-#define MP2_TNF_FLUSH1 1
-#endif
-#ifndef MP2_TNF_EDGE1
-#define MP2_TNF_EDGE1 1
-#endif
 // MODE 5 flush: the 4 KB 5-mer table is cleared by the bulk-copy engine (cp.async.bulk from a page of zeros in
 // L2) instead of 8 STS.128 per lane: the kernel is bound by the LSU data pipe (1 wavefront per clock), the copy
 // engine writes shared memory without going through it, and the copy runs while the warp folds the 4-mer sums
 // into the 136 classes and sends them to the contig's row.
 __device__ __align__(128) uint32_t g_zero_page[1024];
-
-#ifndef MP2_TNF_FMASH
-#define MP2_TNF_FMASH 0
-#endif
-// Right shifts of the streaming loop as IMAD.HI (x >> k = high word of x * 2^(32-k)): the ALU pipe (SHF / LOP3 / PRMT)
-// is the second-busiest resource of tnf_kernel (81 %), the FMA pipe is nearly idle (11 %).  The multipliers live in
-// constant memory so that the compiler cannot turn the multiplications back into shifts: c_shmul[k] = 2^(32-k).
-__constant__ uint32_t c_shmul[32];
-template <int K> __device__ __forceinline__ uint32_t shr_fma(uint32_t x) {
-#if MP2_TNF_FMASH
-    return __umulhi(x, c_shmul[K]);
-#else
-    return x >> K;
-#endif
-}
 
 __constant__ uint8_t c_lut256[256];             // code -> canonical class
 __constant__ uint16_t c_canon_pair[MP2_NCANON];  // class -> smallest code | revcomp code << 8
@@ -97,10 +76,6 @@ static int upload_tables() {
         pair[k] = (uint16_t)(a | (rc << 8));
     }
     MP2_CUDA(cudaMemcpyToSymbol(c_canon_pair, pair, sizeof pair));
-    uint32_t shmul[32];
-    shmul[0] = 0;
-    for (int k = 1; k < 32; k++) shmul[k] = 1u << (32 - k);
-    MP2_CUDA(cudaMemcpyToSymbol(c_shmul, shmul, sizeof shmul));
     if (dev < 64) done[dev] = true;
     return MP2_OK;
 }
@@ -112,7 +87,7 @@ static int upload_tables() {
 //   valid <=> (b & 0xD9) == (isT ? 0x50 : 0x41)
 // `sig` is 0x41414141 exactly when all four bytes are one of AaCcGgTt.
 __device__ __forceinline__ uint32_t decode4_hi(uint32_t w, uint32_t &sig) {
-    const uint32_t s1 = shr_fma<1>(w), s2 = shr_fma<2>(w);
+    const uint32_t s1 = w >> 1, s2 = w >> 2;
     const uint32_t x = (s1 ^ s2) & 0x03030303u;
     const uint32_t isT = s2 & ~s1 & 0x01010101u;
     sig = (w & 0xD9D9D9D9u) ^ (isT * 0x11u);
@@ -196,18 +171,16 @@ __device__ __forceinline__ void tnf_flush(uint32_t *tab, int lane, uint32_t *__r
     __syncwarp();
 }
 
-#define MP2_CSWAP(c, x, y) do { const uint32_t _t = (c) ? (y) : (x); (y) = (c) ? (x) : (y); (x) = _t; } while (0)
 
 // MODE 5 flush.  count4[c] = T4[c] + sum_b T5[c.b] + sum_b T5[b.c]; every table read below is a
-// bank-conflict-free LDS.128 (a quarter warp reads 8 distinct 16-byte bank groups):
-//   * lane L owns the codes 8L..8L+7.  Their prefix marginals are the 32 words of T5 row L = the
-//     uint4s 8L..8L+7 (one uint4 per code); all rows start in bank 0, so lane L reads them in the
-//     order j ^ (L&7).
-//   * their suffix marginals are the words b*256 + 8L..8L+7 for b = 0..3 and T4[8L..8L+7]: two
-//     uint4s each, read in the order h ^ ((L>>2)&1).
-// The two read orders leave the registers permuted by the lane number; two conditional-swap stages
-// bring the prefix sums into the order of the suffix sums, whose uint4 halves go back to the T4
-// region at the very address they came from.  The 136 classes are then gathered from T4.
+// bank-conflict-free LDS.128 (a quarter warp reads 8 distinct 16-byte bank groups) and T5 is read once:
+//   * lane L owns the codes 8L..8L+7.  Their suffix marginals are the words b*256 + 8L..8L+7 for b = 0..3 and
+//     T4[8L..8L+7]: two uint4s each, read in the order h ^ ((L>>2)&1) and added element-wise;
+//   * the same eight uint4s, summed horizontally, are the prefix marginals of the codes 64b + 2L + h, which belong
+//     to other lanes: they are handed over through the T4 region (four conflict-free 64-bit stores, two LDS.128).
+// The 4-mer counts end up in the T4 region at the address of their code; the 136 classes are gathered from there.
+// (Until round 2 the prefix marginals were a second pass over T5: 32 more wavefronts per flush on the pipe that
+// bounds the kernel.)
 __shared__ __align__(8) unsigned long long tnf_bar;   // completion of the table's bulk clear (one warp per CTA)
 
 __device__ __forceinline__ void tnf_bar_init(int lane) {
@@ -223,7 +196,6 @@ __device__ __forceinline__ void tnf_bar_init(int lane) {
 __device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__restrict__ row, uint32_t &phase) {
     const uint4 *t5v = reinterpret_cast<const uint4 *>(tab);
     uint4 *t4v = reinterpret_cast<uint4 *>(tab + 1024);
-#if MP2_TNF_FLUSH1
     // T5 is read ONCE: the uint4 at word b*256 + 8L + 4h holds T5[b . c] for the four codes c = 8L + 4h + 0..3 (added
     // element-wise over b: their suffix marginals) and, summed horizontally, is the prefix marginal of code
     // 64b + 2L + h.  The eight prefix sums go through the T4 region (its own contents are in registers by then) to
@@ -256,32 +228,6 @@ __device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__
         sum[hp].x += p.x; sum[hp].y += p.y; sum[hp].z += p.z; sum[hp].w += p.w;
         t4v[2 * lane + h] = sum[hp];  // only this lane touches these words
     }
-#else
-    const int sg = lane & 7, hx = (lane >> 2) & 1;
-    __syncwarp();
-    uint32_t P[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const uint4 q = t5v[8 * lane + (j ^ sg)];
-        P[j] = q.x + q.y + q.z + q.w;  // code 8L + (j ^ sg)
-    }
-    const bool s1 = sg & 1, s2 = sg & 2;
-    MP2_CSWAP(s1, P[0], P[1]); MP2_CSWAP(s1, P[2], P[3]); MP2_CSWAP(s1, P[4], P[5]); MP2_CSWAP(s1, P[6], P[7]);
-    MP2_CSWAP(s2, P[0], P[2]); MP2_CSWAP(s2, P[1], P[3]); MP2_CSWAP(s2, P[4], P[6]); MP2_CSWAP(s2, P[5], P[7]);
-    // now P[4h'+m] belongs to code 8L + 4(h' ^ hx) + m
-#pragma unroll
-    for (int hp = 0; hp < 2; hp++) {
-        const int h = hp ^ hx;
-        uint4 sum = t4v[2 * lane + h];
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const uint4 q = t5v[b * 64 + 2 * lane + h];
-            sum.x += q.x; sum.y += q.y; sum.z += q.z; sum.w += q.w;
-        }
-        sum.x += P[4 * hp + 0]; sum.y += P[4 * hp + 1]; sum.z += P[4 * hp + 2]; sum.w += P[4 * hp + 3];
-        t4v[2 * lane + h] = sum;  // only this lane touches these words
-    }
-#endif
     __syncwarp();  // every lane is done reading T5; the 4-mer counts are visible in T4
 #if MP2_TNF_TMAZERO
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tnf_bar);
@@ -336,14 +282,14 @@ __device__ __forceinline__ void tnf_count16(uint32_t cw, uint32_t halo, uint32_t
     if (MODE == 5) {
         // 5-mer ending at base j+1 (j even) = bits [2(14-j)+9 : 2(14-j)] of halo:cw; its counter is
         // word index*4 bytes into T5.  The two windows that reach into the halo take a funnel shift, the five
-        // that lie inside cw a plain shift (on the FMA pipe), the last one a left shift.
+        // that lie inside cw a plain shift, the last one a left shift.
         smem_inc(t5 + (__funnelshift_r(cw, halo, 26) & 0xFFCu));
         smem_inc(t5 + (__funnelshift_r(cw, halo, 22) & 0xFFCu));
-        smem_inc(t5 + (shr_fma<18>(cw) & 0xFFCu));
-        smem_inc(t5 + (shr_fma<14>(cw) & 0xFFCu));
-        smem_inc(t5 + (shr_fma<10>(cw) & 0xFFCu));
-        smem_inc(t5 + (shr_fma<6>(cw) & 0xFFCu));
-        smem_inc(t5 + (shr_fma<2>(cw) & 0xFFCu));
+        smem_inc(t5 + ((cw >> 18) & 0xFFCu));
+        smem_inc(t5 + ((cw >> 14) & 0xFFCu));
+        smem_inc(t5 + ((cw >> 10) & 0xFFCu));
+        smem_inc(t5 + ((cw >> 6) & 0xFFCu));
+        smem_inc(t5 + ((cw >> 2) & 0xFFCu));
         smem_inc(t5 + ((cw << 2) & 0xFFCu));
     } else {
 #pragma unroll
@@ -508,10 +454,14 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
         const int safe_hi = (int)(room < ((piece_hi + 15) & ~15) ? room : ((piece_hi + 15) & ~15));
         const bool head_ok = base > 0; // bytes before the piece may be read (halo)
 
-        for (int64_t c = first_contig[kc]; c < n; c++) {
-            const int64_t o0_64 = offsets[c] + mis - base;
+        // the contig boundaries are fetched one segment ahead (a segment's first loads wait for them otherwise)
+        int64_t c = first_contig[kc];
+        int64_t off_c = offsets[c], off_n = offsets[c + 1], off_nn = 0;
+        for (; c < n; c++, off_c = off_n, off_n = off_nn) {
+            off_nn = c + 2 <= n ? offsets[c + 2] : off_n;
+            const int64_t o0_64 = off_c + mis - base;
             if (o0_64 >= piece_hi) break;
-            const int64_t o1_64 = offsets[c + 1] + mis - base;
+            const int64_t o1_64 = off_n + mis - base;
             const int o0 = o0_64 < -64 ? -64 : (int)o0_64;  // only compared with positions >= -3
             const int seg_lo = o0 > piece_lo ? o0 : piece_lo;
             const int seg_hi = o1_64 < piece_hi ? (int)o1_64 : piece_hi;
@@ -523,7 +473,6 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
             const int in_lo = o0 + 3 > seg_lo ? o0 + 3 : seg_lo;
             const int g_in_lo = (in_lo + 15) >> 4;
             const int g_in_hi = (seg_hi >> 4) > g_in_lo ? (seg_hi >> 4) : g_in_lo;  // [g_in_lo, g_in_hi)
-#if MP2_TNF_EDGE1
             // The rows cover the INTERIOR groups only (whole groups inside the segment: always safe to load); the at
             // most three partial groups of the segment (head: up to two, tail: one) are counted together afterwards.
             // So the first row of a segment is an ordinary row, the last one an ordinary row with idle lanes, and the
@@ -597,64 +546,6 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                     gcl += tnf_edge_row<MODE>(vv, cw, 0u, false, g, g_last, o0, seg_lo, seg_hi, pb, head_ok);
                 }
             }
-#else
-            const unsigned g_in_n = (unsigned)(g_in_hi - g_in_lo);
-            // groups below this one exist and may be read whole
-            const int g_load_hi = (g_last + 1) < (safe_hi >> 4) ? (g_last + 1) : (safe_hi >> 4);
-            // packed halo (last 3 codes | bit 8 "not usable") of the group before g_first, kept by
-            // lane 31: the piece's first group of a long contig then takes the vector path too
-            uint32_t carry = 0x100u;
-            if (lane == 31 && (g_first << 4) - 3 >= o0 && ((g_first << 4) >= 4 || head_ok)) {
-                uint32_t sg;
-                const uint32_t ph = decode4(__ldg(reinterpret_cast<const uint32_t *>(pb + (g_first << 4) - 4)), sg);
-                carry = (ph & 0x3Fu) | (((sg ^ 0x41414141u) & 0xFFFFFF00u) ? 0x100u : 0u);
-            }
-            for (int g0 = g_first; g0 <= g_last; g0 += 32 * TNF_UNROLL) {
-                uint4 v[TNF_UNROLL];
-                if (g0 + 32 * TNF_UNROLL <= g_load_hi) {  // warp-uniform: the whole tile can be loaded blindly
-#pragma unroll
-                    for (int u = 0; u < TNF_UNROLL; u++)
-                        v[u] = __ldg(reinterpret_cast<const uint4 *>(pb + ((g0 + 32 * u + lane) << 4)));
-                } else {
-#pragma unroll
-                    for (int u = 0; u < TNF_UNROLL; u++) {
-                        const int g = g0 + 32 * u + lane;
-                        const int P = g << 4;
-                        v[u] = make_uint4(0, 0, 0, 0);
-                        if (g < g_load_hi) {
-                            v[u] = __ldg(reinterpret_cast<const uint4 *>(pb + P));
-                        } else if (g <= g_last) {  // last group of the whole stream: never read past the buffer
-                            v[u] = tnf_load_tail(pb, P, safe_hi);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < TNF_UNROLL; u++) {
-                    if (g0 + 32 * u > g_last) break;  // warp-uniform
-                    const int g = g0 + 32 * u + lane;
-                    uint32_t s0, s1, s2, s3;
-                    const uint32_t m0 = decode4_hi(v[u].x, s0), m1 = decode4_hi(v[u].y, s1);
-                    const uint32_t m2 = decode4_hi(v[u].z, s2), m3 = decode4_hi(v[u].w, s3);
-                    // cw = top bytes of m0..m3, first base most significant
-                    const uint32_t cw = __byte_perm(__byte_perm(m3, m2, 0x0073), __byte_perm(m1, m0, 0x0073), 0x5410);
-                    // all four signatures equal to 0x41414141 <=> 16 valid bases (a group beyond g_last
-                    // was loaded as zeros and is never clean)
-                    const bool clean = (((s0 ^ s1) | (s2 ^ s3) | (s0 ^ s2)) == 0) && (s0 == 0x41414141u);
-                    // halo = last 3 codes of the previous group + bit 8 "not usable"
-                    const uint32_t mine = (cw & 0x3Fu) | (clean ? 0u : 0x100u);
-                    const uint32_t give = lane == 31 ? carry : mine;
-                    const uint32_t halo = __shfl_sync(0xffffffffu, give, src_lane);
-                    carry = mine;  // only lane 31's copy is ever consumed
-                    const bool fast = clean && (halo < 0x100u) && ((unsigned)(g - g_in_lo) < g_in_n);
-                    if (__all_sync(0xffffffffu, fast)) {
-                        gcl += __popc((cw ^ (cw >> 1)) & 0x55555555u);
-                        tnf_count16<MODE>(cw, halo, t5, t4);
-                    } else {
-                        gcl += tnf_edge_row<MODE>(v[u], cw, halo, fast, g, g_last, o0, seg_lo, seg_hi, pb, head_ok);
-                    }
-                }
-            }
-#endif
             gcl = __reduce_add_sync(0xffffffffu, gcl);
             if (lane == 0 && gcl) atomicAdd(&gc_counts[c], (unsigned long long)gcl);
             tnf_flush<MODE>(tab, lane, counts + c * MP2_NCANON, zero_phase);

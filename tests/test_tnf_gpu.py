@@ -51,6 +51,19 @@ def test_signature_matches_reference(comp):
         comp.get_tnf([1, 2])
 
 
+def test_non_ascii_strings(comp, oracle):
+    # a non-ASCII character is one `char` to the reference (chars().count(), src/composition.rs:131) and its UTF-8 bytes
+    # only reset the k-mer window (composition.rs:48-61): GC denominators count characters, k-mers never span it
+    seqs = ["GCéAT", "ACGTé", "éACGTACGT", "ACGT\u4e2dACGT\U0001F9ECTTTT", "é", "ACGTACGTé" * 40]
+    counts = comp.get_tnf(seqs, relative=False)
+    assert np.array_equal(counts, oracle.get_tnf(seqs, relative=False))
+    assert counts[3].sum() == 1 + 1 + 1 and counts[0].sum() == 0
+    assert _same_f32(comp.get_tnf(seqs), oracle.get_tnf(seqs, relative=True))
+    gc = comp.get_gc(seqs)
+    assert _same_f32(gc, oracle.get_gc(seqs))
+    assert gc[0] == np.float32(2) / np.float32(5) and gc[4] == 0.0
+
+
 def test_ragged_random(comp, oracle):
     rng = np.random.default_rng(11)
     alphabet = np.frombuffer(b"ACGTacgtNRYKMSWnU-*", dtype=np.uint8)
