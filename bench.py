@@ -32,13 +32,15 @@ UNIT = "Gbp/s"
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (None if absent)."""
+    """(DRAM bytes per launch of `kernel` from the committed ncu --set full capture, the file they came from), or
+    (None, None).  The bench does not measure DRAM traffic itself (that needs ncu's replay)."""
     for name in ("r2_traffic.json", "r1_traffic.json"):
         try:
-            return json.load(open(os.path.join(ROOT, "profiles", name)))[kernel]["dram_bytes"]
+            return (json.load(open(os.path.join(ROOT, "profiles", name)))[kernel]["dram_bytes"],
+                    f"profiles/{name} (ncu --set full capture of this workload, not measured in this run)")
         except Exception:
             continue
-    return None
+    return None, None
 
 
 def peaks():
@@ -358,8 +360,8 @@ def coverage_phase(args, lib, dev, d, d_off, world, rank, local, barrier):
         bytes_ = sample_bytes if fused else moved[name]
         ach = bytes_ / (t_ms * 1e-3) / 1e9
         r = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-             "traffic": ncu_traffic(name) if (args.mags == 1000 and args.depth_scale == 1.0) else None,
-             "traffic_source": "profiles/r1_traffic.json / r2_traffic.json (ncu --set full capture, not measured in this run)",
+             "traffic": ncu_traffic(name)[0] if (args.mags == 1000 and args.depth_scale == 1.0) else None,
+             "traffic_source": ncu_traffic(name)[1],
              "algorithmic_bytes_per_launch": bytes_, "kernel_ms": t_ms, "launches_timed": kern[name][1]}
         if fused:
             r["algorithmic_bytes"] = "SURVEY 8(d): 8*L + 20*R per sample"
@@ -809,9 +811,8 @@ def main():
         },
         "roofline": {"bound": "hbm", "kernel": "tnf_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic("tnf_kernel") if (args.mags == 1000 and not args.long_contigs) else None,
-                     "traffic_source": "profiles/r1_traffic.json (ncu --set full capture of this workload, not measured "
-                                       "in this run)",
+                     "traffic": ncu_traffic("tnf_kernel")[0] if (args.mags == 1000 and not args.long_contigs) else None,
+                     "traffic_source": ncu_traffic("tnf_kernel")[1],
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_avg_ms,
                      "launches_timed": k_n.value, "peak_source": peak_src},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
