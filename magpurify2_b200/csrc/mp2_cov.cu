@@ -796,7 +796,8 @@ constexpr int CT_CTAB = 96;  // contigs of a tile whose offsets are staged in sh
 // 4096 bins (32 MB, cleared per sample).  Beyond that -- more deep contigs, or depth >= 4606 -- the sample is
 // redone by the general path (2.5x slower, same results).  (256 rows x 32768 bins sent 2 of 80 C3-shaped
 // samples of an 8-GPU run down the general path: one rank at 87 ms per step, the others at 58.)
-constexpr int CT_DEEP_ROWS = 2048;    // contigs per sample that may exceed the shared histogram's depth range
+constexpr int CT_DEEP_ROWS = 2048;    // fewest rows of the pool = contigs per sample that may leave the shared histogram's depth
+                                      // range; the pool grows with the number of contigs of the call (deep_pool_rows)
 constexpr int CT_DEEP_BINS = 4096;    // depths COV_BINS-1 .. COV_BINS-2+4096 are counted in the deep pool
 
 struct TileArgs {
@@ -816,6 +817,7 @@ struct TileArgs {
     int32_t *deep_row_of;       // [n] -1 = none; row of the deep pool claimed by the contig
     uint32_t *deep_pool;        // [CT_DEEP_ROWS][CT_DEEP_BINS] counts of depths >= COV_BINS - 1
     int *deep_rows_used;
+    int deep_rows;              // rows of deep_pool
     const unsigned int *check;  // NULL, or check[0] != 0 => the precondition failed: do nothing
     uint32_t span_host;         // max_span the bounds were computed with (vouched by the caller) ...
     const unsigned int *span_dev;  // ... or measured on the device (then span_host is ignored)
@@ -870,7 +872,7 @@ __device__ __forceinline__ void ct_deep_positions(const TileArgs &a, int64_t c, 
             const int old = atomicCAS(&a.deep_row_of[c], -1, -2);
             if (old == -1) {
                 const int k2 = atomicAdd(a.deep_rows_used, 1);
-                r = k2 < CT_DEEP_ROWS ? k2 : -3;
+                r = k2 < a.deep_rows ? k2 : -3;
                 atomicExch(&a.deep_row_of[c], r);
             } else {
                 r = old;
@@ -1687,7 +1689,7 @@ __device__ __forceinline__ int c4_claim_row(const TileArgs &a, int64_t c) {
         const int old = atomicCAS(&a.deep_row_of[c], -1, -2);
         if (old == -1) {
             const int k2 = atomicAdd(a.deep_rows_used, 1);
-            r = k2 < CT_DEEP_ROWS ? k2 : -3;
+            r = k2 < a.deep_rows ? k2 : -3;
             atomicExch(&a.deep_row_of[c], r);
         } else {
             r = old;
@@ -2213,6 +2215,18 @@ static int cov_general_path(const uint32_t *starts, const uint32_t *ends, const 
                             const TrimParams &tp, int *ctrs, const int *gate, float *d_cov, int64_t cov_stride,
                             mp2_cov_stats *d_stats, cudaStream_t stream);
 
+// Rows of the deep pool for a call with n_contigs contigs.  An organism sequenced beyond the shared histogram's
+// range brings ALL its contigs (hundreds) at once, and how many such organisms a sample holds grows with the shard:
+// a C4 shard of 2 500 MAGs (750 k contigs, 4 GPUs) overflowed 2 048 rows in one sample out of ten, which sent those
+// samples down the general path (one rank at 464 ms per step, the best one at 303, against 226 without fallbacks).
+// One row per 64 contigs, in steps of 1024 rows, 2 048 .. 65 536 (16 KB per row, cleared per sample: 84 MB at C3).
+static int deep_pool_rows(int64_t n_contigs) {
+    int64_t r = ((n_contigs / 64 + 1023) / 1024) * 1024;
+    if (r < CT_DEEP_ROWS) r = CT_DEEP_ROWS;
+    if (r > 65536) r = 65536;
+    return (int)r;
+}
+
 // MP2_COV_RUN_ORDER=0: cov_stream2_kernel draws its runs in array order (development / A-B switch)
 static bool cov_run_order_off() {
     static int v = -1;
@@ -2291,11 +2305,12 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
         MP2_TRY(t_meta.alloc(sizeof(RowMeta) * n_units, stream));
         MP2_TRY(t_deep.alloc(sizeof(int32_t) * n_contigs, stream));
         MP2_TRY(t_drow.alloc(sizeof(int32_t) * n_contigs, stream));
-        MP2_TRY(t_dpool.alloc(sizeof(uint32_t) * (size_t)CT_DEEP_ROWS * CT_DEEP_BINS, stream));
+        const int deep_rows = deep_pool_rows(n_contigs);
+        MP2_TRY(t_dpool.alloc(sizeof(uint32_t) * (size_t)deep_rows * CT_DEEP_BINS, stream));
         MP2_CUDA(cudaMemsetAsync(t_rows.p, 0, sizeof(uint32_t) * COV_BINS * (size_t)n_units, stream));
         MP2_CUDA(cudaMemsetAsync(t_meta.p, 0, sizeof(RowMeta) * n_units, stream));
         MP2_CUDA(cudaMemsetAsync(t_drow.p, 0xFF, sizeof(int32_t) * n_contigs, stream));
-        MP2_CUDA(cudaMemsetAsync(t_dpool.p, 0, sizeof(uint32_t) * (size_t)CT_DEEP_ROWS * CT_DEEP_BINS, stream));
+        MP2_CUDA(cudaMemsetAsync(t_dpool.p, 0, sizeof(uint32_t) * (size_t)deep_rows * CT_DEEP_BINS, stream));
         const bool ordered = fast_ver == 4 && !cov_run_order_off();
         if (ordered) {  // [0, 64) runs per weight class, [64, 128) fill counters of the counting sort
             MP2_TRY(t_order.alloc(sizeof(int32_t) * n_units, stream));
@@ -2348,6 +2363,7 @@ extern "C" int mp2_cov_events_device(const void *d_starts, const void *d_ends, c
         t.work_counter = ctrs.as<int>() + 1;
         t.order = ordered ? t_order.as<int32_t>() : nullptr;
         t.deep_row_of = t_drow.as<int32_t>(); t.deep_pool = t_dpool.as<uint32_t>(); t.deep_rows_used = ctrs.as<int>() + 6;
+        t.deep_rows = deep_rows;
         t.check = measure ? flags.as<unsigned int>() : nullptr;  // tile kernel: flag[0] != 0 => not sorted
         t.span_host = max_span;
         t.span_dev = measure ? flags.as<unsigned int>() + 1 : nullptr;

@@ -415,3 +415,25 @@ def test_depth_that_wanders_across_the_histogram_range(covmod, oracle):
             assert np.array_equal(stats[f], wst[f]), (f, stats[f], wst[f])
         assert np.array_equal(cov.view(np.uint32), wcov.view(np.uint32))
         assert not (stats["flags"] & GENERAL).any()
+
+
+@pytest.mark.parametrize("n_shallow", [0, 200000])
+def test_more_deep_contigs_than_the_smallest_pool(covmod, oracle, n_shallow):
+    """2 500 contigs at 700x all need a row of the deep pool.  Alone they overflow its 2 048 rows and the sample comes
+    back from the general path; inside a call with 200 000 more (empty) contigs the pool has grown (one row per 64
+    contigs) and the shared-memory path finishes the sample.  Same numbers either way."""
+    rng = np.random.default_rng(31)
+    n_deep = 2500
+    lengths = np.concatenate([np.full(n_deep, 400, dtype=np.int64), rng.integers(160, 300, n_shallow).astype(np.int64)])
+    per = int(700 * 250 / 150)
+    st = np.sort(rng.integers(0, 250, (n_deep, per)), axis=1).astype(np.uint32).ravel()
+    en = (st + 150).astype(np.uint32)
+    ev_off = np.concatenate([np.arange(n_deep + 1, dtype=np.int64) * per, np.full(n_shallow, n_deep * per, dtype=np.int64)])
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    wcov, wst = oracle.cov_sample(st, en, ev_off, lengths, 75, 0.05, 0.05, threads=8)
+    assert (wst["max_depth"][:n_deep] > 600).all()
+    cov, stats = covmod.cov_from_events(st, en, ev_off, off, 75, 0.05, 0.05, want_stats=True, max_span=150, max_disorder=0)
+    for f in INT_FIELDS:
+        assert np.array_equal(stats[f], wst[f]), f
+    assert np.array_equal(cov.view(np.uint32), wcov.view(np.uint32))
+    assert bool((stats["flags"] & GENERAL).any()) == (n_shallow == 0)
