@@ -437,3 +437,31 @@ def test_more_deep_contigs_than_the_smallest_pool(covmod, oracle, n_shallow):
         assert np.array_equal(stats[f], wst[f]), f
     assert np.array_equal(cov.view(np.uint32), wcov.view(np.uint32))
     assert bool((stats["flags"] & GENERAL).any()) == (n_shallow == 0)
+
+
+@pytest.mark.parametrize("env", [{"MP2_COV_RUN_ORDER": "0"}, {"MP2_COV_PATH": "general"}, {"MP2_COV_STREAM": "1"}])
+def test_development_switches_keep_parity(env, oracle, tmp_path):
+    """The A/B switches of the coverage path (runs drawn in array order, general path only, round 1's streaming kernel)
+    are read once per process: run each in a child on a sample with a 1 000x organism and compare with the oracle."""
+    import subprocess
+    import sys
+
+    from magpurify2_b200 import synth
+
+    lengths, mag_off, _gc = synth.mag_layout(4, seed=21, mean_bp=7e5, n_contigs=70)
+    st, en, ev_off = synth.make_events(lengths, mag_off, 1, seed=21)
+    deep = np.sort(np.random.default_rng(21).integers(0, lengths[3] - 150, int(1000 * lengths[3] / 150))).astype(np.uint32)
+    st = np.concatenate([st[:ev_off[3]], deep, st[ev_off[4]:]])
+    en = np.concatenate([en[:ev_off[3]], deep + 150, en[ev_off[4]:]]).astype(np.uint32)
+    ev_off = ev_off.copy()
+    ev_off[4:] += len(deep) - (ev_off[4] - ev_off[3])
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    want, _ = oracle.cov_sample(st, en, ev_off, lengths, 75, 0.05, 0.05, threads=8)
+    for name, a in (("st", st), ("en", en), ("ev_off", ev_off), ("off", off)):
+        np.save(tmp_path / f"{name}.npy", a)
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from magpurify2_b200 import _coverage as c; "
+            "d = %r; st, en, eo, off = (np.load(d + '/' + n + '.npy') for n in ('st', 'en', 'ev_off', 'off')); "
+            "np.save(d + '/cov.npy', c.cov_from_events(st, en, eo, off, 75, 0.05, 0.05))"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path)))
+    subprocess.run([sys.executable, "-c", code], check=True, env={**os.environ, **env}, timeout=300)
+    assert np.array_equal(np.load(tmp_path / "cov.npy").view(np.uint32), want.view(np.uint32)), env
