@@ -90,7 +90,8 @@ wmedian_kernel(const float *__restrict__ data, const long long *__restrict__ wei
     // ---- sort (value, weight) ascending: bitonic network over the next power of two ----
     int64_t np2 = 1;
     while (np2 < n) np2 <<= 1;
-    VW *a = np2 <= WM_SMEM_CAP ? reinterpret_cast<VW *>(s_raw) : scratch + (r0 * n_cols + j * n) * 2;
+    const bool in_smem = np2 <= WM_SMEM_CAP;
+    VW *a = in_smem ? reinterpret_cast<VW *>(s_raw) : scratch + (r0 * n_cols + j * n) * 2;
     for (int64_t i = tid; i < np2; i += WM_THREADS) {
         VW e;
         if (i < n) {
@@ -103,17 +104,40 @@ wmedian_kernel(const float *__restrict__ data, const long long *__restrict__ wei
         a[i] = e;
     }
     __syncthreads();
-    for (int64_t k = 2; k <= np2; k <<= 1) {
-        for (int64_t s = k >> 1; s > 0; s >>= 1) {
-            for (int64_t i = tid; i < np2; i += WM_THREADS) {
-                const int64_t p = i ^ s;
-                if (p > i) {
+    if (in_smem) {
+        // One comparator per thread and pass (comparator t of a stage with distance s works on i = t with a zero
+        // inserted at bit log2(s), and i | s), 32-bit indices.  The comparators 32b .. 32b+31 of a stage with s <= 32
+        // touch the elements 64b .. 64b+63 only, and thread t always takes the comparators t, t + WM_THREADS, ...: such
+        // stages follow each other with a warp barrier; only stages with s >= 64 exchange between warps.
+        const int h = (int)(np2 >> 1);
+        int prev_s = 64;
+        for (int k = 2; k <= (int)np2; k <<= 1) {
+            for (int sd = k >> 1; sd > 0; sd >>= 1) {
+                if (sd >= 64 || prev_s >= 64) __syncthreads();
+                else __syncwarp();
+                prev_s = sd;
+                for (int t = tid; t < h; t += WM_THREADS) {
+                    const int i = ((t & ~(sd - 1)) << 1) | (t & (sd - 1)), p = i | sd;
                     const VW x = a[i], y = a[p];
                     const bool up = (i & k) == 0;
                     if (up ? vw_less(y, x) : vw_less(x, y)) { a[i] = y; a[p] = x; }
                 }
             }
-            __syncthreads();
+        }
+        __syncthreads();
+    } else {
+        for (int64_t k = 2; k <= np2; k <<= 1) {
+            for (int64_t s = k >> 1; s > 0; s >>= 1) {
+                for (int64_t i = tid; i < np2; i += WM_THREADS) {
+                    const int64_t p = i ^ s;
+                    if (p > i) {
+                        const VW x = a[i], y = a[p];
+                        const bool up = (i & k) == 0;
+                        if (up ? vw_less(y, x) : vw_less(x, y)) { a[i] = y; a[p] = x; }
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
     // ---- cumulative weights; idx = last position with 2*cs <= total (tools.py:305-306) ----
@@ -224,6 +248,18 @@ __device__ __forceinline__ double ln1p_count(uint32_t c) {
     return c < LOG_LUT - 1 ? __ldg(&g_log_lut[c + 1]) : log((double)c + 1.0);
 }
 
+// The same with the first CLR_SLUT entries of the table in shared memory.  Nearly every count of a 10 kbp contig is
+// below it, and 32 lanes gathering 8-byte entries from an L1-resident table cost one L1 wavefront per 128-byte line
+// they touch (~15 per request): that gather, not HBM, was what clr_mag_kernel waited for.
+#ifndef MP2_CLR_SLUT
+#define MP2_CLR_SLUT 1024
+#endif
+constexpr int CLR_SLUT = MP2_CLR_SLUT;
+__device__ __forceinline__ double ln1p_count_s(uint32_t c, const double *s_ln) {
+    if (CLR_SLUT > 0 && c < (uint32_t)CLR_SLUT - 1) return s_ln[c + 1];
+    return ln1p_count(c);
+}
+
 __global__ void log_lut_kernel() {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < LOG_LUT) g_log_lut[i] = i ? log((double)i) : 0.0;
@@ -259,20 +295,29 @@ static int ensure_log_lut(cudaStream_t stream) { return ensure_device_state(stre
 //      needed here: sum_i len_i rm_i = mean_j A_j, so centroid_j = (A_j - mean_j A_j) / sum_i len_i.
 //   2. row-parallel: a warp per row computes rm_i (lane partial sums + xor butterfly), the CLR row and its
 //      distance to the centroid held in shared memory.
-constexpr int CLRM_THREADS = 1024;
-constexpr int CLRM_SLICES = 7;  // 7 x 136 = 952 column threads
+#ifndef MP2_CLRM_THREADS
+#define MP2_CLRM_THREADS 1024
+#endif
+#ifndef MP2_CLRM_MINB
+#define MP2_CLRM_MINB 1
+#endif
+constexpr int CLRM_THREADS = MP2_CLRM_THREADS;          // sweep: tools/gpu_r2_clr_sweep.sh
+constexpr int CLRM_SLICES = CLRM_THREADS / MP2_NCANON;  // 1024 threads: 7 x 136 = 952 column threads
 
-__global__ void __launch_bounds__(CLRM_THREADS)
+__global__ void __launch_bounds__(CLRM_THREADS, MP2_CLRM_MINB)
 clr_mag_kernel(const uint32_t *__restrict__ counts, const long long *__restrict__ weights,
                const long long *__restrict__ mag_off, float *__restrict__ clr, double *__restrict__ dist) {
     __shared__ double s_part[CLRM_SLICES][MP2_NCANON];
     __shared__ double s_w[CLRM_SLICES];
     __shared__ double s_cen[MP2_NCANON];
     __shared__ double s_mean_a, s_wsum;
+    __shared__ double s_ln[CLR_SLUT > 0 ? CLR_SLUT : 1];
     const int64_t m = blockIdx.x;
     const int64_t r0 = mag_off[m], r1 = mag_off[m + 1];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     constexpr int64_t S = CLRM_SLICES;
+    for (int i = t; i < CLR_SLUT; i += CLRM_THREADS) s_ln[i] = g_log_lut[i];
+    __syncthreads();
     if (t < CLRM_SLICES * MP2_NCANON) {
         const int j = t % MP2_NCANON, g = t / MP2_NCANON;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, ws = 0.0;
@@ -282,15 +327,15 @@ clr_mag_kernel(const uint32_t *__restrict__ counts, const long long *__restrict_
             const uint32_t c2 = counts[(r + 2 * S) * MP2_NCANON + j], c3 = counts[(r + 3 * S) * MP2_NCANON + j];
             const double w0 = (double)weights[r], w1 = (double)weights[r + S];
             const double w2 = (double)weights[r + 2 * S], w3 = (double)weights[r + 3 * S];
-            a0 += w0 * ln1p_count(c0);
-            a1 += w1 * ln1p_count(c1);
-            a2 += w2 * ln1p_count(c2);
-            a3 += w3 * ln1p_count(c3);
+            a0 += w0 * ln1p_count_s(c0, s_ln);
+            a1 += w1 * ln1p_count_s(c1, s_ln);
+            a2 += w2 * ln1p_count_s(c2, s_ln);
+            a3 += w3 * ln1p_count_s(c3, s_ln);
             ws += (w0 + w1) + (w2 + w3);  // integers below 2^53: exact in any order
         }
         for (; r < r1; r += S) {
             const double w0 = (double)weights[r];
-            a0 += w0 * ln1p_count(counts[r * MP2_NCANON + j]);
+            a0 += w0 * ln1p_count_s(counts[r * MP2_NCANON + j], s_ln);
             ws += w0;
         }
         s_part[g][j] = (a0 + a1) + (a2 + a3);
@@ -323,7 +368,7 @@ clr_mag_kernel(const uint32_t *__restrict__ counts, const long long *__restrict_
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             const int j = lane + 32 * k;
-            v[k] = j < MP2_NCANON ? ln1p_count(counts[r * MP2_NCANON + j]) : 0.0;
+            v[k] = j < MP2_NCANON ? ln1p_count_s(counts[r * MP2_NCANON + j], s_ln) : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < 5; k++) s += v[k];
