@@ -36,6 +36,72 @@ __device__ __forceinline__ bool vw_less(const VW &a, const VW &b) {  // tuple or
     return a.key < b.key || (a.key == b.key && a.w < b.w);
 }
 
+// (value, weight) pairs of column j of the MAG's rows into a[0, n), padding that sorts last into a[n, np2)
+__device__ __forceinline__ void wm_load(VW *a, const float *__restrict__ data, const long long *__restrict__ weights,
+                                        int64_t r0, int64_t n, int64_t np2, int64_t n_cols, int64_t j, int tid) {
+    for (int64_t i = tid; i < np2; i += WM_THREADS) {
+        VW e;
+        if (i < n) {
+            e.v = data[(r0 + i) * n_cols + j];
+            e.key = f32_key(e.v);
+            e.w = weights[r0 + i];
+        } else {
+            e.v = 0.f; e.key = 0xFFFFFFFFu; e.w = LLONG_MAX;
+        }
+        a[i] = e;
+    }
+}
+
+// Cumulative weights over the sorted pairs; idx = last position with 2 * cs <= total (tools.py:305-306); an exact
+// tie there gives the mean of the two straddling values (:307-308), anything else the next value (:310).  The
+// position and whether it is a tie travel together as 2 * idx + tie through a maximum over the CTA: the largest
+// qualifying position is the one whose tie bit counts.
+__device__ __forceinline__ void wm_pick(const VW *a, int64_t n, long long total, long long *s_scan, long long *s_idx,
+                                        float *out, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    long long carry = 0, best = -1;  // best = largest 2 * i + tie this thread has seen
+    for (int64_t b = 0; b < n; b += WM_THREADS) {
+        const int64_t i = b + tid;
+        const long long w = i < n ? a[i].w : 0;
+        long long incl = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        long long wpre = 0, blk = 0;
+        for (int w2 = 0; w2 < WM_THREADS / 32; w2++) {
+            if (w2 < warp) wpre += s_scan[w2];
+            blk += s_scan[w2];
+        }
+        const long long cs = carry + wpre + incl;
+        if (i < n && 2 * cs <= total) best = 2 * i + (2 * cs == total ? 1 : 0);  // i grows with b
+        carry += blk;
+        __syncthreads();
+    }
+    // one value per warp, then thread 0 (a 64-bit atomicMax of every thread on one shared word is a CAS loop: it was
+    // most of this kernel's time)
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long t = __shfl_xor_sync(0xffffffffu, best, o);
+        best = t > best ? t : best;
+    }
+    if (lane == 0) s_scan[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+        long long packed = *s_idx;  // -1
+        for (int w2 = 0; w2 < WM_THREADS / 32; w2++) packed = s_scan[w2] > packed ? s_scan[w2] : packed;
+        float med;
+        if (packed < 0) med = a[0].v;  // unreachable for non-negative weights (first weight <= midpoint here)
+        else {
+            const long long idx = packed >> 1;
+            if (packed & 1) med = idx + 1 < n ? __fdiv_rn(__fadd_rn(a[idx].v, a[idx + 1].v), 2.0f) : a[idx].v;
+            else med = a[idx + 1 < n ? idx + 1 : idx].v;
+        }
+        *out = med;
+    }
+}
+
 // One CTA per (MAG, column).  medians[m * n_cols + j]; NaN for columns that are masked out or MAGs
 // that are not scored (<= 2 rows).
 __global__ void __launch_bounds__(WM_THREADS)
@@ -90,21 +156,12 @@ wmedian_kernel(const float *__restrict__ data, const long long *__restrict__ wei
     // ---- sort (value, weight) ascending: bitonic network over the next power of two ----
     int64_t np2 = 1;
     while (np2 < n) np2 <<= 1;
-    const bool in_smem = np2 <= WM_SMEM_CAP;
-    VW *a = in_smem ? reinterpret_cast<VW *>(s_raw) : scratch + (r0 * n_cols + j * n) * 2;
-    for (int64_t i = tid; i < np2; i += WM_THREADS) {
-        VW e;
-        if (i < n) {
-            e.v = data[(r0 + i) * n_cols + j];
-            e.key = f32_key(e.v);
-            e.w = weights[r0 + i];
-        } else {
-            e.v = 0.f; e.key = 0xFFFFFFFFu; e.w = LLONG_MAX;  // padding sorts after everything
-        }
-        a[i] = e;
-    }
-    __syncthreads();
-    if (in_smem) {
+    if (np2 <= WM_SMEM_CAP) {
+        // the shared-memory pointer stays a shared-memory pointer (one pointer for both homes made every access of
+        // the sort a generic LD / ST: 31 % of the kernel's stalls)
+        VW *a = reinterpret_cast<VW *>(s_raw);
+        wm_load(a, data, weights, r0, n, np2, n_cols, j, tid);
+        __syncthreads();
         // One comparator per thread and pass (comparator t of a stage with distance s works on i = t with a zero
         // inserted at bit log2(s), and i | s), 32-bit indices.  The comparators 32b .. 32b+31 of a stage with s <= 32
         // touch the elements 64b .. 64b+63 only, and thread t always takes the comparators t, t + WM_THREADS, ...: such
@@ -125,7 +182,11 @@ wmedian_kernel(const float *__restrict__ data, const long long *__restrict__ wei
             }
         }
         __syncthreads();
+        wm_pick(a, n, total, s_scan, &s_idx, out, tid);
     } else {
+        VW *a = scratch + (r0 * n_cols + j * n) * 2;
+        wm_load(a, data, weights, r0, n, np2, n_cols, j, tid);
+        __syncthreads();
         for (int64_t k = 2; k <= np2; k <<= 1) {
             for (int64_t s = k >> 1; s > 0; s >>= 1) {
                 for (int64_t i = tid; i < np2; i += WM_THREADS) {
@@ -139,41 +200,7 @@ wmedian_kernel(const float *__restrict__ data, const long long *__restrict__ wei
                 __syncthreads();
             }
         }
-    }
-    // ---- cumulative weights; idx = last position with 2*cs <= total (tools.py:305-306) ----
-    long long carry = 0;
-    for (int64_t b = 0; b < n; b += WM_THREADS) {
-        const int64_t i = b + tid;
-        const long long w = i < n ? a[i].w : 0;
-        long long incl = w;
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) s_scan[warp] = incl;
-        __syncthreads();
-        long long wpre = 0, blk = 0;
-        for (int w2 = 0; w2 < WM_THREADS / 32; w2++) {
-            if (w2 < warp) wpre += s_scan[w2];
-            blk += s_scan[w2];
-        }
-        const long long cs = carry + wpre + incl;
-        if (i < n && 2 * cs <= total) atomicMax(&s_idx, (long long)i);
-        carry += blk;
-        __syncthreads();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const long long idx = s_idx;
-        float med;
-        if (idx < 0) med = a[0].v;  // unreachable for non-negative weights (first weight <= midpoint here)
-        else {
-            long long cs = 0;  // recompute cs[idx] exactly (sequential; n is small)
-            for (long long i = 0; i <= idx; i++) cs += a[i].w;
-            if (2 * cs == total) med = idx + 1 < n ? __fdiv_rn(__fadd_rn(a[idx].v, a[idx + 1].v), 2.0f) : a[idx].v;
-            else med = a[idx + 1 < n ? idx + 1 : idx].v;
-        }
-        *out = med;
+        wm_pick(a, n, total, s_scan, &s_idx, out, tid);
     }
 }
 
