@@ -17,7 +17,7 @@ namespace mp2 {
 
 int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n, int64_t n_bases,
                      int64_t chunk_begin, int64_t chunk_end, uint32_t *d_counts,
-                     unsigned long long *d_gc_counts, cudaStream_t stream);
+                     unsigned long long *d_gc_counts, cudaStream_t stream, bool zero_rows);
 int64_t tnf_num_chunks(const void *d_bases, int64_t n_bases);
 int64_t tnf_chunks_ready(const void *d_bases, int64_t done, int64_t n_bases);
 int tnf_valid_from_runs(const int64_t *d_runs, int64_t n_runs, int64_t n_bases, uint32_t *d_valid, cudaStream_t stream);
@@ -203,7 +203,7 @@ extern "C" int mp2_tnf(const uint8_t *bases, const int64_t *offsets, int64_t n, 
             MP2_CUDA(cudaStreamWaitEvent(st.comp, st.ev, 0));
             MP2_TRY(tnf_launch_range(d_bases.as<uint8_t>(), d_off.as<int64_t>(), n, total,
                                      next_chunk, upto, d_counts.as<uint32_t>(),
-                                     d_gcc.as<unsigned long long>(), st.comp));
+                                     d_gcc.as<unsigned long long>(), st.comp, false));
             next_chunk = upto;
         }
         return MP2_OK;

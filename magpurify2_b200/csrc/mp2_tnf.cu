@@ -146,12 +146,14 @@ __global__ void tnf_chunk_map_kernel(const int64_t *__restrict__ offsets, int64_
 
 // Fold the warp's table into the contig's row: 256 codes -> 136 canonical classes, integer global
 // reductions, then zero the table.  MODE 4: T4 is the 4-mer table already.
-__device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__restrict__ row, uint32_t &phase);
+__device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__restrict__ row, uint32_t &phase, bool whole);
 
 template <int MODE>
-__device__ __forceinline__ void tnf_flush(uint32_t *tab, int lane, uint32_t *__restrict__ row, uint32_t &phase) {
+// `whole` (warp-uniform): the segment is the WHOLE contig, nobody else adds to its row: the 136 counts are stored
+// (zeros too) and the row need not have been cleared.
+__device__ __forceinline__ void tnf_flush(uint32_t *tab, int lane, uint32_t *__restrict__ row, uint32_t &phase, bool whole) {
     if (MODE == 5) {
-        tnf_flush5(tab, lane, row, phase);
+        tnf_flush5(tab, lane, row, phase, whole);
         return;
     }
     __syncwarp();
@@ -162,7 +164,8 @@ __device__ __forceinline__ void tnf_flush(uint32_t *tab, int lane, uint32_t *__r
             const uint32_t a = pr & 0xFFu, rc = pr >> 8;
             uint32_t val = tab[a];
             if (rc != a) val += tab[rc];
-            if (val) atomicAdd(&row[k], val);
+            if (whole) row[k] = val;
+            else if (val) atomicAdd(&row[k], val);
         }
     }
     __syncwarp();
@@ -193,7 +196,7 @@ __device__ __forceinline__ void tnf_bar_init(int lane) {
 #endif
 }
 
-__device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__restrict__ row, uint32_t &phase) {
+__device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__restrict__ row, uint32_t &phase, bool whole) {
     const uint4 *t5v = reinterpret_cast<const uint4 *>(tab);
     uint4 *t4v = reinterpret_cast<uint4 *>(tab + 1024);
     // T5 is read ONCE: the uint4 at word b*256 + 8L + 4h holds T5[b . c] for the four codes c = 8L + 4h + 0..3 (added
@@ -251,7 +254,8 @@ __device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__
             const uint32_t a = pr & 0xFFu, rc = pr >> 8;
             uint32_t val = tab[1024 + a];
             if (rc != a) val += tab[1024 + rc];
-            if (val) atomicAdd(&row[k], val);
+            if (whole) row[k] = val;
+            else if (val) atomicAdd(&row[k], val);
         }
     }
     __syncwarp();
@@ -547,8 +551,12 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                 }
             }
             gcl = __reduce_add_sync(0xffffffffu, gcl);
-            if (lane == 0 && gcl) atomicAdd(&gc_counts[c], (unsigned long long)gcl);
-            tnf_flush<MODE>(tab, lane, counts + c * MP2_NCANON, zero_phase);
+            const bool whole = o0_64 >= piece_lo && o1_64 <= piece_hi;  // the whole contig is this segment
+            if (lane == 0) {
+                if (whole) gc_counts[c] = (unsigned long long)gcl;
+                else if (gcl) atomicAdd(&gc_counts[c], (unsigned long long)gcl);
+            }
+            tnf_flush<MODE>(tab, lane, counts + c * MP2_NCANON, zero_phase, whole);
         }
     }
 }
@@ -648,7 +656,7 @@ tnf_packed_kernel(const uint32_t *__restrict__ codes, const uint32_t *__restrict
             }
             gcl = __reduce_add_sync(0xffffffffu, gcl);
             if (lane == 0 && gcl) atomicAdd(&gc_counts[c], (unsigned long long)gcl);
-            tnf_flush<MODE>(tab, lane, counts + c * MP2_NCANON, zero_phase);
+            tnf_flush<MODE>(tab, lane, counts + c * MP2_NCANON, zero_phase, false);
         }
     }
 }
@@ -751,6 +759,16 @@ static int tnf_mode() {
     return mode;
 }
 
+// MP2_TNF_ZERO_ROWS=0: mp2_tnf_device clears all rows with a memset instead of the few that need it (A-B switch).
+static bool tnf_zero_rows() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MP2_TNF_ZERO_ROWS");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // MP2_TNF_SNAP=0 keeps the nominal piece boundaries (development / A-B switch).
 static int tnf_snap() {
     static int snap = -1;
@@ -763,11 +781,38 @@ static int tnf_snap() {
 
 int64_t tnf_num_chunks(const void *d_bases, int64_t n_bases);
 
+// Rows the counting kernel does not store whole: contigs that a piece boundary cuts (their segments add into the row)
+// and empty contigs (no segment at all).  Every other row is written by the one flush of its contig, so a launch over
+// the whole stream clears these few rows instead of all of them (163 MB and 50 us of a 1.4 ms step at C3).
+// One warp per boundary k = 1 .. n_chunks - 1 (adj / first_contig as tnf_chunk_map_kernel left them, chunk_begin = 0).
+__global__ void tnf_zero_split_rows_kernel(const int64_t *__restrict__ offsets, int mis, int piece_shift, int64_t n_chunks,
+                                           const int32_t *__restrict__ first_contig, const int32_t *__restrict__ adj,
+                                           uint32_t *__restrict__ counts, unsigned long long *__restrict__ gc_counts) {
+    const int64_t k = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) + 1;
+    const int lane = threadIdx.x & 31;
+    if (k >= n_chunks) return;
+    const int64_t pos = (k << piece_shift) - mis + adj[k];  // stream position of the boundary
+    const int64_t c = first_contig[k];                      // largest c with offsets[c] <= pos
+    if (offsets[c] < pos && pos < offsets[c + 1]) {
+        for (int j = lane; j < MP2_NCANON; j += 32) counts[c * MP2_NCANON + j] = 0;
+        if (lane == 0) gc_counts[c] = 0;
+    }
+}
+
+__global__ void tnf_zero_empty_rows_kernel(const int64_t *__restrict__ offsets, int64_t n, uint32_t *__restrict__ counts,
+                                           unsigned long long *__restrict__ gc_counts) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n || offsets[c + 1] > offsets[c]) return;
+    for (int j = 0; j < MP2_NCANON; j++) counts[c * MP2_NCANON + j] = 0;
+    gc_counts[c] = 0;
+}
+
 // Enqueue the counting kernels for chunks [chunk_begin, chunk_end) of the stream.
-// d_counts / d_gc_counts must have been zeroed (once) before the first range.
+// d_counts / d_gc_counts must have been zeroed (once) before the first range -- or, for ONE launch over the whole
+// stream, `zero_rows` = true clears just the rows that need it (see above).
 int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n, int64_t n_bases,
                      int64_t chunk_begin, int64_t chunk_end, uint32_t *d_counts,
-                     unsigned long long *d_gc_counts, cudaStream_t stream) {
+                     unsigned long long *d_gc_counts, cudaStream_t stream, bool zero_rows) {
     MP2_TRY(upload_tables());
     const int mis = (int)(reinterpret_cast<uintptr_t>(d_bases) & 15);
     const int64_t n_chunks = chunk_end - chunk_begin;
@@ -783,6 +828,15 @@ int tnf_launch_range(const uint8_t *d_bases, const int64_t *d_offsets, int64_t n
         Launch L("tnf_chunk_map_kernel", stream);
         tnf_chunk_map_kernel<<<(unsigned)((n_chunks + 1 + 255) / 256), 256, 0, stream>>>(
             d_offsets, n, mis, ps, tnf_snap(), chunk_begin, n_chunks, map.as<int32_t>(), adj.as<int32_t>());
+    }
+    MP2_CUDA(cudaGetLastError());
+    if (zero_rows) {
+        if (chunk_begin != 0 || chunk_end != total_pieces) return fail(MP2_EINVAL, "zero_rows needs a launch over the whole stream");
+        Launch L("tnf_zero_rows_kernel", stream);
+        if (n_chunks > 1)
+            tnf_zero_split_rows_kernel<<<(unsigned)(((n_chunks - 1) * 32 + 255) / 256), 256, 0, stream>>>(
+                d_offsets, mis, ps, n_chunks, map.as<int32_t>(), adj.as<int32_t>(), d_counts, d_gc_counts);
+        tnf_zero_empty_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_offsets, n, d_counts, d_gc_counts);
     }
     MP2_CUDA(cudaGetLastError());
     const int mode = tnf_mode();
@@ -863,11 +917,13 @@ extern "C" int mp2_tnf_device(const void *d_bases, const void *d_offsets, int64_
     if (n == 0) return MP2_OK;
     Temp gcc;
     MP2_TRY(gcc.alloc(sizeof(unsigned long long) * n, stream));
-    MP2_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * MP2_NCANON * n, stream));
-    MP2_CUDA(cudaMemsetAsync(gcc.p, 0, sizeof(unsigned long long) * n, stream));
+    if (n_bases == 0 || !tnf_zero_rows()) {  // (no piece, no flush: every row is empty)
+        MP2_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * MP2_NCANON * n, stream));
+        MP2_CUDA(cudaMemsetAsync(gcc.p, 0, sizeof(unsigned long long) * n, stream));
+    }
     MP2_TRY(tnf_launch_range((const uint8_t *)d_bases, (const int64_t *)d_offsets, n, n_bases, 0,
                              tnf_num_chunks(d_bases, n_bases), (uint32_t *)d_counts,
-                             gcc.as<unsigned long long>(), stream));
+                             gcc.as<unsigned long long>(), stream, tnf_zero_rows()));
     MP2_TRY(tnf_finalize((const uint32_t *)d_counts, gcc.as<unsigned long long>(),
                          (const int64_t *)d_offsets, n, (float *)d_rel, (float *)d_gc, stream));
     return MP2_OK;

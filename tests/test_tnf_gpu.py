@@ -147,6 +147,36 @@ def test_device_pointer_entry(comp, oracle):
         assert _same_f32(gc.cpu().numpy(), want_gc)
 
 
+def test_device_entry_defines_every_row(comp, oracle):
+    """mp2_tnf_device does not clear the count rows wholesale: contigs that lie inside one piece are STORED by their
+    one flush, only rows of contigs cut by a piece boundary and of empty contigs are cleared first.  Output buffers
+    full of garbage, contigs of every kind (empty ones in runs, at the very start and end, shorter than a k-mer, longer
+    than several pieces, ending exactly on piece boundaries), twice into the same buffers."""
+    import torch
+
+    from magpurify2_b200 import _lib
+
+    rng = np.random.default_rng(41)
+    alphabet = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    lens = ([0, 0, 3, 16384, 0, 16384 - 3, 1, 0, 0, 70000, 2, 16384 * 3, 5, 0, 40000, 0] +
+            rng.integers(0, 6000, 400).tolist() + [0, 200000, 0, 0, 7, 32768, 0])
+    bases = rng.choice(alphabet, int(sum(lens)), p=[.24, .24, .24, .24, .01, .01, .005, .005, .01])
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    n = len(lens)
+    want = oracle.get_tnf_concat(bases, offsets, relative=False, threads=4)
+    want_gc = oracle.get_gc_concat(bases, offsets)
+    lib = _lib.load()
+    d_b, d_o = torch.from_numpy(bases).cuda(), torch.from_numpy(offsets).cuda()
+    counts = torch.full((n, 136), -559038737, dtype=torch.int32, device="cuda")
+    gc = torch.full((n,), 123.0, dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        _lib.check(lib.mp2_tnf_device(d_b.data_ptr(), d_o.data_ptr(), n, len(bases), counts.data_ptr(), None,
+                                      gc.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert np.array_equal(counts.cpu().numpy().view(np.uint32), want)
+        assert _same_f32(gc.cpu().numpy(), want_gc)
+
+
 @pytest.mark.parametrize("env", [{"MP2_TNF_MODE": "4"}, {"MP2_TNF_PIECE_SHIFT": "15"}, {"MP2_TNF_SNAP": "0"},
                                  {"MP2_TNF_PIECE_SHIFT": "15", "MP2_TNF_SNAP": "0"}])
 def test_development_switches_keep_parity(env, oracle, tmp_path):
