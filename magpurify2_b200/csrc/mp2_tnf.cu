@@ -59,6 +59,17 @@ __device__ __align__(128) uint32_t g_zero_page[1024];
 
 __constant__ uint8_t c_lut256[256];             // code -> canonical class
 __constant__ uint16_t c_canon_pair[MP2_NCANON];  // class -> smallest code | revcomp code << 8
+// MODE 5 flush: the 4-mer count of code c waits for the class gather at word tnf_swz(c) of the T4 region, not at word c.
+// Read at word c, the 32 classes of one gather instruction cost 11 (smallest codes) + 24 (their reverse complements,
+// which differ in the TOP bits and so share banks) wavefronts per flush; with this XOR swizzle -- linear over GF(2) in
+// c >> 2, so that the four codes of a uint4 stay one uint4, found by search -- 17, and the two STS.128 of the sums
+// stay conflict-free.  c_canon_pair5 holds the swizzled words.
+__host__ __device__ constexpr uint32_t tnf_swz_g(uint32_t v) {  // v = c >> 2 (6 bits) -> 8-bit XOR mask
+    return ((v & 1u) ? 111u : 0u) ^ ((v & 2u) ? 79u : 0u) ^ ((v & 4u) ? 199u : 0u) ^ ((v & 8u) ? 226u : 0u) ^
+           ((v & 16u) ? 31u : 0u) ^ ((v & 32u) ? 177u : 0u);
+}
+__host__ __device__ constexpr uint32_t tnf_swz(uint32_t c) { return c ^ tnf_swz_g(c >> 2); }
+__constant__ uint16_t c_canon_pair5[MP2_NCANON];
 
 static int upload_tables() {
     static std::mutex mu;  // callers may be threads driving different GPUs
@@ -76,6 +87,9 @@ static int upload_tables() {
         pair[k] = (uint16_t)(a | (rc << 8));
     }
     MP2_CUDA(cudaMemcpyToSymbol(c_canon_pair, pair, sizeof pair));
+    uint16_t pair5[MP2_NCANON];
+    for (int k = 0; k < MP2_NCANON; k++) pair5[k] = (uint16_t)(tnf_swz(pair[k] & 0xFFu) | (tnf_swz(pair[k] >> 8) << 8));
+    MP2_CUDA(cudaMemcpyToSymbol(c_canon_pair5, pair5, sizeof pair5));
     if (dev < 64) done[dev] = true;
     return MP2_OK;
 }
@@ -229,7 +243,17 @@ __device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__
         const int h = hp ^ hx;
         const uint4 p = t4v[2 * lane + h];
         sum[hp].x += p.x; sum[hp].y += p.y; sum[hp].z += p.z; sum[hp].w += p.w;
-        t4v[2 * lane + h] = sum[hp];  // only this lane touches these words
+    }
+    __syncwarp();  // every lane has read its prefix sums: the region takes the 4-mer counts, swizzled (tnf_swz)
+    const uint32_t g_lane = tnf_swz_g(2u * (uint32_t)lane);
+#pragma unroll
+    for (int hp = 0; hp < 2; hp++) {
+        const int h = hp ^ hx;
+        const uint32_t g = g_lane ^ (h ? tnf_swz_g(1u) : 0u);  // linear: g(2L + h) = g(2L) ^ g(h)
+        uint4 o = sum[hp];                                      // element e goes to position e ^ (g & 3)
+        if (g & 1u) { uint32_t t = o.x; o.x = o.y; o.y = t; t = o.z; o.z = o.w; o.w = t; }
+        if (g & 2u) { uint32_t t = o.x; o.x = o.z; o.z = t; t = o.y; o.y = o.w; o.w = t; }
+        t4v[(2u * (uint32_t)lane + (uint32_t)h) ^ (g >> 2)] = o;
     }
     __syncwarp();  // every lane is done reading T5; the 4-mer counts are visible in T4
 #if MP2_TNF_TMAZERO
@@ -250,7 +274,7 @@ __device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__
 #pragma unroll
     for (int k = lane; k < MP2_NCANON + 24; k += 32) {
         if (k < MP2_NCANON) {
-            const uint32_t pr = c_canon_pair[k];
+            const uint32_t pr = c_canon_pair5[k];  // words of the two codes (equal for a palindrome)
             const uint32_t a = pr & 0xFFu, rc = pr >> 8;
             uint32_t val = tab[1024 + a];
             if (rc != a) val += tab[1024 + rc];
