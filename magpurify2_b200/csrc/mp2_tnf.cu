@@ -39,6 +39,7 @@ static int tnf_piece_shift(int64_t n_bases) {
 #define MP2_TNF_UNROLL 4
 #endif
 constexpr int TNF_UNROLL = MP2_TNF_UNROLL;  // 16-byte groups in flight per lane
+static_assert(TNF_UNROLL >= 1 && TNF_UNROLL <= 4, "the halos of a tile travel in one 32-bit shuffle, 7 bits each");
 
 // Table words per warp: MODE 4 counts one 4-mer per base into T4[256]; MODE 5 counts one 5-mer
 // per TWO bases into T5[1024] (a 5-mer b0..b4 stands for the 4-mers b0..b3 and b1..b4) and
@@ -506,27 +507,62 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
             // So the first row of a segment is an ordinary row, the last one an ordinary row with idle lanes, and the
             // per-base masks are built once per segment instead of once per edge row.
             if (g_in_hi > g_in_lo) {
-                // packed halo (last 3 codes | bit 8 "not usable") of the group before g_in_lo, kept by lane 31;
-                // its bytes lie inside the contig (16 g_in_lo >= o0 + 3) and inside the buffer (g_in_lo >= 1)
-                uint32_t carry = 0x100u;
+                // halo of a group = last 3 codes of the group before it | bit 6 "not usable", 7 bits.  The one before
+                // g_in_lo is kept by lane 31; its bytes lie inside the contig (16 g_in_lo >= o0 + 3) and inside the
+                // buffer (g_in_lo >= 1).
+                uint32_t carry = 0x40u;
                 if (lane == 31) {
                     uint32_t sg;
                     const uint32_t ph = decode4(__ldg(reinterpret_cast<const uint32_t *>(pb + (g_in_lo << 4) - 4)), sg);
-                    carry = (ph & 0x3Fu) | (((sg ^ 0x41414141u) & 0xFFFFFF00u) ? 0x100u : 0u);
+                    carry = (ph & 0x3Fu) | (((sg ^ 0x41414141u) & 0xFFFFFF00u) ? 0x40u : 0u);
                 }
-                for (int g0 = g_in_lo; g0 < g_in_hi; g0 += 32 * TNF_UNROLL) {
-                    uint4 v[TNF_UNROLL];
-                    if (g0 + 32 * TNF_UNROLL <= g_in_hi) {  // warp-uniform: the whole tile is interior
+                int g0 = g_in_lo;
+                // ---- whole tiles: TNF_UNROLL rows decoded together, ONE shuffle for their halos (the shuffle runs on the
+                // pipe that bounds the kernel: 4 % of its wavefronts were per-row shuffles) ----
+                for (; g0 + 32 * TNF_UNROLL <= g_in_hi; g0 += 32 * TNF_UNROLL) {
+                    uint32_t cw[TNF_UNROLL];
+                    uint32_t pk = 0;  // this lane's TNF_UNROLL halos-to-give, 7 bits each
+                    {
+                        uint4 v[TNF_UNROLL];
 #pragma unroll
                         for (int u = 0; u < TNF_UNROLL; u++)
                             v[u] = __ldg(reinterpret_cast<const uint4 *>(pb + ((g0 + 32 * u + lane) << 4)));
-                    } else {
 #pragma unroll
                         for (int u = 0; u < TNF_UNROLL; u++) {
-                            const int g = g0 + 32 * u + lane;
-                            v[u] = make_uint4(0, 0, 0, 0);
-                            if (g < g_in_hi) v[u] = __ldg(reinterpret_cast<const uint4 *>(pb + (g << 4)));
+                            uint32_t s0, s1, s2, s3;
+                            const uint32_t m0 = decode4_hi(v[u].x, s0), m1 = decode4_hi(v[u].y, s1);
+                            const uint32_t m2 = decode4_hi(v[u].z, s2), m3 = decode4_hi(v[u].w, s3);
+                            cw[u] = __byte_perm(__byte_perm(m3, m2, 0x0073), __byte_perm(m1, m0, 0x0073), 0x5410);
+                            const bool clean = (((s0 ^ s1) | (s2 ^ s3) | (s0 ^ s2)) == 0) && (s0 == 0x41414141u);
+                            pk |= ((cw[u] & 0x3Fu) | (clean ? 0u : 0x40u)) << (7 * u);
                         }
+                    }
+                    // lane L takes the halos of its groups from lane L - 1; lane 0's come from lane 31's groups one row
+                    // earlier: the carry and this tile's rows 0 .. TNF_UNROLL - 2
+                    const uint32_t got = __shfl_sync(0xffffffffu, lane == 31 ? (carry | (pk << 7)) : pk, src_lane);
+                    carry = (pk >> (7 * (TNF_UNROLL - 1))) & 0x7Fu;  // only lane 31's copy is ever consumed
+#pragma unroll
+                    for (int u = 0; u < TNF_UNROLL; u++) {
+                        const uint32_t halo = (got >> (7 * u)) & 0x7Fu;
+                        const bool fast = !((pk >> (7 * u)) & 0x40u) && halo < 0x40u;
+                        if (__all_sync(0xffffffffu, fast)) {
+                            gcl += __popc((cw[u] ^ (cw[u] >> 1)) & 0x55555555u);
+                            tnf_count16<MODE>(cw[u], halo, t5, t4);
+                        } else {  // a group with a non-ACGT byte: its bytes are fetched again (L1) for the exact masks
+                            const int g = g0 + 32 * u + lane;
+                            const uint4 vv = __ldg(reinterpret_cast<const uint4 *>(pb + (g << 4)));
+                            gcl += tnf_edge_row<MODE>(vv, cw[u], halo, fast, g, g_in_hi - 1, o0, seg_lo, seg_hi, pb, head_ok);
+                        }
+                    }
+                }
+                // ---- the segment's last, partial tile: row by row ----
+                if (g0 < g_in_hi) {
+                    uint4 v[TNF_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < TNF_UNROLL; u++) {
+                        const int g = g0 + 32 * u + lane;
+                        v[u] = make_uint4(0, 0, 0, 0);
+                        if (g < g_in_hi) v[u] = __ldg(reinterpret_cast<const uint4 *>(pb + (g << 4)));
                     }
 #pragma unroll
                     for (int u = 0; u < TNF_UNROLL; u++) {
@@ -538,11 +574,10 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                         const uint32_t cw = __byte_perm(__byte_perm(m3, m2, 0x0073), __byte_perm(m1, m0, 0x0073), 0x5410);
                         // 16 valid bases (a group beyond the interior was loaded as zeros and is never clean)
                         const bool clean = (((s0 ^ s1) | (s2 ^ s3) | (s0 ^ s2)) == 0) && (s0 == 0x41414141u);
-                        const uint32_t mine = (cw & 0x3Fu) | (clean ? 0u : 0x100u);
-                        const uint32_t give = lane == 31 ? carry : mine;
-                        const uint32_t halo = __shfl_sync(0xffffffffu, give, src_lane);
-                        carry = mine;  // only lane 31's copy is ever consumed
-                        const bool fast = clean && (halo < 0x100u);
+                        const uint32_t mine = (cw & 0x3Fu) | (clean ? 0u : 0x40u);
+                        const uint32_t halo = __shfl_sync(0xffffffffu, lane == 31 ? carry : mine, src_lane);
+                        carry = mine;
+                        const bool fast = clean && (halo < 0x40u);
                         if (__all_sync(0xffffffffu, fast)) {
                             gcl += __popc((cw ^ (cw >> 1)) & 0x55555555u);
                             tnf_count16<MODE>(cw, halo, t5, t4);
@@ -551,7 +586,7 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                                 gcl += __popc((cw ^ (cw >> 1)) & 0x55555555u);
                                 tnf_count16<MODE>(cw, halo, t5, t4);
                             }
-                        } else {  // a group with a non-ACGT byte
+                        } else {
                             gcl += tnf_edge_row<MODE>(v[u], cw, halo, fast, g, g_in_hi - 1, o0, seg_lo, seg_hi, pb, head_ok);
                         }
                     }
