@@ -39,7 +39,7 @@ static int tnf_piece_shift(int64_t n_bases) {
 #define MP2_TNF_UNROLL 4
 #endif
 constexpr int TNF_UNROLL = MP2_TNF_UNROLL;  // 16-byte groups in flight per lane
-static_assert(TNF_UNROLL >= 1 && TNF_UNROLL <= 4, "the halos of a tile travel in one 32-bit shuffle, 7 bits each");
+static_assert(TNF_UNROLL == 4, "the halos of a tile travel in one 32-bit shuffle, 7 bits each (mask 0x08102040 = their bits 6)");
 
 // Table words per warp: MODE 4 counts one 4-mer per base into T4[256]; MODE 5 counts one 5-mer
 // per TWO bases into T5[1024] (a 5-mer b0..b4 stands for the 4-mers b0..b3 and b1..b4) and
@@ -390,11 +390,45 @@ __device__ __noinline__ uint4 tnf_load_tail(const uint8_t *__restrict__ pb, int 
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Row with at least one group that is not clean.  Lanes whose group is clean take the vector path;
-// the others (typically the one or two groups holding a contig end or an N) compute the exact
-// per-base validity of their group, and then the WARP counts each such group together: lane b takes
-// the 4-mer ending at base 15-b, so a masked group costs one shared-memory reduction instead of 16
-// predicated ones.  Called by the whole warp.  Returns the number of G/C bases counted for this lane.
+// Exact per-base masks of ONE group (16 bases at piece-relative position 16 g, signatures s0..s3 of its four words, codes
+// cw): K gets bit (15-j) set when the 4-mer ENDING at base j counts for this segment, ph the codes of the 4 bytes before
+// the group; returns the number of G/C bases of the group that belong to the segment.
+__device__ __forceinline__ uint32_t tnf_group_masks(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t cw, int g,
+                                                    int o0, int seg_lo, int seg_hi, const uint8_t *__restrict__ pb,
+                                                    bool head_ok, uint32_t &K, uint32_t &ph) {
+    const int P = g << 4;
+    uint32_t hw = 0;  // halo bytes straight from memory (positions P-4..P-1)
+    if (P >= 4 || head_ok) hw = __ldg(reinterpret_cast<const uint32_t *>(pb + P - 4));
+    uint32_t sh_;
+    ph = decode4(hw, sh_);
+    // W: bit (18-i) <-> position P-3+i is a valid base of this contig below seg_hi
+    uint32_t W = ~((bad4(sh_) & 7u) << 16 | bad4(s0) << 12 | bad4(s1) << 8 | bad4(s2) << 4 | bad4(s3)) & 0x7FFFFu;
+    if (P < 4 && !head_ok) W &= 0xFFFFu;
+    uint32_t own;
+    tnf_range_masks(P, o0, seg_lo, seg_hi, W, own);
+    return tnf_masked_prep(cw, W, own, K);
+}
+
+// The warp counts every group with K != 0 together: lane b takes the 4-mer ending at base 15-b, so a masked group
+// costs one shared-memory reduction instead of 16 predicated ones.  Called by the whole warp.
+__device__ __forceinline__ void tnf_count_masked(uint32_t cw, uint32_t ph, uint32_t K, uint32_t t4, int lane) {
+    unsigned todo = __ballot_sync(0xffffffffu, K != 0);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t cb = __shfl_sync(0xffffffffu, cw, src), hb = __shfl_sync(0xffffffffu, ph, src);
+        const uint32_t kb = __shfl_sync(0xffffffffu, K, src);
+        if ((kb >> lane) & 1u) {  // K has 16 bits: lanes 16..31 never count
+            const uint32_t t = lane ? __funnelshift_r(cb, hb, 2 * lane - 2) : (cb << 2);
+            smem_inc(t4 + (t & 0x3FCu));
+        }
+    }
+}
+
+// Row with at least one group that is not clean (a non-ACGT byte).  Lanes whose group is clean take the vector path;
+// the others compute the exact per-base validity of their group, and then the warp counts those groups together.
+// Called by the whole warp, out of line so that the streaming loop stays small.  Returns the number of G/C bases
+// counted for this lane.
 template <int MODE>
 __device__ __noinline__ uint32_t tnf_edge_row(uint4 v, uint32_t cw, uint32_t halo, bool fast, int g, int g_last,
                                               int o0, int seg_lo, int seg_hi, const uint8_t *__restrict__ pb,
@@ -410,30 +444,10 @@ __device__ __noinline__ uint32_t tnf_edge_row(uint4 v, uint32_t cw, uint32_t hal
         } else {
             uint32_t s0, s1, s2, s3;
             decode4_hi(v.x, s0); decode4_hi(v.y, s1); decode4_hi(v.z, s2); decode4_hi(v.w, s3);
-            const int P = g << 4;
-            uint32_t hw = 0;  // halo bytes straight from memory (positions P-4..P-1)
-            if (P >= 4 || head_ok) hw = __ldg(reinterpret_cast<const uint32_t *>(pb + P - 4));
-            uint32_t sh_;
-            ph = decode4(hw, sh_);
-            // W: bit (18-i) <-> position P-3+i is a valid base of this contig below seg_hi
-            uint32_t W = ~((bad4(sh_) & 7u) << 16 | bad4(s0) << 12 | bad4(s1) << 8 | bad4(s2) << 4 | bad4(s3)) & 0x7FFFFu;
-            if (P < 4 && !head_ok) W &= 0xFFFFu;
-            uint32_t own;
-            tnf_range_masks(P, o0, seg_lo, seg_hi, W, own);
-            gcn = tnf_masked_prep(cw, W, own, K);
+            gcn = tnf_group_masks(s0, s1, s2, s3, cw, g, o0, seg_lo, seg_hi, pb, head_ok, K, ph);
         }
     }
-    unsigned todo = __ballot_sync(0xffffffffu, K != 0);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t cb = __shfl_sync(0xffffffffu, cw, src), hb = __shfl_sync(0xffffffffu, ph, src);
-        const uint32_t kb = __shfl_sync(0xffffffffu, K, src);
-        if ((kb >> lane) & 1u) {  // K has 16 bits: lanes 16..31 never count
-            const uint32_t t = lane ? __funnelshift_r(cb, hb, 2 * lane - 2) : (cb << 2);
-            smem_inc(t4 + (t & 0x3FCu));
-        }
-    }
+    tnf_count_masked(cw, ph, K, t4, lane);
     return gcn;
 }
 
@@ -541,17 +555,26 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                     // earlier: the carry and this tile's rows 0 .. TNF_UNROLL - 2
                     const uint32_t got = __shfl_sync(0xffffffffu, lane == 31 ? (carry | (pk << 7)) : pk, src_lane);
                     carry = (pk >> (7 * (TNF_UNROLL - 1))) & 0x7Fu;  // only lane 31's copy is ever consumed
+                    // a group is fast when it is clean and so is the one before it: bit 6 of its own and of the received field
+                    if (__all_sync(0xffffffffu, ((pk | got) & 0x08102040u) == 0)) {  // the whole tile: one vote
 #pragma unroll
-                    for (int u = 0; u < TNF_UNROLL; u++) {
-                        const uint32_t halo = (got >> (7 * u)) & 0x7Fu;
-                        const bool fast = !((pk >> (7 * u)) & 0x40u) && halo < 0x40u;
-                        if (__all_sync(0xffffffffu, fast)) {
+                        for (int u = 0; u < TNF_UNROLL; u++) {
                             gcl += __popc((cw[u] ^ (cw[u] >> 1)) & 0x55555555u);
-                            tnf_count16<MODE>(cw[u], halo, t5, t4);
-                        } else {  // a group with a non-ACGT byte: its bytes are fetched again (L1) for the exact masks
-                            const int g = g0 + 32 * u + lane;
-                            const uint4 vv = __ldg(reinterpret_cast<const uint4 *>(pb + (g << 4)));
-                            gcl += tnf_edge_row<MODE>(vv, cw[u], halo, fast, g, g_in_hi - 1, o0, seg_lo, seg_hi, pb, head_ok);
+                            tnf_count16<MODE>(cw[u], (got >> (7 * u)) & 0x3Fu, t5, t4);
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < TNF_UNROLL; u++) {
+                            const uint32_t halo = (got >> (7 * u)) & 0x7Fu;
+                            const bool fast = !((pk >> (7 * u)) & 0x40u) && halo < 0x40u;
+                            if (__all_sync(0xffffffffu, fast)) {
+                                gcl += __popc((cw[u] ^ (cw[u] >> 1)) & 0x55555555u);
+                                tnf_count16<MODE>(cw[u], halo, t5, t4);
+                            } else {  // a group with a non-ACGT byte: its bytes are fetched again (L1) for the exact masks
+                                const int g = g0 + 32 * u + lane;
+                                const uint4 vv = __ldg(reinterpret_cast<const uint4 *>(pb + (g << 4)));
+                                gcl += tnf_edge_row<MODE>(vv, cw[u], halo, fast, g, g_in_hi - 1, o0, seg_lo, seg_hi, pb, head_ok);
+                            }
                         }
                     }
                 }
@@ -606,7 +629,9 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                     const uint32_t m0 = decode4_hi(vv.x, s0), m1 = decode4_hi(vv.y, s1);
                     const uint32_t m2 = decode4_hi(vv.z, s2), m3 = decode4_hi(vv.w, s3);
                     const uint32_t cw = __byte_perm(__byte_perm(m3, m2, 0x0073), __byte_perm(m1, m0, 0x0073), 0x5410);
-                    gcl += tnf_edge_row<MODE>(vv, cw, 0u, false, g, g_last, o0, seg_lo, seg_hi, pb, head_ok);
+                    uint32_t K = 0, ph = 0;
+                    if (g != INT_MAX) gcl += tnf_group_masks(s0, s1, s2, s3, cw, g, o0, seg_lo, seg_hi, pb, head_ok, K, ph);
+                    tnf_count_masked(cw, ph, K, t4, lane);
                 }
             }
             gcl = __reduce_add_sync(0xffffffffu, gcl);
