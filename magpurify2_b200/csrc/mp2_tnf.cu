@@ -4,16 +4,17 @@
 // (/root/reference/src/composition.rs:42-63, 67-74, 94-124, 128-132, 148-161).
 //
 // Layout in HBM: all contigs of a batch concatenated as one byte stream (1 B/base) plus
-// int64 offsets[n+1].  The stream is cut into fixed 16 KiB pieces; a piece owns the k-mers that
-// END inside it, so work per warp is independent of contig length (a 10 Mbp contig is just 640
-// pieces, a piece full of tiny contigs is a loop over segments).  A warp is a CTA: per segment
-// (= piece ∩ contig) it counts into its own shared-memory table and flushes the table into the
-// contig's row with integer global reductions (order independent => bit exact).
+// int64 offsets[n+1].  The stream is cut into pieces of nominally 16 / 32 KiB whose boundaries snap to contig starts;
+// a piece owns the k-mers that END inside it, so work per warp is independent of contig length (a 10 Mbp contig is
+// just 320 pieces, a piece full of tiny contigs is a loop over segments).  A warp is a CTA: per segment
+// (= piece ∩ contig) it counts into its own shared-memory table and flushes the table into the contig's row -- stored
+// when the segment is the whole contig, integer global reductions otherwise (order independent => bit exact).
 //
-// What bounds the kernel is the shared-memory data pipe (1 wavefront/clk/SM): a warp-wide
-// red.shared on 32 random words costs ~3.4 wavefronts (worst bank load), so the design minimises
-// wavefronts: one increment per TWO bases (5-mer table), a flush whose table reads are all
-// conflict-free LDS.128, and an interior row path without divergence (edge rows are out of line).
+// What bounds the kernel is the shared-memory data pipe (1 wavefront/clk/SM): a warp-wide red.shared on 32 random
+// words costs ~3.8 wavefronts (worst bank load), so the design minimises wavefronts: one increment per TWO bases
+// (5-mer table), a flush that reads the table once with conflict-free LDS.128 and gathers the 136 classes from a
+// swizzled home, one shuffle and one vote per tile of four rows, rows that hold interior groups only (the few partial
+// groups of a segment are counted together, out of the streaming loop).
 #include <climits>
 #include <cstdlib>
 #include <mutex>
