@@ -69,7 +69,8 @@ int mp2_tnf(const uint8_t *bases, const int64_t *offsets, int64_t n, int device,
             uint32_t *counts, float *rel, float *gc);
 
 /* Same, inputs and outputs resident on the current device.  d_counts is REQUIRED (it is the
- * accumulation target and is zeroed by the call); d_rel / d_gc may be NULL.
+ * accumulation target; the call defines every row of it whatever it held before: rows of contigs that
+ * lie inside one piece of the stream are stored, the others are cleared first); d_rel / d_gc may be NULL.
  * n_bases = offsets[n] (passed so the call needs no device->host read). */
 int mp2_tnf_device(const void *d_bases, const void *d_offsets, int64_t n, int64_t n_bases,
                    void *d_counts, void *d_rel, void *d_gc, void *stream);
