@@ -601,11 +601,13 @@ def main():
     side_s = torch.cuda.Stream(device=dev)  # the GC score does not depend on the CLR distances: it runs beside them
 
     def step():
-        # counts + relative TNF + GC of every contig
+        # counts + GC of every contig; the relative profiles (get_tnf's output) are normalised on the side stream
         _lib.check(lib.mp2_tnf_device(bases.data_ptr(), d_off.data_ptr(), n, L, d_counts.data_ptr(),
-                                      d_rel.data_ptr(), d_gc.data_ptr(), stream))
-        # per-MAG scores: GC log-ratio -> gc_content_score (side stream), CLR/centroid distance -> tnf_score
+                                      None, d_gc.data_ptr(), stream))
+        # per-MAG scores: relative TNF + GC log-ratio -> gc_content_score (side stream) beside
+        # CLR/centroid distance -> tnf_score (neither needs the other)
         side_s.wait_stream(main_s)
+        _lib.check(lib.mp2_tnf_normalize_device(d_counts.data_ptr(), n, d_rel.data_ptr(), side_s.cuda_stream))
         _lib.check(lib.mp2_logratio_device(d_gc.data_ptr(), d_len.data_ptr(), d_mag_off.data_ptr(), n_mags, n, 1, None,
                                            2.0, 1e-5, 0.0, 1.0, 3, 0, d_scores[1].data_ptr(), None, side_s.cuda_stream))
         _lib.check(lib.mp2_clr_centroid_device(d_counts.data_ptr(), d_len.data_ptr(), d_mag_off.data_ptr(), n_mags, n,
@@ -805,8 +807,8 @@ def main():
             "mags_per_gpu": args.mags, "contigs_per_gpu": n, "bases_per_gpu": L,
             "input": "ASCII, 1 B/base, resident in HBM", "l2": "inputs (GBs) far larger than the 126 MB L2",
             "parallelism": f"mag-shard x{world}",
-            "step": "mp2_tnf_device (counts, relative TNF, GC) + CLR/centroid + 2x weighted-median log-ratio scores (the GC "
-                    "score on a side stream beside the CLR pass)"
+            "step": "mp2_tnf_device (counts, GC) + CLR/centroid + weighted-median log-ratio score on the main stream; "
+                    "mp2_tnf_normalize_device (relative TNF) + the GC log-ratio score on a side stream beside them"
                     + (" + all_gather of the scores" if world > 1 else ""),
         },
         "roofline": {"bound": "hbm", "kernel": "tnf_kernel", "achieved": achieved, "peak": peak,

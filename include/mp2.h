@@ -75,6 +75,11 @@ int mp2_tnf(const uint8_t *bases, const int64_t *offsets, int64_t n, int device,
 int mp2_tnf_device(const void *d_bases, const void *d_offsets, int64_t n, int64_t n_bases,
                    void *d_counts, void *d_rel, void *d_gc, void *stream);
 
+/* Relative profiles from raw counts already on the device: rel[i][j] = (float)counts[i][j] / (float)row sum, NaN -> 0
+ * (src/composition.rs:111-118; what get_tnf(relative=True) adds to get_tnf(relative=False)).  d_rel may alias nothing
+ * of d_counts.  Lets a caller that asked mp2_tnf_device for counts only normalise beside its other work. */
+int mp2_tnf_normalize_device(const void *d_counts, int64_t n, void *d_rel, void *stream);
+
 /* 2-bit packed variant of the same path (north_star layout): codes = 2 bits per base, 16 bases
  * per uint32, FIRST base in the MOST significant bits; valid = 1 bit per base, 32 bases per
  * uint32, first base most significant (0 = N / IUPAC / any non-ACGT byte); gcmask is not needed:

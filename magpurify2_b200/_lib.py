@@ -63,6 +63,7 @@ SIGNATURES = {
     "mp2_launch_count": (_i64, []),
     "mp2_tnf": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "mp2_tnf_device": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "mp2_tnf_normalize_device": (_i32, [_vp, _i64, _vp, _vp]),
     "mp2_tnf_packed_device": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "mp2_pack_device": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "mp2_packed_words": (_i64, [_i64, C.POINTER(_i64)]),

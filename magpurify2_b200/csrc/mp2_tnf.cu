@@ -1014,6 +1014,14 @@ extern "C" int mp2_tnf_device(const void *d_bases, const void *d_offsets, int64_
     return MP2_OK;
 }
 
+extern "C" int mp2_tnf_normalize_device(const void *d_counts, int64_t n, void *d_rel, void *stream_) {
+    using namespace mp2;
+    if (n < 0) return fail(MP2_EINVAL, "negative size");
+    if (!d_counts || !d_rel) return fail(MP2_EINVAL, "NULL argument");
+    MP2_TRY(require_device(-1));
+    return tnf_finalize((const uint32_t *)d_counts, nullptr, nullptr, n, (float *)d_rel, nullptr, (cudaStream_t)stream_);
+}
+
 extern "C" int mp2_pack_device(const void *d_bases, int64_t n_bases, void *d_codes, void *d_valid, void *stream_) {
     using namespace mp2;
     if (n_bases < 0) return fail(MP2_EINVAL, "negative size");

@@ -147,6 +147,30 @@ def test_device_pointer_entry(comp, oracle):
         assert _same_f32(gc.cpu().numpy(), want_gc)
 
 
+def test_normalize_device_equals_relative_output(comp, oracle):
+    """mp2_tnf_normalize_device on the counts of mp2_tnf_device == the relative output of the same call == the oracle
+    (empty and < 4 bp sequences: all-zero rows, NaN -> 0)."""
+    import torch
+
+    from magpurify2_b200 import _lib, synth
+
+    d = synth.make_mags(2, seed=9, mean_bp=3e5, n_contigs=70)
+    n = len(d["offsets"]) - 1
+    want = oracle.get_tnf_concat(d["bases"], d["offsets"], relative=True, threads=4)
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    d_b, d_o = torch.from_numpy(d["bases"]).cuda(), torch.from_numpy(d["offsets"]).cuda()
+    counts = torch.empty((n, 136), dtype=torch.int32, device="cuda")
+    rel_a = torch.empty((n, 136), dtype=torch.float32, device="cuda")
+    rel_b = torch.full((n, 136), 5.0, dtype=torch.float32, device="cuda")
+    _lib.check(lib.mp2_tnf_device(d_b.data_ptr(), d_o.data_ptr(), n, len(d["bases"]), counts.data_ptr(), rel_a.data_ptr(), None, st))
+    _lib.check(lib.mp2_tnf_normalize_device(counts.data_ptr(), n, rel_b.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(rel_a, rel_b)
+    assert _same_f32(rel_b.cpu().numpy(), want)
+    assert lib.mp2_tnf_normalize_device(None, n, rel_b.data_ptr(), st) != 0
+
+
 def test_device_entry_defines_every_row(comp, oracle):
     """mp2_tnf_device does not clear the count rows wholesale: contigs that lie inside one piece are STORED by their
     one flush, only rows of contigs cut by a piece boundary and of empty contigs are cleared first.  Output buffers
