@@ -282,11 +282,6 @@ __device__ __forceinline__ double ln1p_count(uint32_t c) {
 #define MP2_CLR_SLUT 1024
 #endif
 constexpr int CLR_SLUT = MP2_CLR_SLUT;
-__device__ __forceinline__ double ln1p_count_s(uint32_t c, const double *s_ln) {
-    if (CLR_SLUT > 0 && c < (uint32_t)CLR_SLUT - 1) return s_ln[c + 1];
-    return ln1p_count(c);
-}
-
 __global__ void log_lut_kernel() {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < LOG_LUT) g_log_lut[i] = i ? log((double)i) : 0.0;
@@ -316,104 +311,173 @@ static int ensure_log_lut(cudaStream_t stream) { return ensure_device_state(stre
 // clr_ij = ln(c_ij + 1) - rm_i, rm_i = mean_j ln(c_ij + 1); centroid_j = sum_i len_i clr_ij / sum_i len_i;
 // d_i = ||clr_i - centroid||_2.  f64 throughout.
 //
-// One CTA per MAG, two passes over the MAG's count rows (the second one hits L2):
-//   1. column-parallel: A_j = sum_i len_i ln(c_ij + 1) over 7 row slices x 136 columns, four independent
-//      rows in flight per thread (the chain count -> table -> FMA is latency bound).  The row means are not
-//      needed here: sum_i len_i rm_i = mean_j A_j, so centroid_j = (A_j - mean_j A_j) / sum_i len_i.
-//   2. row-parallel: a warp per row computes rm_i (lane partial sums + xor butterfly), the CLR row and its
-//      distance to the centroid held in shared memory.
+// One CTA per MAG, two passes over the MAG's count rows (the second one hits L2), BOTH row-parallel: a warp per row,
+// lane L holds the columns L, L + 32, ... (one coalesced 544-byte row per five loads), two rows in flight.
+//   1. A_j = sum_i len_i ln(c_ij + 1): five running sums per lane, reduced over the CTA's warps through shared memory.
+//      The row means are not needed here: sum_i len_i rm_i = mean_j A_j, so centroid_j = (A_j - mean_j A_j) / sum_i len_i.
+//   2. rm_i (lane partial sums + xor butterfly), the CLR row and its distance to the centroid held in shared memory.
+// ln(c + 1) comes from the shared-memory table; a count beyond it takes the out-of-line path (global table / log()),
+// so that the two loops stay a few dozen instructions per row.  (The first version ran pass 1 column-parallel --
+// 7 x 136 threads, each re-loading and converting the row's length -- and inlined the log() fallback into both loops:
+// 90 M executed warp instructions per C3 step against 25 M now.)
 #ifndef MP2_CLRM_THREADS
 #define MP2_CLRM_THREADS 1024
 #endif
 #ifndef MP2_CLRM_MINB
 #define MP2_CLRM_MINB 1
 #endif
-constexpr int CLRM_THREADS = MP2_CLRM_THREADS;          // sweep: tools/gpu_r2_clr_sweep.sh
-constexpr int CLRM_SLICES = CLRM_THREADS / MP2_NCANON;  // 1024 threads: 7 x 136 = 952 column threads
+constexpr int CLRM_THREADS = MP2_CLRM_THREADS;  // sweep: tools/gpu_r2_clr_sweep.sh
+constexpr int CLRM_WARPS = CLRM_THREADS / 32;
+constexpr int CLRM_K = (MP2_NCANON + 31) / 32;  // columns per lane (5; the last one only on lanes 0..7)
+
+__device__ __noinline__ double ln1p_count_slow(uint32_t c) { return ln1p_count(c); }
+
+// this lane's CLRM_K columns of one row (ln(0 + 1) = 0: the missing columns of the last load add nothing)
+__device__ __forceinline__ void clr_row_load(const uint32_t *__restrict__ row, int lane, uint32_t (&c)[CLRM_K]) {
+#pragma unroll
+    for (int k = 0; k < CLRM_K; k++) {
+        const int j = lane + 32 * k;
+        c[k] = j < MP2_NCANON ? row[j] : 0u;
+    }
+}
+__device__ __forceinline__ void clr_logs(const uint32_t (&c)[CLRM_K], const double *s_ln, double (&v)[CLRM_K]) {
+    // one warp-uniform test per row instead of a branch per count: the OR of the counts bounds their maximum
+    uint32_t orr = 0;
+#pragma unroll
+    for (int k = 0; k < CLRM_K; k++) orr |= c[k];
+    if (CLR_SLUT > 0 && !__any_sync(0xffffffffu, orr >= (uint32_t)CLR_SLUT - 1)) {
+#pragma unroll
+        for (int k = 0; k < CLRM_K; k++) v[k] = s_ln[c[k] + 1];
+    } else {
+#pragma unroll
+        for (int k = 0; k < CLRM_K; k++)
+            v[k] = (CLR_SLUT > 0 && c[k] < (uint32_t)CLR_SLUT - 1) ? s_ln[c[k] + 1] : ln1p_count_slow(c[k]);
+    }
+}
+__device__ __forceinline__ void clr_row_logs(const uint32_t *__restrict__ row, int lane, const double *s_ln, double (&v)[CLRM_K]) {
+    uint32_t c[CLRM_K];
+    clr_row_load(row, lane, c);
+    clr_logs(c, s_ln, v);
+}
 
 __global__ void __launch_bounds__(CLRM_THREADS, MP2_CLRM_MINB)
 clr_mag_kernel(const uint32_t *__restrict__ counts, const long long *__restrict__ weights,
                const long long *__restrict__ mag_off, float *__restrict__ clr, double *__restrict__ dist) {
-    __shared__ double s_part[CLRM_SLICES][MP2_NCANON];
-    __shared__ double s_w[CLRM_SLICES];
+    __shared__ double s_part[CLRM_WARPS][MP2_NCANON];
+    __shared__ double s_w[CLRM_WARPS];
+    __shared__ double s_a[MP2_NCANON];
     __shared__ double s_cen[MP2_NCANON];
     __shared__ double s_mean_a, s_wsum;
     __shared__ double s_ln[CLR_SLUT > 0 ? CLR_SLUT : 1];
     const int64_t m = blockIdx.x;
     const int64_t r0 = mag_off[m], r1 = mag_off[m + 1];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    constexpr int64_t S = CLRM_SLICES;
     for (int i = t; i < CLR_SLUT; i += CLRM_THREADS) s_ln[i] = g_log_lut[i];
     __syncthreads();
-    if (t < CLRM_SLICES * MP2_NCANON) {
-        const int j = t % MP2_NCANON, g = t / MP2_NCANON;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, ws = 0.0;
-        int64_t r = r0 + g;
-        for (; r + 3 * S < r1; r += 4 * S) {
-            const uint32_t c0 = counts[r * MP2_NCANON + j], c1 = counts[(r + S) * MP2_NCANON + j];
-            const uint32_t c2 = counts[(r + 2 * S) * MP2_NCANON + j], c3 = counts[(r + 3 * S) * MP2_NCANON + j];
-            const double w0 = (double)weights[r], w1 = (double)weights[r + S];
-            const double w2 = (double)weights[r + 2 * S], w3 = (double)weights[r + 3 * S];
-            a0 += w0 * ln1p_count_s(c0, s_ln);
-            a1 += w1 * ln1p_count_s(c1, s_ln);
-            a2 += w2 * ln1p_count_s(c2, s_ln);
-            a3 += w3 * ln1p_count_s(c3, s_ln);
-            ws += (w0 + w1) + (w2 + w3);  // integers below 2^53: exact in any order
+    // ---- pass 1: A_j, total length ----
+    {
+        double acc[CLRM_K], ws = 0.0;
+#pragma unroll
+        for (int k = 0; k < CLRM_K; k++) acc[k] = 0.0;
+        int64_t r = r0 + warp;
+        for (; r + 3 * CLRM_WARPS < r1; r += 4 * CLRM_WARPS) {  // four rows in flight: the loop waits for HBM, not for issue slots
+            uint32_t c[4][CLRM_K];
+            double w[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                w[q] = (double)weights[r + q * CLRM_WARPS];
+                clr_row_load(counts + (r + q * CLRM_WARPS) * MP2_NCANON, lane, c[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                double v[CLRM_K];
+                clr_logs(c[q], s_ln, v);
+#pragma unroll
+                for (int k = 0; k < CLRM_K; k++) acc[k] = fma(w[q], v[k], acc[k]);
+                ws += w[q];  // integers below 2^53: exact in any order
+            }
         }
-        for (; r < r1; r += S) {
-            const double w0 = (double)weights[r];
-            a0 += w0 * ln1p_count_s(counts[r * MP2_NCANON + j], s_ln);
-            ws += w0;
+        for (; r < r1; r += CLRM_WARPS) {
+            double va[CLRM_K];
+            const double wa = (double)weights[r];
+            clr_row_logs(counts + r * MP2_NCANON, lane, s_ln, va);
+#pragma unroll
+            for (int k = 0; k < CLRM_K; k++) acc[k] = fma(wa, va[k], acc[k]);
+            ws += wa;
         }
-        s_part[g][j] = (a0 + a1) + (a2 + a3);
-        if (j == 0) s_w[g] = ws;
+#pragma unroll
+        for (int k = 0; k < CLRM_K; k++) {
+            const int j = lane + 32 * k;
+            if (j < MP2_NCANON) s_part[warp][j] = acc[k];
+        }
+        if (lane == 0) s_w[warp] = ws;
     }
     __syncthreads();
     if (t < MP2_NCANON) {
         double a = 0.0;
-        for (int k = 0; k < CLRM_SLICES; k++) a += s_part[k][t];
-        s_part[0][t] = a;  // only thread t reads column t of the other slices
+        for (int w = 0; w < CLRM_WARPS; w++) a += s_part[w][t];
+        s_a[t] = a;
     }
     __syncthreads();
     if (warp == 0) {
         double sa = 0.0;
-        for (int j = lane; j < MP2_NCANON; j += 32) sa += s_part[0][j];
+        for (int j = lane; j < MP2_NCANON; j += 32) sa += s_a[j];
         for (int o = 16; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
         if (lane == 0) {
             double w = 0.0;
-            for (int k = 0; k < CLRM_SLICES; k++) w += s_w[k];
+            for (int k = 0; k < CLRM_WARPS; k++) w += s_w[k];
             s_mean_a = sa / (double)MP2_NCANON;
             s_wsum = w;
         }
     }
     __syncthreads();
-    if (t < MP2_NCANON) s_cen[t] = s_wsum > 0.0 ? (s_part[0][t] - s_mean_a) / s_wsum : 0.0;
+    if (t < MP2_NCANON) s_cen[t] = s_wsum > 0.0 ? (s_a[t] - s_mean_a) / s_wsum : 0.0;
     __syncthreads();
-    for (int64_t r = r0 + warp; r < r1; r += CLRM_THREADS / 32) {
-        double v[5];
-        double s = 0.0;
+    // ---- pass 2: row mean, CLR row, distance to the centroid ----
+    double cen[CLRM_K];
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-            const int j = lane + 32 * k;
-            v[k] = j < MP2_NCANON ? ln1p_count_s(counts[r * MP2_NCANON + j], s_ln) : 0.0;
+    for (int k = 0; k < CLRM_K; k++) cen[k] = lane + 32 * k < MP2_NCANON ? s_cen[lane + 32 * k] : 0.0;
+    // The kernel is bound by the FP64 pipe: four operations per count here (sum, minus centroid, minus row mean, fused
+    // square-add) and one in pass 1.  (Taking the distance from sum_j u_j^2 - 136 rm_i^2 would need three and one
+    // butterfly, but its cancellation turns the exact 0 of a contig that IS the centroid into 1e-6.)
+    auto finish_row = [&](int64_t r, const double (&v)[CLRM_K]) {
+        double s = 0.0, u[CLRM_K];
+#pragma unroll
+        for (int k = 0; k < CLRM_K; k++) {
+            u[k] = v[k] - cen[k];  // missing columns: 0 - 0
+            s += v[k];
         }
-#pragma unroll
-        for (int k = 0; k < 5; k++) s += v[k];
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         const double rm = s / (double)MP2_NCANON;
         double d2 = 0.0;
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
+        for (int k = 0; k < CLRM_K; k++) {
             const int j = lane + 32 * k;
             if (j < MP2_NCANON) {
-                const double x = v[k] - rm;
-                if (clr) clr[r * MP2_NCANON + j] = (float)x;
-                const double d = x - s_cen[j];
-                d2 += d * d;
+                if (clr) clr[r * MP2_NCANON + j] = (float)(v[k] - rm);
+                const double d = u[k] - rm;
+                d2 = fma(d, d, d2);
             }
         }
         for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
         if (lane == 0) dist[r] = sqrt(d2);
+    };
+    int64_t r = r0 + warp;
+    for (; r + 3 * CLRM_WARPS < r1; r += 4 * CLRM_WARPS) {  // four rows in flight (L2 latency)
+        uint32_t c[4][CLRM_K];
+#pragma unroll
+        for (int q = 0; q < 4; q++) clr_row_load(counts + (r + q * CLRM_WARPS) * MP2_NCANON, lane, c[q]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double v[CLRM_K];
+            clr_logs(c[q], s_ln, v);
+            finish_row(r + q * CLRM_WARPS, v);
+        }
+    }
+    for (; r < r1; r += CLRM_WARPS) {
+        double v[CLRM_K];
+        clr_row_logs(counts + r * MP2_NCANON, lane, s_ln, v);
+        finish_row(r, v);
     }
 }
 
