@@ -437,9 +437,10 @@ clr_mag_kernel(const uint32_t *__restrict__ counts, const long long *__restrict_
     double cen[CLRM_K];
 #pragma unroll
     for (int k = 0; k < CLRM_K; k++) cen[k] = lane + 32 * k < MP2_NCANON ? s_cen[lane + 32 * k] : 0.0;
-    // The kernel is bound by the FP64 pipe: four operations per count here (sum, minus centroid, minus row mean, fused
-    // square-add) and one in pass 1.  (Taking the distance from sum_j u_j^2 - 136 rm_i^2 would need three and one
-    // butterfly, but its cancellation turns the exact 0 of a contig that IS the centroid into 1e-6.)
+    // Four FP64 operations per count here (sum, minus centroid, minus row mean, fused square-add) and one in pass 1.
+    // (Taking the distance from sum_j u_j^2 - 136 rm_i^2 needs three and ONE butterfly -- 0.128 instead of 0.140 ms,
+    // the kernel waits on its dependent chains, not on the FP64 pipe (25 % busy) -- but its cancellation turns the exact 0
+    // of a contig that IS the centroid into 1e-6.)
     auto finish_row = [&](int64_t r, const double (&v)[CLRM_K]) {
         double s = 0.0, u[CLRM_K];
 #pragma unroll
