@@ -53,6 +53,17 @@ template <int MODE> struct TnfTab {
 #ifndef MP2_TNF_TMAZERO
 #define MP2_TNF_TMAZERO 1
 #endif
+// -DMP2_TNF_BOUNDS=1: every global load of tnf_kernel and every computed shared-memory / row index is checked and a
+// violation traps (compute-sanitizer is not available on the pool the kernels are developed on; the parity tests are
+// run once per change with this build: tools/gpu_r2_bounds.sh).
+#ifndef MP2_TNF_BOUNDS
+#define MP2_TNF_BOUNDS 0
+#endif
+#if MP2_TNF_BOUNDS
+#define TNF_CHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define TNF_CHECK(cond) do { } while (0)
+#endif
 // MODE 5 flush: the 4 KB 5-mer table is cleared by the bulk-copy engine (cp.async.bulk from a page of zeros in
 // L2) instead of 8 STS.128 per lane: the kernel is bound by the LSU data pipe (1 wavefront per clock), the copy
 // engine writes shared memory without going through it, and the copy runs while the warp folds the 4-mer sums
@@ -255,6 +266,7 @@ __device__ __forceinline__ void tnf_flush5(uint32_t *tab, int lane, uint32_t *__
         uint4 o = sum[hp];                                      // element e goes to position e ^ (g & 3)
         if (g & 1u) { uint32_t t = o.x; o.x = o.y; o.y = t; t = o.z; o.z = o.w; o.w = t; }
         if (g & 2u) { uint32_t t = o.x; o.x = o.z; o.z = t; t = o.y; o.y = o.w; o.w = t; }
+        TNF_CHECK(((2u * (uint32_t)lane + (uint32_t)h) ^ (g >> 2)) < 64u);
         t4v[(2u * (uint32_t)lane + (uint32_t)h) ^ (g >> 2)] = o;
     }
     __syncwarp();  // every lane is done reading T5; the 4-mer counts are visible in T4
@@ -526,6 +538,8 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                 // g_in_lo is kept by lane 31; its bytes lie inside the contig (16 g_in_lo >= o0 + 3) and inside the
                 // buffer (g_in_lo >= 1).
                 uint32_t carry = 0x40u;
+                TNF_CHECK(c >= 0 && c < n && base + ((int64_t)g_in_lo << 4) - 4 >= 0 &&
+                          ((int64_t)g_in_hi << 4) <= room);
                 if (lane == 31) {
                     uint32_t sg;
                     const uint32_t ph = decode4(__ldg(reinterpret_cast<const uint32_t *>(pb + (g_in_lo << 4) - 4)), sg);
@@ -540,8 +554,10 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                     {
                         uint4 v[TNF_UNROLL];
 #pragma unroll
-                        for (int u = 0; u < TNF_UNROLL; u++)
+                        for (int u = 0; u < TNF_UNROLL; u++) {
+                            TNF_CHECK(g0 + 32 * u + lane >= 0 && (((int64_t)(g0 + 32 * u + lane) << 4) + 16) <= room);
                             v[u] = __ldg(reinterpret_cast<const uint4 *>(pb + ((g0 + 32 * u + lane) << 4)));
+                        }
 #pragma unroll
                         for (int u = 0; u < TNF_UNROLL; u++) {
                             uint32_t s0, s1, s2, s3;
@@ -573,6 +589,7 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                                 tnf_count16<MODE>(cw[u], halo, t5, t4);
                             } else {  // a group with a non-ACGT byte: its bytes are fetched again (L1) for the exact masks
                                 const int g = g0 + 32 * u + lane;
+                                TNF_CHECK(g < g_in_hi);
                                 const uint4 vv = __ldg(reinterpret_cast<const uint4 *>(pb + (g << 4)));
                                 gcl += tnf_edge_row<MODE>(vv, cw[u], halo, fast, g, g_in_hi - 1, o0, seg_lo, seg_hi, pb, head_ok);
                             }
@@ -624,6 +641,7 @@ tnf_kernel(const uint8_t *__restrict__ bases_al, int mis, int64_t end_q,
                     uint4 vv = make_uint4(0, 0, 0, 0);
                     if (g != INT_MAX) {
                         const int P = g << 4;
+                        TNF_CHECK(g >= 0 && g <= g_last && P < safe_hi && (int64_t)safe_hi <= room);
                         vv = P + 16 <= safe_hi ? __ldg(reinterpret_cast<const uint4 *>(pb + P)) : tnf_load_tail(pb, P, safe_hi);
                     }
                     uint32_t s0, s1, s2, s3;
